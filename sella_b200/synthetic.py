@@ -1,0 +1,74 @@
+"""Synthetic potential-energy surfaces used as benchmark / test *inputs*
+(SURVEY.md section 8d).  No optimiser arithmetic lives here.
+
+``quadratic_system(b, n)``: the fixed indefinite-quadratic surface of system ``b``
+
+    f(x) = 1/2 (x - x*)^T A (x - x*),   g(x) = A (x - x*)
+    A = Q diag(lam) Q^T,  lam_0 = -0.5 (exactly one negative curvature, i.e. an
+    order-1 saddle at x*),  lam_i = 0.1 + |N(0,1)|  otherwise,
+    x0 = x* + 0.3 N(0,1)^n / sqrt(n),     rng = RandomState(1000 + b)
+
+``quadratic_batch_torch`` draws the same family directly on a torch device for
+the large benchmark configurations (1024 x 384^2 and up), where a per-system
+host QR would take minutes.
+"""
+import numpy as np
+
+
+def quadratic_system(b, n, conditioning="normal"):
+    rng = np.random.RandomState(1000 + b)
+    Q, _ = np.linalg.qr(rng.normal(size=(n, n)))
+    if conditioning == "loguniform":
+        lam = np.exp(rng.uniform(np.log(0.05), np.log(50.0), size=n))
+    else:
+        lam = 0.1 + np.abs(rng.normal(size=n))
+    lam[0] = -0.5
+    A = (Q * lam[None, :]) @ Q.T
+    A = 0.5 * (A + A.T)
+    xstar = rng.normal(size=n)
+    x0 = xstar + 0.3 * rng.normal(size=n) / np.sqrt(n)
+    return A, xstar, x0
+
+
+def quadratic_batch(batch, n, first=0, conditioning="normal"):
+    """Stacked (A[b,n,n], xstar[b,n], x0[b,n]) for systems first..first+batch-1."""
+    A = np.empty((batch, n, n))
+    xs = np.empty((batch, n))
+    x0 = np.empty((batch, n))
+    for i in range(batch):
+        A[i], xs[i], x0[i] = quadratic_system(first + i, n, conditioning)
+    return A, xs, x0
+
+
+def quadratic_func(A, xstar):
+    """Host callable x -> (f, g) for one system (used by the CPU oracle)."""
+    def func(x):
+        d = x - xstar
+        g = A @ d
+        return 0.5 * (d @ g), g
+    return func
+
+
+def quadratic_batch_torch(batch, n, device, seed=1000, chunk=256):
+    """Same family, generated with torch on ``device`` (input generation only)."""
+    import torch
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    A = torch.empty((batch, n, n), dtype=torch.float64, device=device)
+    xs = torch.empty((batch, n), dtype=torch.float64, device=device)
+    x0 = torch.empty((batch, n), dtype=torch.float64, device=device)
+    for lo in range(0, batch, chunk):
+        hi = min(batch, lo + chunk)
+        m = hi - lo
+        G = torch.randn((m, n, n), dtype=torch.float64, device=device, generator=gen)
+        Q, _ = torch.linalg.qr(G)
+        lam = 0.1 + torch.randn((m, n), dtype=torch.float64, device=device,
+                                generator=gen).abs()
+        lam[:, 0] = -0.5
+        Ab = (Q * lam[:, None, :]) @ Q.transpose(1, 2)
+        A[lo:hi] = 0.5 * (Ab + Ab.transpose(1, 2))
+        xs[lo:hi] = torch.randn((m, n), dtype=torch.float64, device=device, generator=gen)
+        x0[lo:hi] = xs[lo:hi] + 0.3 * torch.randn(
+            (m, n), dtype=torch.float64, device=device, generator=gen) / n ** 0.5
+        del G, Q, Ab
+    return A, xs, x0
