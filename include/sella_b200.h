@@ -1,0 +1,158 @@
+/* sella_b200 -- C ABI of the B200-native Sella saddle-search inner loop.
+ *
+ * Every entry point is a batched, device-resident replacement for one numerical
+ * operator of the reference (zadorlab/sella); the reference interface each one
+ * replaces is cited as file:line relative to the reference tree.  The binding a
+ * maintainer of the reference would add (ctypes) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers to contiguous fp64 (double) / int32 data;
+ *   - matrices are row-major n x n ("numpy C order", as the reference stores B),
+ *     batch-leading: M[b][i][j] at M + (b*n + i)*n + j;
+ *   - vector blocks are vector-major: X[b][v][:] at X + (b*nvec + v)*n;
+ *   - `active` (int32[batch], may be NULL) masks systems: 0 = leave untouched;
+ *   - `status` (int32[batch]) receives OR-ed SB_ST_* bits (per-system error codes,
+ *     the batched analogue of the reference's exceptions / negative returns);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *   - return value: 0 on success, a cudaError_t or a negative argument error.
+ * No call synchronises the device or touches host memory.
+ */
+#ifndef SELLA_B200_H
+#define SELLA_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_ST_MGS_MAXITER 1     /* sella/utilities/math.pyx:132-133 (return -2) */
+#define SB_ST_TR_NOCONV 2       /* sella/optimize/restricted_step.py:116-117    */
+#define SB_ST_EIGH_NOCONV 4
+#define SB_ST_DAVIDSON_CAP 8
+#define SB_ST_SINGULAR 16
+#define SB_ST_DAVIDSON_STALL 32 /* sella/eigensolvers.py:99-109                 */
+
+/* library / device introspection */
+int sb_version(void);
+int sb_device_sms(void);
+
+/* Y[b,v,:] = A[b] @ X[b,v,:]  (transposed=0)   or   A[b].T @ X[b,v,:]  (1).
+ * Replaces A.dot(V) in rayleigh_ritz (sella/eigensolvers.py:52,112), the
+ * gradient difference of NumericalHessian._matvec on a quadratic surface
+ * (sella/linalg.py:82-87), B @ S (sella/hessian_update.py:119) and V.T @ g /
+ * V @ c of QuasiNewton (sella/optimize/stepper.py:86,93-95).                     */
+int sb_hv(const double* A, const double* X, double* Y, const int32_t* active,
+          int batch, int n, int nvec, int transposed, void* stream);
+/* same, for nvec vectors stored in blocks of ldv >= nvec slots per system
+ * (X and Y both [b, ldv, n]; only the first nvec slots are touched).             */
+int sb_hv_ld(const double* A, const double* X, double* Y, const int32_t* active,
+             int batch, int n, int nvec, int ldv, int transposed, void* stream);
+
+/* Quadratic surface evaluator (benchmark PES):
+ * g[b] = A[b] (x[b]-xstar[b]),  f[b] = 1/2 (x-xstar).g ; dwork: batch*n doubles. */
+int sb_quadratic_pes(const double* A, const double* xstar, const double* x,
+                     double* f, double* g, double* dwork, const int32_t* active,
+                     int batch, int n, void* stream);
+
+/* Symmetric eigendecomposition, replaces scipy.linalg.eigh at
+ * sella/linalg.py:174-195, sella/optimize/stepper.py:79-83,
+ * sella/eigensolvers.py:11, sella/_gpu.py:70-97 (gpu_eigh / gpu_eigh_t).
+ * evals[b,:] ascending; Vt[b,i,:] = eigenvector i (row = eigenvector).
+ * work: batch*n*n doubles, small: 3*batch*n doubles.                              */
+int sb_eigh(const double* A, double* evals, double* Vt, double* work, double* small_work,
+            int32_t* status, const int32_t* active, int batch, int n, void* stream);
+
+/* ---- orthogonalisation ------------------------------------------------------
+ * modified_gram_schmidt(Xin, Yin, eps1, eps2, maxiter): sella/utilities/math.pyx:143-159
+ * (cdef mgs :74-140).  X[b,nx,n] is orthonormalised in place against (an
+ * orthonormalised copy of) Y[b,ny,n] and itself; dropped columns are compacted away,
+ * leftovers zeroed.  nkept[b] = columns kept, or -2 (iteration limit, also sets
+ * SB_ST_MGS_MAXITER).  Ywork: b*ny*n doubles (ny may be 0, Y/Ywork NULL).           */
+int sb_mgs(double* X, int nx, const double* Y, double* Ywork, int ny, int n,
+           double eps1, double eps2, int maxiter, int32_t* nkept, int32_t* status,
+           const int32_t* active, int batch, void* stream);
+
+/* ---- Davidson / Rayleigh-Ritz (sella/eigensolvers.py:31-153) --------------------
+ * Device-resident state of one batched diagonalisation:
+ *   V, AV   [b,kcap,n]  current basis and its image (free space)
+ *   Vs, AVs [b,kcap,n]  operator history of NumericalHessian (linalg.py:89-90)
+ *   ksz, ninit, nhist, dav_state  int32[b]
+ * dav_state: 0 = expanding, 1 = finished, 2 = not participating.                   */
+/* start vectors: mode 0 -> v0 (eigensolvers.py:43-44); mode 1 -> eigenvectors of the
+ * preconditioner with negative eigenvalue, at least one (eigensolvers.py:46-50);
+ * pl/Pvt: spectrum (ascending) and eigenvectors (rows) of the preconditioner.       */
+int sb_davidson_init(const double* v0, const double* pl, const double* Pvt, int mode,
+                     double* V, int kcap, int n, int32_t* ksz, int32_t* ninit, int32_t* nhist,
+                     int32_t* dav_state, int32_t* status, const int32_t* part, int batch, void* stream);
+/* one Rayleigh-Ritz step (eigensolvers.py:56-89): lams[b,kcap]; for systems that go
+ * on, rv[b,0,:] = residual, rv[b,1,:] = Ritz vector of the chosen pair, theta[b].    */
+int sb_davidson_rr(double* V, double* AV, int kcap, const int32_t* ksz, int n, double gamma,
+                   int maxiter_eff, double* lams, double* rv, double* theta,
+                   int32_t* dav_state, int32_t* status, int batch, void* stream);
+/* correction equation in the eigenbasis of the preconditioner (eigensolvers.py:115-139):
+ * rvhat = Pvt @ [r, v]; method 0 = jd0/jd0_alt, 1 = gd.  that[b,n]: t = Pvt.T @ that.  */
+int sb_davidson_jd_coeff(const double* rvhat, const double* pl, const double* theta, double* that,
+                         int n, int method, const int32_t* dav_state, int batch, void* stream);
+/* normalise / Lanczos fallback / MGS against V / append (eigensolvers.py:90-111);
+ * vnew[b,n] = the appended direction.  p_identity: closed form for P = I.           */
+int sb_davidson_expand(const double* t, const double* rv, const double* theta, double* V,
+                       double* Ywork, int kcap, const int32_t* ksz, int n, int p_identity,
+                       int lanczos, double* vnew, int32_t* dav_state, int32_t* status,
+                       int batch, void* stream);
+/* NumericalHessian._matvec, sella/linalg.py:39-95: displaced geometry with the
+ * canonical sign (prepare), then Av and history bookkeeping (finish).  `mask`/`maskval`:
+ * only systems with mask[b] == maskval take part (mask may be NULL).                 */
+int sb_hvp_prepare(const double* vfull, long long vstride, const double* x0, const double* g0,
+                   double eta, double* xdisp, double* signnorm, int n, const int32_t* mask,
+                   int maskval, int batch, void* stream);
+int sb_hvp_finish(const double* vfull, long long vstride, const double* gplus, const double* g0,
+                  const double* signnorm, double eta, double* AV, double* Vs, double* AVs, int kcap,
+                  int32_t* ksz, int32_t* nhist, int n, const int32_t* mask, int maskval, int batch,
+                  void* stream);
+/* vstride: distance in doubles between the direction vectors of consecutive systems. */
+/* PES.diag tail, sella/peswrapper.py:541-551: Ritz rotation of the history (in place). */
+int sb_history_ritz(double* Vs, double* AVs, int kcap, const int32_t* nhist, int n,
+                    int32_t* nvec_out, const int32_t* dav_state, int32_t* status, int batch, void* stream);
+
+/* ---- quasi-Newton update (sella/hessian_update.py:40-152, sella/linalg.py:274-304) ----
+ * method: 0 TS-BFGS, 1 PSB, 2 Greenstadt; kvec may be NULL (one secant pair).         */
+int sb_update_prep(const double* S, const double* Y, double* Ytil, int kcap, const int32_t* kvec,
+                   int n, int ncart, int first, double* lam0, int32_t* skip, int32_t* status,
+                   const int32_t* active, int batch, void* stream);
+int sb_fill_scaled_identity(double* B, double* evals, double* Vt, const double* lam0, int n,
+                            int ncart, const int32_t* skip, int batch, void* stream);
+int sb_abs_scale(const double* VtS, const double* evals, double* out, int kcap, int n,
+                 const int32_t* skip, int batch, void* stream);
+int sb_update_mid(const double* S, const double* Ytil, const double* BS, const double* absBS,
+                  double* U, double* J, double* W, double* Xwork, int kcap, const int32_t* kvec,
+                  int n, int method, const int32_t* skip, int32_t* status, int batch, void* stream);
+int sb_update_apply(double* B, const double* U, const double* J, const double* W, int kcap,
+                    const int32_t* kvec, int n, const int32_t* skip, int batch, void* stream);
+
+/* ---- restricted step (sella/optimize/restricted_step.py:72-121, stepper.py:75-96) ----
+ * quasi-Newton model in the eigenbasis; Vg = Vt @ g.  tr: coef with s = Vt.T @ coef;
+ * ras: the Cartesian step itself (max atomic displacement constraint).               */
+int sb_qn_tr(const double* Vg, const double* evals, const double* delta, int order, int n,
+             double* coef, double* smag, double* alpha, int32_t* status, const int32_t* active,
+             int batch, void* stream);
+int sb_qn_ras(const double* Vg, const double* evals, const double* Vt, const double* delta,
+              int order, int n, double* s, double* smag, double* alpha, int32_t* status,
+              const int32_t* active, int batch, void* stream);
+
+/* ---- per-step bookkeeping (sella/peswrapper.py:578-602, optimize/optimize.py:362-434) ----
+ * dpar = {rho_inc, rho_dec, sigma_inc, sigma_dec, delta_min} (host array of 5 doubles),
+ * ipar = {order, eig, nsteps_per_diag, diag_every_n(<0: never)} (host array of 4 ints). */
+int sb_axpy(const double* x, const double* s, double* out, int n, const int32_t* active,
+            int batch, void* stream);
+int sb_kick_finish(double* x, double* f, double* g, const double* xnew, const double* fnew,
+                   const double* gnew, const double* s, const double* Bs, const double* smag,
+                   double* dg, double* delta, double* rho, int32_t* nsteps, const double* dpar,
+                   const int32_t* ipar, int n, const int32_t* active, int batch, void* stream);
+int sb_ev_decide(const double* evals, int n, int has_evals, int32_t* since_diag, int32_t* ev,
+                 const double* dpar, const int32_t* ipar, const int32_t* active, int batch, void* stream);
+int sb_converged(const double* g, int n, double fmax_tol, double* fmax_out, int32_t* conv,
+                 int batch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

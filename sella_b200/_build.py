@@ -1,0 +1,63 @@
+"""Builds libsella_b200.so (hand-written sm_100a CUDA + C ABI) in-tree with nvcc.
+
+    python -m sella_b200._build            # incremental
+    python -m sella_b200._build --force [-v]
+
+The shared object lives next to the sources (sella_b200/csrc/libsella_b200.so),
+is git-ignored, and travels to the GPU box with the repository snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(CSRC, "libsella_b200.so")
+OBJDIR = os.path.join(CSRC, "_build")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+         "-Xcompiler", "-fPIC"]
+
+
+def sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _stale(target, deps):
+    if not os.path.isfile(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJDIR, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "sella_b200.h"))
+    objs, procs = [], []
+    for src in sources():
+        obj = os.path.join(OBJDIR, src[:-3] + ".o")
+        objs.append(obj)
+        if force or _stale(obj, [os.path.join(CSRC, src)] + headers):
+            cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+            if verbose:
+                cmd += ["-Xptxas", "-v"]
+            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE,
+                                                stderr=subprocess.STDOUT)))
+    failed = False
+    for src, p in procs:
+        out = p.communicate()[0].decode()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write("nvcc failed for %s:\n%s\n" % (src, out))
+        elif verbose:
+            print(out)
+    if failed:
+        raise RuntimeError("building libsella_b200.so failed")
+    if force or procs or _stale(LIB, objs):
+        subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,277 @@
+"""Batched, device-resident saddle searches: many independent Sella runs advance
+in lock step, one CTA (or tile) per system inside every kernel.
+
+Host code is plain Python orchestration of the C-ABI kernels; all state stays in
+HBM between steps and the only host<->device traffic on the hot path is one
+4-byte "does any system re-diagonalise / keep expanding" flag per decision.
+
+Mirrors, per system, the reference's
+  Sella.step / _predict_step      sella/optimize/optimize.py:317-440
+  PES.kick / PES.diag             sella/peswrapper.py:508-602
+  ApproximateHessian.update       sella/linalg.py:274-304
+for the Cartesian, unconstrained case (Ufree = I: `proj_trans=False,
+proj_rot=False` in reference terms), quasi-Newton step model, trust-region or
+restricted-atomic-step constraint.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import kernels as K
+from ._lib import I, D, LL, _p, _stream, call, check_f64, require_cuda
+
+_DEFAULTS = dict(
+    minimum=dict(delta0=1e-1, sigma_inc=1.15, sigma_dec=0.90, rho_inc=1.035,
+                 rho_dec=100.0, method="qn", eig=False),
+    saddle=dict(delta0=0.1, sigma_inc=1.15, sigma_dec=0.65, rho_inc=1.035,
+                rho_dec=5.0, method="prfo", eig=True),
+)
+_UPDATE_METHODS = {"TS-BFGS": 0, "PSB": 1, "Greenstadt": 2}
+_EIGENSOLVERS = {"jd0": 0, "jd0_alt": 0, "gd": 1, "lanczos": 2}
+_QN_NAMES = ("qn", "quasi-newton", "quasi newton", "newton", "mmf",
+             "minimum mode following", "minimum-mode following", "dimer")
+_TR_NAMES = ("tr", "trust region", "trust-region", "trust radius", "trust-radius")
+_RAS_NAMES = ("ras", "restricted atomic step")
+
+DAV_EXPAND, DAV_DONE, DAV_IDLE = 0, 1, 2
+
+
+class QuadraticSurface:
+    """Device evaluator of the synthetic surfaces of SURVEY.md 8d
+    (f = 1/2 (x-x*)^T A (x-x*)).  Any object with the same `evaluate` signature can
+    be plugged into BatchedSella (that is the PES plug-in boundary)."""
+
+    def __init__(self, A, xstar):
+        check_f64(A, xstar)
+        self.A, self.xstar = A, xstar
+        self.batch, self.n = xstar.shape
+        self._work = torch.empty_like(xstar)
+        self.neval = 0
+
+    def evaluate(self, x, f_out, g_out, active=None):
+        self.neval += 1
+        call("sb_quadratic_pes", _p(self.A), _p(self.xstar), _p(x), _p(f_out), _p(g_out),
+             _p(self._work), _p(active), I(self.batch), I(self.n), _stream())
+
+
+class BatchedSella:
+    def __init__(self, surface, x0, order=1, delta0=None, sigma_inc=None, sigma_dec=None,
+                 rho_dec=None, rho_inc=None, eig=None, eta=1e-4, method=None, gamma=0.1,
+                 rs=None, nsteps_per_diag=3, diag_every_n=None, diag_maxiter=None,
+                 eigensolver="jd0", update_method="TS-BFGS", kcap=16):
+        require_cuda()
+        d = _DEFAULTS["minimum" if order == 0 else "saddle"]
+        self.surface = surface
+        check_f64(x0)
+        self.batch, self.n = x0.shape
+        b, n = self.batch, self.n
+        dev = x0.device
+        self.dev = dev
+        self.order = int(order)
+        method = d["method"] if method is None else method
+        if method.lower() not in _QN_NAMES:
+            raise NotImplementedError(
+                "step model %r: only the quasi-Newton model is on the batched path yet" % method)
+        rs = "ras" if rs is None else rs
+        if rs in _TR_NAMES:
+            self.rs = "tr"
+        elif rs in _RAS_NAMES:
+            self.rs = "ras"
+            if n % 3:
+                raise ValueError("restricted atomic step needs 3N coordinates")
+        else:
+            raise ValueError("Unknown restricted step name: {}".format(rs))
+        self.eig = d["eig"] if eig is None else bool(eig)
+        self.eta = float(eta)
+        self.gamma = float(gamma)
+        self.diag_maxiter = diag_maxiter
+        if eigensolver not in _EIGENSOLVERS:
+            raise NotImplementedError("eigensolver %r is not available on the batched path" % eigensolver)
+        self.eigensolver = _EIGENSOLVERS[eigensolver]
+        self.update_method = _UPDATE_METHODS[update_method]
+        self.kcap = int(kcap)
+        assert 2 <= self.kcap <= 32
+
+        delta0 = d["delta0"] if delta0 is None else delta0
+        delta_init = delta0 if self.rs == "ras" else delta0 * n
+        self._dpar = (ctypes.c_double * 5)(
+            d["rho_inc"] if rho_inc is None else rho_inc,
+            d["rho_dec"] if rho_dec is None else rho_dec,
+            d["sigma_inc"] if sigma_inc is None else sigma_inc,
+            d["sigma_dec"] if sigma_dec is None else sigma_dec,
+            self.eta)
+        self._ipar = (ctypes.c_int * 4)(self.order, int(self.eig), int(nsteps_per_diag),
+                                        -1 if diag_every_n is None else int(diag_every_n))
+
+        f64 = dict(dtype=torch.float64, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        z = lambda *s: torch.zeros(*s, **f64)      # noqa: E731
+        zi = lambda *s: torch.zeros(*s, **i32)     # noqa: E731
+        kc = self.kcap
+        # geometry / surface values
+        self.x = x0.clone()
+        self.f, self.g = z(b), z(b, n)
+        self.xnew, self.fnew, self.gnew = z(b, n), z(b), z(b, n)
+        self.xdisp, self.fplus, self.gplus = z(b, n), z(b), z(b, n)
+        # step state
+        self.s, self.dg, self.Vg, self.coef = z(b, n), z(b, n), z(b, n), z(b, n)
+        self.delta = torch.full((b,), float(delta_init), **f64)
+        self.rho = torch.ones(b, **f64)
+        self.smag, self.alpha = z(b), z(b)
+        self.nsteps, self.since_diag, self.ev = zi(b), zi(b), zi(b)
+        self.status = zi(b)
+        self.fmax, self.conv = z(b), zi(b)
+        # approximate Hessian and its spectrum
+        self.B = z(b, n, n)
+        self.evals, self.Vt = z(b, n), z(b, n, n)
+        self.eig_ws = K.EighWorkspace(b, n, dev)
+        self.H_initialized = False
+        self.eig_valid = False
+        # Davidson state
+        self.V, self.AV, self.Vs, self.AVs, self.Yw = (z(b, kc, n) for _ in range(5))
+        self.ksz, self.ninit, self.nhist, self.dav_state, self.nvec = (zi(b) for _ in range(5))
+        self.lams = z(b, kc)
+        self.rv, self.rvhat = z(b, 2, n), z(b, 2, n)
+        self.theta, self.that, self.t, self.vnew, self.signnorm = z(b), z(b, n), z(b, n), z(b, n), z(b)
+        # update work space: one-pair (step) and kcap-pair (post-diagonalisation)
+        self.up1 = {k: z(b, 1, n) for k in ("Ytil", "BS", "VtS", "aC", "aBS", "U", "J", "W", "Xw")}
+        self.upk = {k: z(b, kc, n) for k in ("Ytil", "BS", "VtS", "aC", "aBS", "U", "J", "W", "Xw")}
+        self.lam0, self.skip = z(b), zi(b)
+        self.initialized = False
+        self.ndiag = 0
+
+    # ------------------------------------------------------------------ helpers
+    def _eigh(self, active=None):
+        call("sb_eigh", _p(self.B), _p(self.evals), _p(self.Vt), _p(self.eig_ws.work),
+             _p(self.eig_ws.small), _p(self.status), _p(active), I(self.batch), I(self.n), _stream())
+
+    def _update(self, S, Y, bufs, kvec, nv, active, bs_ready=False):
+        """ApproximateHessian.update (linalg.py:274-304) for S, Y of shape [b,kc,n]."""
+        b, n = self.batch, self.n
+        kc = S.shape[1]
+        first = not self.H_initialized
+        call("sb_update_prep", _p(S), _p(Y), _p(bufs["Ytil"]), I(kc), _p(kvec), I(n), I(n), I(int(first)),
+             _p(self.lam0), _p(self.skip), _p(self.status), _p(active), I(b), _stream())
+        if first:
+            call("sb_fill_scaled_identity", _p(self.B), _p(self.evals), _p(self.Vt), _p(self.lam0), I(n),
+                 I(n), _p(self.skip), I(b), _stream())
+            self.H_initialized = True
+            bs_ready = False
+        if not bs_ready:
+            K.hv_ld(self.B, S, bufs["BS"], nv, active=active)
+        if self.update_method == 0:
+            K.hv_ld(self.Vt, S, bufs["VtS"], nv, active=active)
+            call("sb_abs_scale", _p(bufs["VtS"]), _p(self.evals), _p(bufs["aC"]), I(kc), I(n), _p(self.skip),
+                 I(b), _stream())
+            K.hv_ld(self.Vt, bufs["aC"], bufs["aBS"], nv, transposed=True, active=active)
+        call("sb_update_mid", _p(S), _p(bufs["Ytil"]), _p(bufs["BS"]),
+             _p(bufs["aBS"] if self.update_method == 0 else None), _p(bufs["U"]), _p(bufs["J"]), _p(bufs["W"]),
+             _p(bufs["Xw"]), I(kc), _p(kvec), I(n), I(self.update_method), _p(self.skip), _p(self.status),
+             I(b), _stream())
+        call("sb_update_apply", _p(self.B), _p(bufs["U"]), _p(bufs["J"]), _p(bufs["W"]), I(kc), _p(kvec),
+             I(n), _p(self.skip), I(b), _stream())
+        self.eig_valid = False
+
+    def _hvp(self, vec, vstride, mask, maskval, active):
+        """One finite-difference Hessian-vector product per participating system."""
+        b, n = self.batch, self.n
+        call("sb_hvp_prepare", _p(vec), LL(vstride), _p(self.x), _p(self.g), D(self.eta), _p(self.xdisp),
+             _p(self.signnorm), I(n), _p(mask), I(maskval), I(b), _stream())
+        self.surface.evaluate(self.xdisp, self.fplus, self.gplus, active=active)
+        call("sb_hvp_finish", _p(vec), LL(vstride), _p(self.gplus), _p(self.g), _p(self.signnorm), D(self.eta),
+             _p(self.AV), _p(self.Vs), _p(self.AVs), I(self.kcap), _p(self.ksz), _p(self.nhist), I(n),
+             _p(mask), I(maskval), I(b), _stream())
+
+    def _diag(self, part=None):
+        """PES.diag (peswrapper.py:508-556) for the systems with part[b] != 0."""
+        b, n, kc = self.batch, self.n, self.kcap
+        first = not self.H_initialized          # P = identity, v0 = g
+        if not first:
+            self._eigh(active=part)             # spectrum of the preconditioner P = B
+        call("sb_davidson_init", _p(self.g), _p(self.evals), _p(self.Vt), I(0 if first else 1), _p(self.V),
+             I(kc), I(n), _p(self.ksz), _p(self.ninit), _p(self.nhist), _p(self.dav_state), _p(self.status),
+             _p(part), I(b), _stream())
+        nstart = 1 if first else int(self.ninit.max().item())
+        for j in range(nstart):
+            m = ((self.dav_state == DAV_EXPAND) & (self.ninit > j)).to(torch.int32)
+            self._hvp(self.V[:, j], kc * n, m, 1, m)
+        maxiter_eff = n if self.diag_maxiter is None else min(n, int(self.diag_maxiter))
+        rounds = nstart
+        while True:
+            call("sb_davidson_rr", _p(self.V), _p(self.AV), I(kc), _p(self.ksz), I(n), D(self.gamma),
+                 I(maxiter_eff), _p(self.lams), _p(self.rv), _p(self.theta), _p(self.dav_state),
+                 _p(self.status), I(b), _stream())
+            m = (self.dav_state == DAV_EXPAND).to(torch.int32)
+            if int(m.sum().item()) == 0:
+                break
+            lanczos = int(self.eigensolver == 2)
+            if first or lanczos:
+                tin = None
+            else:
+                K.hv_ld(self.Vt, self.rv, self.rvhat, 2, active=m)
+                call("sb_davidson_jd_coeff", _p(self.rvhat), _p(self.evals), _p(self.theta), _p(self.that),
+                     I(n), I(self.eigensolver), _p(self.dav_state), I(b), _stream())
+                K.hv_ld(self.Vt, self.that.view(b, 1, n), self.t.view(b, 1, n), 1, transposed=True, active=m)
+                tin = self.t
+            call("sb_davidson_expand", _p(tin), _p(self.rv), _p(self.theta), _p(self.V), _p(self.Yw), I(kc),
+                 _p(self.ksz), I(n), I(int(first)), I(lanczos), _p(self.vnew), _p(self.dav_state),
+                 _p(self.status), I(b), _stream())
+            m = (self.dav_state == DAV_EXPAND).to(torch.int32)
+            self._hvp(self.vnew, n, self.dav_state, DAV_EXPAND, m)
+            rounds += 1
+        call("sb_history_ritz", _p(self.Vs), _p(self.AVs), I(kc), _p(self.nhist), I(n), _p(self.nvec),
+             _p(self.dav_state), _p(self.status), I(b), _stream())
+        self._update(self.Vs, self.AVs, self.upk, self.nvec, min(rounds, kc), part)
+        self.ndiag += 1
+
+    # ------------------------------------------------------------------ public
+    def step(self, active=None):
+        """One Sella.step for every (active) system."""
+        b, n = self.batch, self.n
+        if not self.initialized:
+            self.surface.evaluate(self.x, self.f, self.g)
+            if self.eig:
+                self._diag(None)
+                self.since_diag.fill_(-1)
+            self.initialized = True
+        # ---- _predict_step: restricted step from the spectral model
+        if not self.H_initialized:
+            raise NotImplementedError("steps on an uninitialised Hessian (eig=False) are not batched yet")
+        if not self.eig_valid:
+            self._eigh(active)
+            self.eig_valid = True
+        K.hv_ld(self.Vt, self.g.view(b, 1, n), self.Vg.view(b, 1, n), 1, active=active)
+        if self.rs == "tr":
+            call("sb_qn_tr", _p(self.Vg), _p(self.evals), _p(self.delta), I(self.order), I(n), _p(self.coef),
+                 _p(self.smag), _p(self.alpha), _p(self.status), _p(active), I(b), _stream())
+            K.hv_ld(self.Vt, self.coef.view(b, 1, n), self.s.view(b, 1, n), 1, transposed=True, active=active)
+        else:
+            call("sb_qn_ras", _p(self.Vg), _p(self.evals), _p(self.Vt), _p(self.delta), I(self.order), I(n),
+                 _p(self.s), _p(self.smag), _p(self.alpha), _p(self.status), _p(active), I(b), _stream())
+        # ---- re-diagonalise?  (spectrum of the Hessian before this step's update)
+        call("sb_ev_decide", _p(self.evals), I(n), I(1), _p(self.since_diag), _p(self.ev), self._dpar,
+             self._ipar, _p(active), I(b), _stream())
+        # ---- kick
+        call("sb_axpy", _p(self.x), _p(self.s), _p(self.xnew), I(n), _p(active), I(b), _stream())
+        self.surface.evaluate(self.xnew, self.fnew, self.gnew, active=active)
+        S1 = self.s.view(b, 1, n)
+        K.hv_ld(self.B, S1, self.up1["BS"], 1, active=active)
+        call("sb_kick_finish", _p(self.x), _p(self.f), _p(self.g), _p(self.xnew), _p(self.fnew), _p(self.gnew),
+             _p(self.s), _p(self.up1["BS"]), _p(self.smag), _p(self.dg), _p(self.delta), _p(self.rho),
+             _p(self.nsteps), self._dpar, self._ipar, I(n), _p(active), I(b), _stream())
+        self._update(S1, self.dg.view(b, 1, n), self.up1, None, 1, active, bs_ready=True)
+        if self.eig and int(self.ev.sum().item()) > 0:
+            self._diag(self.ev)
+
+    def converged(self, fmax):
+        call("sb_converged", _p(self.g), I(self.n), D(float(fmax)), _p(self.fmax), _p(self.conv),
+             I(self.batch), _stream())
+        return self.conv
+
+    def check_status(self):
+        st = self.status.cpu().numpy()
+        if st.any():
+            bad = np.nonzero(st)[0]
+            raise RuntimeError("sella_b200: %d system(s) reported errors, first: system %d status %d"
+                               % (len(bad), bad[0], st[bad[0]]))

@@ -1,0 +1,216 @@
+// extern "C" surface of libsella_b200.so (declarations: include/sella_b200.h).
+#include "common.cuh"
+#include "../../include/sella_b200.h"
+
+extern "C" int sb_hv_impl(const double*, const double*, double*, const int*, int, int, int, int,
+                          cudaStream_t);
+extern "C" int sb_eigh_impl(const double*, double*, double*, double*, double*, int*, const int*, int, int,
+                            cudaStream_t);
+extern "C" int sb_hv_ld_impl(const double*, const double*, double*, const int*, int, int, int, int, int,
+                             cudaStream_t);
+extern "C" int sb_mgs_impl(double*, int, const double*, double*, int, int, double, double, int, int*, int*,
+                           const int*, int, cudaStream_t);
+extern "C" int sb_davidson_init_impl(const double*, const double*, const double*, int, double*, int, int, int*,
+                                     int*, int*, int*, int*, const int*, int, cudaStream_t);
+extern "C" int sb_davidson_rr_impl(double*, double*, int, const int*, int, double, int, double*, double*, double*,
+                                   int*, int*, int, cudaStream_t);
+extern "C" int sb_davidson_jd_coeff_impl(const double*, const double*, const double*, double*, int, int,
+                                         const int*, int, cudaStream_t);
+extern "C" int sb_davidson_expand_impl(const double*, const double*, const double*, double*, double*, int,
+                                       const int*, int, int, int, double*, int*, int*, int, cudaStream_t);
+extern "C" int sb_hvp_prepare_impl(const double*, long long, const double*, const double*, double, double*, double*,
+                                   int, const int*, int, int, cudaStream_t);
+extern "C" int sb_hvp_finish_impl(const double*, long long, const double*, const double*, const double*, double,
+                                  double*, double*, double*, int, int*, int*, int, const int*, int, int,
+                                  cudaStream_t);
+extern "C" int sb_history_ritz_impl(double*, double*, int, const int*, int, int*, const int*, int*, int,
+                                    cudaStream_t);
+extern "C" int sb_update_prep_impl(const double*, const double*, double*, int, const int*, int, int, int, double*,
+                                   int*, int*, const int*, int, cudaStream_t);
+extern "C" int sb_fill_scaled_identity_impl(double*, double*, double*, const double*, int, int, const int*, int,
+                                            cudaStream_t);
+extern "C" int sb_abs_scale_impl(const double*, const double*, double*, int, int, const int*, int, cudaStream_t);
+extern "C" int sb_update_mid_impl(const double*, const double*, const double*, const double*, double*, double*,
+                                  double*, double*, int, const int*, int, int, const int*, int*, int, cudaStream_t);
+extern "C" int sb_update_apply_impl(double*, const double*, const double*, const double*, int, const int*, int,
+                                    const int*, int, cudaStream_t);
+extern "C" int sb_qn_tr_impl(const double*, const double*, const double*, int, int, double*, double*, double*, int*,
+                             const int*, int, cudaStream_t);
+extern "C" int sb_qn_ras_impl(const double*, const double*, const double*, const double*, int, int, double*,
+                              double*, double*, int*, const int*, int, cudaStream_t);
+extern "C" int sb_axpy_impl(const double*, const double*, double*, int, const int*, int, cudaStream_t);
+extern "C" int sb_kick_finish_impl(double*, double*, double*, const double*, const double*, const double*,
+                                   const double*, const double*, const double*, double*, double*, double*, int*,
+                                   const double*, const int*, int, const int*, int, cudaStream_t);
+extern "C" int sb_ev_decide_impl(const double*, int, int, int*, int*, const double*, const int*, const int*, int,
+                                 cudaStream_t);
+extern "C" int sb_converged_impl(const double*, int, double, double*, int*, int, cudaStream_t);
+
+namespace {
+
+__global__ void diff_kernel(const double* __restrict__ x, const double* __restrict__ x0,
+                            double* __restrict__ d, const int* __restrict__ active, int n) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[(size_t)b * n + i] = x[(size_t)b * n + i] - x0[(size_t)b * n + i];
+}
+
+// f[b] = scale * x[b].y[b]   (deterministic block reduction)
+__global__ void dot_kernel(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ f,
+                           double scale, const int* __restrict__ active, int n) {
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    __shared__ double scratch[SB_SCRATCH_DOUBLES];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        acc = fma(x[(size_t)b * n + i], y[(size_t)b * n + i], acc);
+    acc = sb_block_sum(acc, scratch);
+    if (threadIdx.x == 0) f[b] = scale * acc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sb_version(void) { return 1; }
+
+int sb_device_sms(void) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    return sms;
+}
+
+int sb_hv(const double* A, const double* X, double* Y, const int32_t* active, int batch, int n, int nvec,
+          int transposed, void* stream) {
+    if (batch <= 0 || n <= 0 || nvec <= 0) return -1;
+    return sb_hv_impl(A, X, Y, active, batch, n, nvec, transposed, (cudaStream_t)stream);
+}
+
+int sb_hv_ld(const double* A, const double* X, double* Y, const int32_t* active, int batch, int n, int nvec,
+             int ldv, int transposed, void* stream) {
+    if (batch <= 0 || n <= 0 || nvec <= 0 || ldv < nvec) return -1;
+    return sb_hv_ld_impl(A, X, Y, active, batch, n, nvec, ldv, transposed, (cudaStream_t)stream);
+}
+
+int sb_quadratic_pes(const double* A, const double* xstar, const double* x, double* f, double* g,
+                     double* dwork, const int32_t* active, int batch, int n, void* stream) {
+    if (batch <= 0 || n <= 0) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((n + 255) / 256, batch);
+    diff_kernel<<<grid, 256, 0, st>>>(x, xstar, dwork, active, n);
+    int rc = sb_hv_impl(A, dwork, g, active, batch, n, 1, 0, st);
+    if (rc) return rc;
+    dot_kernel<<<batch, 256, 0, st>>>(dwork, g, f, 0.5, active, n);
+    return SB_LAUNCH_CHECK();
+}
+
+int sb_eigh(const double* A, double* evals, double* Vt, double* work, double* small_work, int32_t* status,
+            const int32_t* active, int batch, int n, void* stream) {
+    if (batch <= 0 || n <= 0) return -1;
+    return sb_eigh_impl(A, evals, Vt, work, small_work, status, active, batch, n, (cudaStream_t)stream);
+}
+
+#define ST ((cudaStream_t)stream)
+int sb_mgs(double* X, int nx, const double* Y, double* Ywork, int ny, int n, double eps1, double eps2,
+           int maxiter, int32_t* nkept, int32_t* status, const int32_t* active, int batch, void* stream) {
+    if (batch <= 0 || n <= 0 || nx <= 0) return -1;
+    return sb_mgs_impl(X, nx, Y, Ywork, ny, n, eps1, eps2, maxiter, nkept, status, active, batch, ST);
+}
+int sb_davidson_init(const double* v0, const double* pl, const double* Pvt, int mode, double* V, int kcap, int n,
+                     int32_t* ksz, int32_t* ninit, int32_t* nhist, int32_t* dav_state, int32_t* status,
+                     const int32_t* part, int batch, void* stream) {
+    if (kcap > 32 || kcap < 2) return -1;
+    return sb_davidson_init_impl(v0, pl, Pvt, mode, V, kcap, n, ksz, ninit, nhist, dav_state, status, part, batch,
+                                 ST);
+}
+int sb_davidson_rr(double* V, double* AV, int kcap, const int32_t* ksz, int n, double gamma, int maxiter_eff,
+                   double* lams, double* rv, double* theta, int32_t* dav_state, int32_t* status, int batch,
+                   void* stream) {
+    if (kcap > 32) return -1;
+    return sb_davidson_rr_impl(V, AV, kcap, ksz, n, gamma, maxiter_eff, lams, rv, theta, dav_state, status, batch,
+                               ST);
+}
+int sb_davidson_jd_coeff(const double* rvhat, const double* pl, const double* theta, double* that, int n,
+                         int method, const int32_t* dav_state, int batch, void* stream) {
+    return sb_davidson_jd_coeff_impl(rvhat, pl, theta, that, n, method, dav_state, batch, ST);
+}
+int sb_davidson_expand(const double* t, const double* rv, const double* theta, double* V, double* Ywork, int kcap,
+                       const int32_t* ksz, int n, int p_identity, int lanczos, double* vnew, int32_t* dav_state,
+                       int32_t* status, int batch, void* stream) {
+    return sb_davidson_expand_impl(t, rv, theta, V, Ywork, kcap, ksz, n, p_identity, lanczos, vnew, dav_state,
+                                   status, batch, ST);
+}
+int sb_hvp_prepare(const double* vfull, long long vstride, const double* x0, const double* g0, double eta,
+                   double* xdisp, double* signnorm, int n, const int32_t* mask, int maskval, int batch,
+                   void* stream) {
+    return sb_hvp_prepare_impl(vfull, vstride, x0, g0, eta, xdisp, signnorm, n, mask, maskval, batch, ST);
+}
+int sb_hvp_finish(const double* vfull, long long vstride, const double* gplus, const double* g0,
+                  const double* signnorm, double eta, double* AV, double* Vs, double* AVs, int kcap, int32_t* ksz,
+                  int32_t* nhist, int n, const int32_t* mask, int maskval, int batch, void* stream) {
+    return sb_hvp_finish_impl(vfull, vstride, gplus, g0, signnorm, eta, AV, Vs, AVs, kcap, ksz, nhist, n, mask,
+                              maskval, batch, ST);
+}
+int sb_history_ritz(double* Vs, double* AVs, int kcap, const int32_t* nhist, int n, int32_t* nvec_out,
+                    const int32_t* dav_state, int32_t* status, int batch, void* stream) {
+    if (kcap > 32) return -1;
+    return sb_history_ritz_impl(Vs, AVs, kcap, nhist, n, nvec_out, dav_state, status, batch, ST);
+}
+int sb_update_prep(const double* S, const double* Y, double* Ytil, int kcap, const int32_t* kvec, int n, int ncart,
+                   int first, double* lam0, int32_t* skip, int32_t* status, const int32_t* active, int batch,
+                   void* stream) {
+    if (kcap > 32 || kcap < 1) return -1;
+    return sb_update_prep_impl(S, Y, Ytil, kcap, kvec, n, ncart, first, lam0, skip, status, active, batch, ST);
+}
+int sb_fill_scaled_identity(double* B, double* evals, double* Vt, const double* lam0, int n, int ncart,
+                            const int32_t* skip, int batch, void* stream) {
+    return sb_fill_scaled_identity_impl(B, evals, Vt, lam0, n, ncart, skip, batch, ST);
+}
+int sb_abs_scale(const double* VtS, const double* evals, double* out, int kcap, int n, const int32_t* skip,
+                 int batch, void* stream) {
+    return sb_abs_scale_impl(VtS, evals, out, kcap, n, skip, batch, ST);
+}
+int sb_update_mid(const double* S, const double* Ytil, const double* BS, const double* absBS, double* U, double* J,
+                  double* W, double* Xwork, int kcap, const int32_t* kvec, int n, int method, const int32_t* skip,
+                  int32_t* status, int batch, void* stream) {
+    if (method < 0 || method > 2 || kcap > 32) return -1;
+    if (method == 0 && !absBS) return -1;
+    return sb_update_mid_impl(S, Ytil, BS, absBS, U, J, W, Xwork, kcap, kvec, n, method, skip, status, batch, ST);
+}
+int sb_update_apply(double* B, const double* U, const double* J, const double* W, int kcap, const int32_t* kvec,
+                    int n, const int32_t* skip, int batch, void* stream) {
+    return sb_update_apply_impl(B, U, J, W, kcap, kvec, n, skip, batch, ST);
+}
+int sb_qn_tr(const double* Vg, const double* evals, const double* delta, int order, int n, double* coef,
+             double* smag, double* alpha, int32_t* status, const int32_t* active, int batch, void* stream) {
+    return sb_qn_tr_impl(Vg, evals, delta, order, n, coef, smag, alpha, status, active, batch, ST);
+}
+int sb_qn_ras(const double* Vg, const double* evals, const double* Vt, const double* delta, int order, int n,
+              double* s, double* smag, double* alpha, int32_t* status, const int32_t* active, int batch,
+              void* stream) {
+    if (n % 3) return -1;
+    return sb_qn_ras_impl(Vg, evals, Vt, delta, order, n, s, smag, alpha, status, active, batch, ST);
+}
+int sb_axpy(const double* x, const double* s, double* out, int n, const int32_t* active, int batch, void* stream) {
+    return sb_axpy_impl(x, s, out, n, active, batch, ST);
+}
+int sb_kick_finish(double* x, double* f, double* g, const double* xnew, const double* fnew, const double* gnew,
+                   const double* s, const double* Bs, const double* smag, double* dg, double* delta, double* rho,
+                   int32_t* nsteps, const double* dpar, const int32_t* ipar, int n, const int32_t* active,
+                   int batch, void* stream) {
+    return sb_kick_finish_impl(x, f, g, xnew, fnew, gnew, s, Bs, smag, dg, delta, rho, nsteps, dpar, ipar, n,
+                               active, batch, ST);
+}
+int sb_ev_decide(const double* evals, int n, int has_evals, int32_t* since_diag, int32_t* ev, const double* dpar,
+                 const int32_t* ipar, const int32_t* active, int batch, void* stream) {
+    return sb_ev_decide_impl(evals, n, has_evals, since_diag, ev, dpar, ipar, active, batch, ST);
+}
+int sb_converged(const double* g, int n, double fmax_tol, double* fmax_out, int32_t* conv, int batch,
+                 void* stream) {
+    return sb_converged_impl(g, n, fmax_tol, fmax_out, conv, batch, ST);
+}
+#undef ST
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+"""Batched device operators (torch CUDA tensors in/out) over the C ABI.
+
+Shapes: matrices [b, n, n]; vector blocks [b, nvec, n] ("vector-major": each
+vector contiguous); per-system scalars [b].  All float64, contiguous, on the
+current CUDA device.  `active` is an optional int32 [b] mask.
+"""
+import torch
+
+from . import _lib
+from ._lib import I, D, _p, _stream, call, check_f64, require_cuda
+
+
+def _mask(active):
+    if active is None:
+        return None
+    if active.dtype != torch.int32:
+        active = active.to(torch.int32)
+    return active.contiguous()
+
+
+def hv(A, X, transposed=False, active=None, out=None):
+    """Y[b,v] = A[b] @ X[b,v]  (or A[b].T @ X[b,v])."""
+    require_cuda()
+    squeeze = X.dim() == 2
+    if squeeze:
+        X = X.unsqueeze(1)
+    X = X.contiguous()
+    check_f64(A, X)
+    b, n, _ = A.shape
+    nvec = X.shape[1]
+    Y = torch.empty_like(X) if out is None else out
+    if active is not None and out is None:
+        Y.zero_()
+    active = _mask(active)
+    call("sb_hv", _p(A), _p(X), _p(Y), _p(active), I(b), I(n), I(nvec), I(int(transposed)), _stream())
+    return Y.squeeze(1) if squeeze else Y
+
+
+def quadratic_pes(A, xstar, x, active=None, f=None, g=None):
+    """f, g of the fixed quadratic surfaces 1/2 (x-x*)^T A (x-x*)."""
+    require_cuda()
+    check_f64(A, xstar, x)
+    b, n, _ = A.shape
+    f = torch.empty(b, dtype=torch.float64, device=A.device) if f is None else f
+    g = torch.empty_like(x) if g is None else g
+    work = torch.empty_like(x)
+    active = _mask(active)
+    call("sb_quadratic_pes", _p(A), _p(xstar), _p(x), _p(f), _p(g), _p(work), _p(active), I(b), I(n),
+         _stream())
+    return f, g
+
+
+class EighWorkspace:
+    def __init__(self, batch, n, device):
+        self.work = torch.empty((batch, n, n), dtype=torch.float64, device=device)
+        self.small = torch.empty((3, batch, n), dtype=torch.float64, device=device)
+
+
+def eigh(A, active=None, evals=None, Vt=None, ws=None, status=None):
+    """Ascending eigenvalues [b,n] and eigenvectors as ROWS of Vt [b,n,n]."""
+    require_cuda()
+    check_f64(A)
+    b, n, _ = A.shape
+    dev = A.device
+    evals = torch.empty((b, n), dtype=torch.float64, device=dev) if evals is None else evals
+    Vt = torch.empty((b, n, n), dtype=torch.float64, device=dev) if Vt is None else Vt
+    ws = EighWorkspace(b, n, dev) if ws is None else ws
+    status = torch.zeros(b, dtype=torch.int32, device=dev) if status is None else status
+    active = _mask(active)
+    call("sb_eigh", _p(A), _p(evals), _p(Vt), _p(ws.work), _p(ws.small), _p(status), _p(active), I(b),
+         I(n), _stream())
+    return evals, Vt, status
+
+
+# --------------------------------------------------------------------------
+# thin wrappers used by the batched engine (all arguments preallocated tensors)
+# --------------------------------------------------------------------------
+from ._lib import LL  # noqa: E402
+
+
+def hv_ld(A, X, Y, nvec, transposed=False, active=None):
+    """In-place variant on [b, ldv, n] blocks: first `nvec` slots only."""
+    b, n, _ = A.shape
+    call("sb_hv_ld", _p(A), _p(X), _p(Y), _p(active), I(b), I(n), I(nvec), I(X.shape[1]),
+         I(int(transposed)), _stream())
+    return Y
+
+
+def mgs(X, Y=None, eps1=1e-15, eps2=1e-6, maxiter=100, active=None):
+    """Batched modified_gram_schmidt: X [b,nx,n] (modified in place), Y [b,ny,n]."""
+    require_cuda()
+    check_f64(X, Y)
+    b, nx, n = X.shape
+    ny = 0 if Y is None else Y.shape[1]
+    Ywork = None if Y is None else torch.empty_like(Y)
+    nkept = torch.zeros(b, dtype=torch.int32, device=X.device)
+    status = torch.zeros(b, dtype=torch.int32, device=X.device)
+    call("sb_mgs", _p(X), I(nx), _p(Y), _p(Ywork), I(ny), I(n), D(eps1), D(eps2), I(maxiter),
+         _p(nkept), _p(status), _p(_mask(active)), I(b), _stream())
+    return nkept, status

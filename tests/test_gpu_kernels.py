@@ -1,0 +1,102 @@
+"""GPU parity tests of the individual CUDA operators (through the C ABI) against
+numpy/scipy (the arithmetic the reference itself calls) and the CPU oracle."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def to_dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev())
+
+
+def rand_sym(rng, b, n):
+    A = rng.normal(size=(b, n, n))
+    return 0.5 * (A + A.transpose(0, 2, 1))
+
+
+@pytest.mark.parametrize("n", [16, 30, 33, 96, 192, 384, 768, 1536])
+@pytest.mark.parametrize("nvec", [1, 2, 3, 5])
+def test_hv_and_transpose(n, nvec):
+    from sella_b200 import kernels as K
+    rng = np.random.RandomState(n + nvec)
+    b = 3 if n >= 768 else 7
+    A = rng.normal(size=(b, n, n))
+    X = rng.normal(size=(b, nvec, n))
+    Y = K.hv(to_dev(A), to_dev(X)).cpu().numpy()
+    ref = np.einsum("bij,bvj->bvi", A, X)
+    np.testing.assert_allclose(Y, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+    Yt = K.hv(to_dev(A), to_dev(X), transposed=True).cpu().numpy()
+    reft = np.einsum("bji,bvj->bvi", A, X)
+    np.testing.assert_allclose(Yt, reft, rtol=1e-12, atol=1e-12 * np.abs(reft).max())
+
+
+def test_hv_many_systems_and_mask():
+    from sella_b200 import kernels as K
+    rng = np.random.RandomState(5)
+    b, n = 301, 192           # > #SMs: exercises the persistent tile loop and ring wrap
+    A = rng.normal(size=(b, n, n)); x = rng.normal(size=(b, n))
+    act = (rng.rand(b) > 0.3).astype(np.int32)
+    out = torch.full((b, 1, n), 7.0, dtype=torch.float64, device=dev())
+    K.hv(to_dev(A), to_dev(x[:, None, :]), active=to_dev(act), out=out)
+    got = out.cpu().numpy()[:, 0]
+    ref = np.einsum("bij,bj->bi", A, x)
+    np.testing.assert_allclose(got[act == 1], ref[act == 1], rtol=1e-12, atol=1e-11)
+    assert np.all(got[act == 0] == 7.0)
+    out.fill_(7.0)
+    K.hv(to_dev(A), to_dev(x[:, None, :]), transposed=True, active=to_dev(act), out=out)
+    got = out.cpu().numpy()[:, 0]
+    ref = np.einsum("bji,bj->bi", A, x)
+    np.testing.assert_allclose(got[act == 1], ref[act == 1], rtol=1e-12, atol=1e-11)
+    assert np.all(got[act == 0] == 7.0)
+
+
+def test_quadratic_pes_matches_host_surface():
+    from sella_b200 import kernels as K
+    from sella_b200.synthetic import quadratic_batch
+    A, xs, x0 = quadratic_batch(5, 96)
+    f, g = K.quadratic_pes(to_dev(A), to_dev(xs), to_dev(x0))
+    d = x0 - xs
+    gref = np.einsum("bij,bj->bi", A, d)
+    np.testing.assert_allclose(g.cpu().numpy(), gref, rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(f.cpu().numpy(), 0.5 * np.einsum("bi,bi->b", d, gref), rtol=1e-12)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 24, 96, 192, 384])
+def test_eigh_against_lapack(n):
+    from sella_b200 import kernels as K
+    rng = np.random.RandomState(100 + n)
+    b = 6
+    A = rand_sym(rng, b, n)
+    # quasi-Newton-like member: scaled identity + low rank (massively degenerate)
+    u = rng.normal(size=(n, min(2, n)))
+    A[1] = 0.7 * np.eye(n) + u @ u.T - 2.0 * np.outer(u[:, 0], u[:, 0])
+    A[2] = np.diag(rng.normal(size=n))            # already diagonal
+    w, Vt, status = K.eigh(to_dev(A))
+    w, Vt = w.cpu().numpy(), Vt.cpu().numpy()
+    assert int(status.abs().sum()) == 0
+    for i in range(b):
+        wref = np.linalg.eigvalsh(A[i])
+        scale = max(1.0, np.abs(wref).max())
+        np.testing.assert_allclose(w[i], wref, rtol=0, atol=5e-13 * scale * max(1, n / 32))
+        V = Vt[i].T
+        np.testing.assert_allclose(V.T @ V, np.eye(n), atol=5e-13 * max(1, n / 32))
+        np.testing.assert_allclose(A[i] @ V, V * w[i][None, :], atol=5e-12 * scale * max(1, n / 32))
+
+
+def test_eigh_mask_leaves_inactive_untouched():
+    from sella_b200 import kernels as K
+    rng = np.random.RandomState(3)
+    A = rand_sym(rng, 4, 48)
+    act = np.array([1, 0, 1, 0], dtype=np.int32)
+    w0 = torch.full((4, 48), -5.0, dtype=torch.float64, device=dev())
+    V0 = torch.full((4, 48, 48), -5.0, dtype=torch.float64, device=dev())
+    K.eigh(to_dev(A), active=to_dev(act), evals=w0, Vt=V0)
+    assert torch.all(w0[1] == -5.0) and torch.all(V0[3] == -5.0)
+    np.testing.assert_allclose(w0[0].cpu().numpy(), np.linalg.eigvalsh(A[0]), atol=1e-12)
