@@ -34,6 +34,8 @@ extern "C" {
 /* library / device introspection */
 int sb_version(void);
 int sb_device_sms(void);
+/* kernels launched by this library since load (bench.py: gpu_launches) */
+long long sb_launch_count(void);
 
 /* Y[b,v,:] = A[b] @ X[b,v,:]  (transposed=0)   or   A[b].T @ X[b,v,:]  (1).
  * Replaces A.dot(V) in rayleigh_ritz (sella/eigensolvers.py:52,112), the

@@ -46,6 +46,8 @@ extern "C" int sb_ev_decide_impl(const double*, int, int, int*, int*, const doub
                                  cudaStream_t);
 extern "C" int sb_converged_impl(const double*, int, double, double*, int*, int, cudaStream_t);
 
+long long sb_launch_counter = 0;
+
 namespace {
 
 __global__ void diff_kernel(const double* __restrict__ x, const double* __restrict__ x0,
@@ -75,6 +77,8 @@ extern "C" {
 
 int sb_version(void) { return 1; }
 
+long long sb_launch_count(void) { return sb_launch_counter; }
+
 int sb_device_sms(void) {
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
@@ -99,9 +103,11 @@ int sb_quadratic_pes(const double* A, const double* xstar, const double* x, doub
     if (batch <= 0 || n <= 0) return -1;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid((n + 255) / 256, batch);
+    SB_COUNT(1);
     diff_kernel<<<grid, 256, 0, st>>>(x, xstar, dwork, active, n);
     int rc = sb_hv_impl(A, dwork, g, active, batch, n, 1, 0, st);
     if (rc) return rc;
+    SB_COUNT(1);
     dot_kernel<<<batch, 256, 0, st>>>(dwork, g, f, 0.5, active, n);
     return SB_LAUNCH_CHECK();
 }

@@ -111,5 +111,9 @@ __device__ __forceinline__ void sb_block_sum2(double& a, double& b, double* scra
 }
 #define SB_SCRATCH_DOUBLES 68
 
+// number of kernels this library has launched (reported by bench.py as gpu_launches)
+extern "C" long long sb_launch_counter;
+#define SB_COUNT(k) (sb_launch_counter += (k))
+
 static inline int sb_check(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }
 #define SB_LAUNCH_CHECK() sb_check(cudaGetLastError())

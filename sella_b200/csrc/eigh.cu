@@ -352,12 +352,14 @@ extern "C" int sb_eigh_impl(const double* A, double* evals, double* Vt, double* 
     {
         const size_t smem = (size_t)(5 * n + SB_SCRATCH_DOUBLES) * sizeof(double);
         cudaFuncSetAttribute(tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        SB_COUNT(1);
         tridiag_kernel<<<batch, EIG_THREADS, smem, st>>>(work, d, e, tau, active, n);
     }
     {
         int threads = EIG_THREADS;
         size_t smem = (size_t)(threads / 32) * n * sizeof(double);
         cudaFuncSetAttribute(formqt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        SB_COUNT(1);
         formqt_kernel<<<batch, threads, smem, st>>>(work, tau, Vt, active, n);
     }
     {
@@ -368,17 +370,18 @@ extern "C" int sb_eigh_impl(const double* A, double* evals, double* Vt, double* 
         if (threads < 32) threads = 32;
         const size_t smem = (size_t)4 * n * sizeof(double);
         switch (cpt) {
-            case 1: ql_kernel<1><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
-            case 2: ql_kernel<2><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
-            case 3: ql_kernel<3><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
-            case 4: ql_kernel<4><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
-            case 5: case 6: ql_kernel<6><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
-            case 7: case 8: ql_kernel<8><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
+            case 1: SB_COUNT(1); ql_kernel<1><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
+            case 2: SB_COUNT(1); ql_kernel<2><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
+            case 3: SB_COUNT(1); ql_kernel<3><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
+            case 4: SB_COUNT(1); ql_kernel<4><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
+            case 5: case 6: SB_COUNT(1); ql_kernel<6><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
+            case 7: case 8: SB_COUNT(1); ql_kernel<8><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
             default: return -2;  // n > 2048 not supported by this build
         }
     }
     {
         const size_t smem = (size_t)n * (sizeof(double) + 2 * sizeof(int));
+        SB_COUNT(1);
         sort_kernel<<<batch, EIG_THREADS, smem, st>>>(d, evals, Vt, active, n);
     }
     return SB_LAUNCH_CHECK();

@@ -332,17 +332,20 @@ int launch_hv(const double* A, const double* X, double* Y, const int* active, in
               int ldv, cudaStream_t st) {
     query_device();
     if ((n & 1) || n < 16) {
+        SB_COUNT(1);
         hv_ldg_kernel<NV><<<batch, 256, 0, st>>>(A, X, Y, active, batch, n, ldv);
         return SB_LAUNCH_CHECK();
     }
     HvPlan p = plan_hv(n, NV, false);
     if (p.smem > (size_t)g_smem_optin) {
+        SB_COUNT(1);
         hv_ldg_kernel<NV><<<batch, 256, 0, st>>>(A, X, Y, active, batch, n, ldv);
         return SB_LAUNCH_CHECK();
     }
     cudaFuncSetAttribute(hv_tma_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     const long long ntiles = (long long)batch * ((n + p.rows - 1) / p.rows);
     const int grid = (int)(ntiles < g_sms ? ntiles : g_sms);
+    SB_COUNT(1);
     hv_tma_kernel<NV><<<grid, HV_THREADS, p.smem, st>>>(A, X, Y, active, batch, n, ldv, p.rows, p.stages);
     return SB_LAUNCH_CHECK();
 }
@@ -354,11 +357,13 @@ int launch_hvt(const double* A, const double* C, double* Y, const int* active, i
     const bool tma_ok = !(n & 1) && n >= 16 && (n / 2) <= 4 * (NCW * 32);
     HvPlan p = plan_hv(n, NV, true);
     if (!tma_ok || p.smem > (size_t)g_smem_optin) {
+        SB_COUNT(1);
         hvt_ldg_kernel<NV><<<batch, 256, 0, st>>>(A, C, Y, active, batch, n, ldv);
         return SB_LAUNCH_CHECK();
     }
     cudaFuncSetAttribute(hvt_tma_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     const int grid = batch < g_sms ? batch : g_sms;
+    SB_COUNT(1);
     hvt_tma_kernel<NV><<<grid, HV_THREADS, p.smem, st>>>(A, C, Y, active, batch, n, ldv, p.rows, p.stages);
     return SB_LAUNCH_CHECK();
 }

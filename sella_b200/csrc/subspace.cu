@@ -586,6 +586,7 @@ extern "C" int sb_mgs_impl(double* X, int nx, const double* Y, double* Ywork, in
                            cudaStream_t st) {
     const size_t smem = (size_t)(n + SB_SCRATCH_DOUBLES) * sizeof(double);
     cudaFuncSetAttribute(mgs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SB_COUNT(1);
     mgs_kernel<<<batch, SS_THREADS, smem, st>>>(X, nx, Y, Ywork, ny, n, eps1, eps2, maxiter, nkept, status,
                                                 active);
     return SB_LAUNCH_CHECK();
@@ -596,6 +597,7 @@ extern "C" int sb_davidson_init_impl(const double* v0, const double* pl, const d
                                      int* status, const int* part, int batch, cudaStream_t st) {
     const size_t smem = (size_t)(n + SB_SCRATCH_DOUBLES) * sizeof(double);
     cudaFuncSetAttribute(davidson_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SB_COUNT(1);
     davidson_init_kernel<<<batch, SS_THREADS, smem, st>>>(v0, pl, Pvt, mode, V, kcap, n, ksz, ninit, nhist,
                                                           dav_state, status, part);
     return SB_LAUNCH_CHECK();
@@ -606,6 +608,7 @@ extern "C" int sb_davidson_rr_impl(double* V, double* AV, int kcap, const int* k
                                    int* status, int batch, cudaStream_t st) {
     const size_t smem = sizeof(RRShared);
     cudaFuncSetAttribute(rr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SB_COUNT(1);
     rr_kernel<<<batch, SS_THREADS, smem, st>>>(V, AV, kcap, ksz, n, gamma, maxiter_eff, lams, rv, theta,
                                                dav_state, status);
     return SB_LAUNCH_CHECK();
@@ -613,6 +616,7 @@ extern "C" int sb_davidson_rr_impl(double* V, double* AV, int kcap, const int* k
 
 extern "C" int sb_davidson_jd_coeff_impl(const double* rvhat, const double* pl, const double* theta, double* that,
                                          int n, int method, const int* dav_state, int batch, cudaStream_t st) {
+    SB_COUNT(1);
     jd_coeff_kernel<<<batch, SS_THREADS, 0, st>>>(rvhat, pl, theta, that, n, method, dav_state);
     return SB_LAUNCH_CHECK();
 }
@@ -623,6 +627,7 @@ extern "C" int sb_davidson_expand_impl(const double* tin, const double* rv, cons
                                        cudaStream_t st) {
     const size_t smem = (size_t)n * sizeof(double) + sizeof(ExpShared);
     cudaFuncSetAttribute(expand_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SB_COUNT(1);
     expand_finish_kernel<<<batch, SS_THREADS, smem, st>>>(tin, rv, theta, V, Ywork, kcap, ksz, n, p_identity,
                                                           lanczos, vnew, dav_state, status);
     return SB_LAUNCH_CHECK();
@@ -631,6 +636,7 @@ extern "C" int sb_davidson_expand_impl(const double* tin, const double* rv, cons
 extern "C" int sb_hvp_prepare_impl(const double* vfull, long long vstride, const double* x0, const double* g0,
                                    double eta, double* xdisp, double* signnorm, int n, const int* mask,
                                    int maskval, int batch, cudaStream_t st) {
+    SB_COUNT(1);
     hvp_prepare_kernel<<<batch, SS_THREADS, 0, st>>>(vfull, (size_t)vstride, x0, g0, eta, xdisp, signnorm, n, mask,
                                                      maskval);
     return SB_LAUNCH_CHECK();
@@ -640,6 +646,7 @@ extern "C" int sb_hvp_finish_impl(const double* vfull, long long vstride, const 
                                   const double* signnorm, double eta, double* AV, double* Vs, double* AVs,
                                   int kcap, int* ksz, int* nhist, int n, const int* mask, int maskval, int batch,
                                   cudaStream_t st) {
+    SB_COUNT(1);
     hvp_finish_kernel<<<batch, SS_THREADS, 0, st>>>(vfull, (size_t)vstride, gplus, g0, signnorm, eta, AV, Vs, AVs,
                                                     kcap, ksz, nhist, n, mask, maskval);
     return SB_LAUNCH_CHECK();
@@ -649,6 +656,7 @@ extern "C" int sb_history_ritz_impl(double* Vs, double* AVs, int kcap, const int
                                     const int* dav_state, int* status, int batch, cudaStream_t st) {
     const size_t smem = sizeof(RRShared);
     cudaFuncSetAttribute(history_ritz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SB_COUNT(1);
     history_ritz_kernel<<<batch, SS_THREADS, smem, st>>>(Vs, AVs, kcap, nhist, n, nvec_out, dav_state, status);
     return SB_LAUNCH_CHECK();
 }

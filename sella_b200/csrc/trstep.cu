@@ -301,6 +301,7 @@ extern "C" int sb_qn_tr_impl(const double* Vg, const double* evals, const double
                              cudaStream_t st) {
     const size_t smem = (size_t)(2 * n + SB_SCRATCH_DOUBLES) * sizeof(double);
     cudaFuncSetAttribute(qn_tr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SB_COUNT(1);
     qn_tr_kernel<<<batch, TR_THREADS, smem, st>>>(Vg, evals, delta, order, n, coef, smag, alpha, status, active);
     return SB_LAUNCH_CHECK();
 }
@@ -310,6 +311,7 @@ extern "C" int sb_qn_ras_impl(const double* Vg, const double* evals, const doubl
                               const int* active, int batch, cudaStream_t st) {
     const size_t smem = (size_t)(6 * n + SB_SCRATCH_DOUBLES) * sizeof(double);
     cudaFuncSetAttribute(qn_ras_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SB_COUNT(1);
     qn_ras_kernel<<<batch, TR_THREADS, smem, st>>>(Vg, evals, Vt, delta, order, n, s, smag, alpha, status, active);
     return SB_LAUNCH_CHECK();
 }
@@ -317,6 +319,7 @@ extern "C" int sb_qn_ras_impl(const double* Vg, const double* evals, const doubl
 extern "C" int sb_axpy_impl(const double* x, const double* s, double* out, int n, const int* active, int batch,
                             cudaStream_t st) {
     dim3 grid((n + 255) / 256, batch);
+    SB_COUNT(1);
     axpy_kernel<<<grid, 256, 0, st>>>(x, s, out, n, active);
     return SB_LAUNCH_CHECK();
 }
@@ -328,6 +331,7 @@ extern "C" int sb_kick_finish_impl(double* x, double* f, double* g, const double
     StepParams P;
     P.rho_inc = dpar[0]; P.rho_dec = dpar[1]; P.sigma_inc = dpar[2]; P.sigma_dec = dpar[3]; P.delta_min = dpar[4];
     P.order = ipar[0]; P.eig = ipar[1]; P.nsteps_per_diag = ipar[2]; P.diag_every_n = ipar[3];
+    SB_COUNT(1);
     kick_finish_kernel<<<batch, TR_THREADS, 0, st>>>(x, f, g, xnew, fnew, gnew, s, Bs, smag, dg, delta, rho,
                                                      nsteps, P, n, active);
     return SB_LAUNCH_CHECK();
@@ -339,12 +343,14 @@ extern "C" int sb_ev_decide_impl(const double* evals, int n, int has_evals, int*
     StepParams P;
     P.rho_inc = dpar[0]; P.rho_dec = dpar[1]; P.sigma_inc = dpar[2]; P.sigma_dec = dpar[3]; P.delta_min = dpar[4];
     P.order = ipar[0]; P.eig = ipar[1]; P.nsteps_per_diag = ipar[2]; P.diag_every_n = ipar[3];
+    SB_COUNT(1);
     ev_decide_kernel<<<(batch + 127) / 128, 128, 0, st>>>(evals, n, has_evals, since_diag, ev, P, batch, active);
     return SB_LAUNCH_CHECK();
 }
 
 extern "C" int sb_converged_impl(const double* g, int n, double fmax_tol, double* fmax_out, int* conv, int batch,
                                  cudaStream_t st) {
+    SB_COUNT(1);
     converged_kernel<<<batch, TR_THREADS, 0, st>>>(g, n, fmax_tol, fmax_out, conv);
     return SB_LAUNCH_CHECK();
 }

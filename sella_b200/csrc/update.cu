@@ -295,6 +295,7 @@ extern "C" int sb_update_prep_impl(const double* S, const double* Y, double* Yti
                                    const int* active, int batch, cudaStream_t st) {
     const size_t smem = sizeof(PrepShared);
     cudaFuncSetAttribute(update_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SB_COUNT(1);
     update_prep_kernel<<<batch, UP_THREADS, smem, st>>>(S, Y, Ytil, kcap, kvec, n, ncart, first, lam0, skip,
                                                         status, active);
     return SB_LAUNCH_CHECK();
@@ -303,6 +304,7 @@ extern "C" int sb_update_prep_impl(const double* S, const double* Y, double* Yti
 extern "C" int sb_fill_scaled_identity_impl(double* B, double* evals, double* Vt, const double* lam0, int n,
                                             int ncart, const int* skip, int batch, cudaStream_t st) {
     dim3 grid((unsigned)(((size_t)n * n + 255) / 256), batch);
+    SB_COUNT(1);
     fill_scaled_identity_kernel<<<grid, 256, 0, st>>>(B, evals, Vt, lam0, n, ncart, skip);
     return SB_LAUNCH_CHECK();
 }
@@ -310,6 +312,7 @@ extern "C" int sb_fill_scaled_identity_impl(double* B, double* evals, double* Vt
 extern "C" int sb_abs_scale_impl(const double* VtS, const double* evals, double* out, int kcap, int n,
                                  const int* skip, int batch, cudaStream_t st) {
     dim3 grid((unsigned)(((size_t)kcap * n + 255) / 256), batch);
+    SB_COUNT(1);
     abs_scale_kernel<<<grid, 256, 0, st>>>(VtS, evals, out, kcap, n, skip);
     return SB_LAUNCH_CHECK();
 }
@@ -319,6 +322,7 @@ extern "C" int sb_update_mid_impl(const double* S, const double* Ytil, const dou
                                   int method, const int* skip, int* status, int batch, cudaStream_t st) {
     const size_t smem = sizeof(MidShared);
     cudaFuncSetAttribute(update_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SB_COUNT(1);
     update_mid_kernel<<<batch, UP_THREADS, smem, st>>>(S, Ytil, BS, aBS, U, J, W, Xw, kcap, kvec, n, method,
                                                        skip, status);
     return SB_LAUNCH_CHECK();
@@ -329,6 +333,7 @@ extern "C" int sb_update_apply_impl(double* B, const double* U, const double* J,
     const size_t smem = (size_t)3 * KC * n * sizeof(double);
     cudaFuncSetAttribute(update_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((n + ROWS_PER_CTA - 1) / ROWS_PER_CTA, batch);
+    SB_COUNT(1);
     update_apply_kernel<<<grid, UP_THREADS, smem, st>>>(B, U, J, W, kcap, kvec, n, skip);
     return SB_LAUNCH_CHECK();
 }
