@@ -126,9 +126,27 @@ int sb_abs_scale(const double* VtS, const double* evals, double* out, int kcap, 
                  const int32_t* skip, int batch, void* stream);
 int sb_update_mid(const double* S, const double* Ytil, const double* BS, const double* absBS,
                   double* U, double* J, double* W, double* Xwork, int kcap, const int32_t* kvec,
-                  int n, int method, const int32_t* skip, int32_t* status, int batch, void* stream);
+                  int n, int method, const int32_t* skip, int32_t* status, double* Cout, int batch,
+                  void* stream);
+/* Cout (may be NULL): [b, 32*33] receives C = J^T S (k x k, leading dimension 33).     */
 int sb_update_apply(double* B, const double* U, const double* J, const double* W, int kcap,
                     const int32_t* kvec, int n, const int32_t* skip, int batch, void* stream);
+
+/* ---- eigendecomposition update after a low-rank Hessian update -------------------
+ * Replaces the fresh scipy.linalg.eigh(B) the reference runs after every update
+ * (sella/linalg.py:293 -> 174-195) by the diagonal-plus-rank-one update of the existing
+ * eigenpairs (secular equation, LAPACK dlaed2/3/4 scheme).
+ * sb_lowrank_factor: Delta = U J^T + J U^T - U sym(C) U^T = sum_t sig[t] p_t p_t^T,
+ *   P [b, 2*kcap, n], sig [b, 2*kcap], nterm [b]; kcap <= 16.
+ * caller: Z = Vt @ P  (sb_hv_ld with nvec = 2k, ldv = 2*kcap).
+ * sb_secular_update: (evals, Vt) of B  ->  (evals, Vt) of B + Delta, in place
+ *   (evals ascending, rows of Vt = eigenvectors); work, qwork: b*n*n doubles each.   */
+int sb_lowrank_factor(const double* U, const double* J, const double* Cmat, int kcap,
+                      const int32_t* kvec, int n, double* P, double* sig, int32_t* nterm,
+                      const int32_t* skip, int batch, void* stream);
+int sb_secular_update(double* evals, double* Vt, double* Z, int zcap, const double* sig,
+                      const int32_t* nterm, int n, double* work, double* qwork, int32_t* status,
+                      const int32_t* skip, int batch, void* stream);
 
 /* ---- restricted step (sella/optimize/restricted_step.py:72-121, stepper.py:75-96) ----
  * quasi-Newton model in the eigenbasis; Vg = Vt @ g.  tr: coef with s = Vt.T @ coef;

@@ -59,7 +59,8 @@ class BatchedSella:
     def __init__(self, surface, x0, order=1, delta0=None, sigma_inc=None, sigma_dec=None,
                  rho_dec=None, rho_inc=None, eig=None, eta=1e-4, method=None, gamma=0.1,
                  rs=None, nsteps_per_diag=3, diag_every_n=None, diag_maxiter=None,
-                 eigensolver="jd0", update_method="TS-BFGS", kcap=16):
+                 eigensolver="jd0", update_method="TS-BFGS", kcap=16, eig_mode="update",
+                 eig_refresh_every=0):
         require_cuda()
         d = _DEFAULTS["minimum" if order == 0 else "saddle"]
         self.surface = surface
@@ -92,6 +93,14 @@ class BatchedSella:
         self.update_method = _UPDATE_METHODS[update_method]
         self.kcap = int(kcap)
         assert 2 <= self.kcap <= 32
+        # "update": keep (evals, Vt) current through the secular-equation update of
+        # every low-rank Hessian update (needs kcap <= 16); "direct": full eigensolve
+        # whenever the spectrum is needed (the reference's behaviour).
+        if eig_mode not in ("update", "direct"):
+            raise ValueError("eig_mode must be 'update' or 'direct'")
+        self.eig_mode = eig_mode if self.kcap <= 16 else "direct"
+        self.eig_refresh_every = int(eig_refresh_every)
+        self._updates_since_refresh = 0
 
         delta0 = d["delta0"] if delta0 is None else delta0
         delta_init = delta0 if self.rs == "ras" else delta0 * n
@@ -138,6 +147,12 @@ class BatchedSella:
         self.up1 = {k: z(b, 1, n) for k in ("Ytil", "BS", "VtS", "aC", "aBS", "U", "J", "W", "Xw")}
         self.upk = {k: z(b, kc, n) for k in ("Ytil", "BS", "VtS", "aC", "aBS", "U", "J", "W", "Xw")}
         self.lam0, self.skip = z(b), zi(b)
+        if self.eig_mode == "update":
+            self.sec1 = dict(P=z(b, 2, n), Z=z(b, 2, n), sig=z(b, 2))
+            self.seck = dict(P=z(b, 2 * kc, n), Z=z(b, 2 * kc, n), sig=z(b, 2 * kc))
+            self.Cmat = z(b, 32 * 33)
+            self.nterm = zi(b)
+            self.qwork = z(b, n, n)
         self.initialized = False
         self.ndiag = 0
 
@@ -165,13 +180,27 @@ class BatchedSella:
             call("sb_abs_scale", _p(bufs["VtS"]), _p(self.evals), _p(bufs["aC"]), I(kc), I(n), _p(self.skip),
                  I(b), _stream())
             K.hv_ld(self.Vt, bufs["aC"], bufs["aBS"], nv, transposed=True, active=active)
+        track = self.eig_mode == "update" and (self.eig_valid or first)
         call("sb_update_mid", _p(S), _p(bufs["Ytil"]), _p(bufs["BS"]),
              _p(bufs["aBS"] if self.update_method == 0 else None), _p(bufs["U"]), _p(bufs["J"]), _p(bufs["W"]),
              _p(bufs["Xw"]), I(kc), _p(kvec), I(n), I(self.update_method), _p(self.skip), _p(self.status),
-             I(b), _stream())
+             _p(self.Cmat if track else None), I(b), _stream())
         call("sb_update_apply", _p(self.B), _p(bufs["U"]), _p(bufs["J"]), _p(bufs["W"]), I(kc), _p(kvec),
              I(n), _p(self.skip), I(b), _stream())
-        self.eig_valid = False
+        self._updates_since_refresh += 1
+        if track and not (self.eig_refresh_every and self._updates_since_refresh >= self.eig_refresh_every):
+            # B+ = B + Delta: carry the eigenpairs along instead of a fresh eigensolve
+            sec = self.sec1 if kc == 1 else self.seck
+            call("sb_lowrank_factor", _p(bufs["U"]), _p(bufs["J"]), _p(self.Cmat), I(kc), _p(kvec), I(n),
+                 _p(sec["P"]), _p(sec["sig"]), _p(self.nterm), _p(self.skip), I(b), _stream())
+            K.hv_ld(self.Vt, sec["P"], sec["Z"], 2 * nv, active=active)
+            call("sb_secular_update", _p(self.evals), _p(self.Vt), _p(sec["Z"]), I(2 * kc), _p(sec["sig"]),
+                 _p(self.nterm), I(n), _p(self.eig_ws.work), _p(self.qwork), _p(self.status), _p(self.skip),
+                 I(b), _stream())
+            self.eig_valid = True
+        else:
+            self.eig_valid = False
+            self._updates_since_refresh = 0
 
     def _hvp(self, vec, vstride, mask, maskval, active):
         """One finite-difference Hessian-vector product per participating system."""
@@ -187,7 +216,7 @@ class BatchedSella:
         """PES.diag (peswrapper.py:508-556) for the systems with part[b] != 0."""
         b, n, kc = self.batch, self.n, self.kcap
         first = not self.H_initialized          # P = identity, v0 = g
-        if not first:
+        if not first and not self.eig_valid:
             self._eigh(active=part)             # spectrum of the preconditioner P = B
         call("sb_davidson_init", _p(self.g), _p(self.evals), _p(self.Vt), I(0 if first else 1), _p(self.V),
              I(kc), I(n), _p(self.ksz), _p(self.ninit), _p(self.nhist), _p(self.dav_state), _p(self.status),

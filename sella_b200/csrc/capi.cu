@@ -31,7 +31,12 @@ extern "C" int sb_fill_scaled_identity_impl(double*, double*, double*, const dou
                                             cudaStream_t);
 extern "C" int sb_abs_scale_impl(const double*, const double*, double*, int, int, const int*, int, cudaStream_t);
 extern "C" int sb_update_mid_impl(const double*, const double*, const double*, const double*, double*, double*,
-                                  double*, double*, int, const int*, int, int, const int*, int*, int, cudaStream_t);
+                                  double*, double*, int, const int*, int, int, const int*, int*, double*, int,
+                                  cudaStream_t);
+extern "C" int sb_lowrank_factor_impl(const double*, const double*, const double*, int, const int*, int, double*,
+                                      double*, int*, const int*, int, cudaStream_t);
+extern "C" int sb_secular_update_impl(double*, double*, double*, int, const double*, const int*, int, double*,
+                                      double*, int*, const int*, int, cudaStream_t);
 extern "C" int sb_update_apply_impl(double*, const double*, const double*, const double*, int, const int*, int,
                                     const int*, int, cudaStream_t);
 extern "C" int sb_qn_tr_impl(const double*, const double*, const double*, int, int, double*, double*, double*, int*,
@@ -180,10 +185,21 @@ int sb_abs_scale(const double* VtS, const double* evals, double* out, int kcap, 
 }
 int sb_update_mid(const double* S, const double* Ytil, const double* BS, const double* absBS, double* U, double* J,
                   double* W, double* Xwork, int kcap, const int32_t* kvec, int n, int method, const int32_t* skip,
-                  int32_t* status, int batch, void* stream) {
+                  int32_t* status, double* Cout, int batch, void* stream) {
     if (method < 0 || method > 2 || kcap > 32) return -1;
     if (method == 0 && !absBS) return -1;
-    return sb_update_mid_impl(S, Ytil, BS, absBS, U, J, W, Xwork, kcap, kvec, n, method, skip, status, batch, ST);
+    return sb_update_mid_impl(S, Ytil, BS, absBS, U, J, W, Xwork, kcap, kvec, n, method, skip, status, Cout, batch,
+                              ST);
+}
+int sb_lowrank_factor(const double* U, const double* J, const double* Cmat, int kcap, const int32_t* kvec, int n,
+                      double* P, double* sig, int32_t* nterm, const int32_t* skip, int batch, void* stream) {
+    if (kcap < 1 || kcap > 16) return -1;
+    return sb_lowrank_factor_impl(U, J, Cmat, kcap, kvec, n, P, sig, nterm, skip, batch, ST);
+}
+int sb_secular_update(double* evals, double* Vt, double* Z, int zcap, const double* sig, const int32_t* nterm,
+                      int n, double* work, double* qwork, int32_t* status, const int32_t* skip, int batch,
+                      void* stream) {
+    return sb_secular_update_impl(evals, Vt, Z, zcap, sig, nterm, n, work, qwork, status, skip, batch, ST);
 }
 int sb_update_apply(double* B, const double* U, const double* J, const double* W, int kcap, const int32_t* kvec,
                     int n, const int32_t* skip, int batch, void* stream) {

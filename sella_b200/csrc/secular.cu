@@ -1,0 +1,496 @@
+// Eigendecomposition UPDATE of the approximate Hessian after a low-rank secant
+// update:  B+ = B + Delta,  Delta = U J^T + J U^T - U C_sym U^T  (rank <= 2k).
+//
+// The reference recomputes scipy.linalg.eigh(B) from scratch after every update
+// (sella/linalg.py:293 -> 174-195; 10 n^3 flops, its single biggest per-step cost).
+// Given B = V diag(d) V^T this file instead applies the classical
+// "diagonal plus rank-one" machinery (Bunch-Nielsen-Sorensen 1978; the merge step of
+// LAPACK's divide & conquer, dlaed2/dlaed4/dlaed3, with the Gu-Eisenstat recomputed
+// z-vector for orthogonality):
+//
+//   1. lowrank_factor : Delta = sum_t sigma_t p_t p_t^T with orthonormal p_t
+//                       (Gram matrix of [U J], small symmetric eigenproblems);
+//   2. (hv.cu)        : z_t = V^T p_t for all terms in one pass over Vt;
+//   3. secular_update : for each term: deflation (negligible z_i, or nearly equal
+//                       d_i, d_j combined by a plane rotation of two eigenvectors),
+//                       roots of 1 + rho sum z_i^2/(d_i - lambda) = 0 for the rest,
+//                       z recomputed from the roots, new eigenvectors
+//                       V_nd <- V_nd Qhat; finally eigenvalues sorted ascending and the
+//                       rows of Vt permuted in place.
+//
+// Quasi-Newton Hessians are "scaled identity + low rank": almost everything deflates
+// and an update costs a few passes over Vt instead of a full eigensolve.  The result
+// is the eigendecomposition of the same matrix, to rounding.
+#include "small_dense.cuh"
+
+namespace {
+
+constexpr int SEC_THREADS = 256;
+constexpr double SEC_EPS = 2.220446049250313e-16;
+
+struct FactorShared {
+    double G[SB_KMAT], E[SB_KMAT], K[SB_KMAT], Y[SB_KMAT], Mc[SB_KMAT], T[SB_KMAT], A[SB_KMAT];
+    double w[SB_KMAX], sg[SB_KMAX];
+    int perm[SB_KMAX];
+    int rank;
+};
+
+// F = [U_0..U_{k-1}, J_0..J_{k-1}] (2k vectors, 2k <= 32).  P[b,t,:] = p_t, sig[b,t],
+// nterm[b].  Cmat: k x k (ld SB_KLD) = J^T S as written by update_mid.
+__global__ void __launch_bounds__(SEC_THREADS)
+lowrank_factor_kernel(const double* __restrict__ U_, const double* __restrict__ J_, const double* __restrict__ Cmat_,
+                      int kcap, const int* __restrict__ kvec, int n, double* __restrict__ P_, double* __restrict__ sig_,
+                      int* __restrict__ nterm, const int* __restrict__ skip) {
+    const int b = blockIdx.x;
+    if (skip[b]) { if (threadIdx.x == 0) nterm[b] = 0; return; }
+    extern __shared__ unsigned char raw[];
+    FactorShared& S = *reinterpret_cast<FactorShared*>(raw);
+    const int k = kvec ? kvec[b] : 1;
+    const int m = 2 * k;
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    const double* U = U_ + (size_t)b * kcap * n;
+    const double* J = J_ + (size_t)b * kcap * n;
+    const double* C = Cmat_ + (size_t)b * SB_KMAT;
+    double* P = P_ + (size_t)b * 2 * kcap * n;
+    auto F = [&](int a) { return a < k ? U + (size_t)a * n : J + (size_t)(a - k) * n; };
+    // Gram matrix of F
+    for (int pr = warp; pr < m * m; pr += nw) {
+        const int i = pr / m, j = pr % m;
+        if (j < i) continue;
+        const double* x = F(i);
+        const double* y = F(j);
+        double acc = 0.0;
+        for (int e = lane; e < n; e += 32) acc = fma(x[e], y[e], acc);
+        acc = sb_warp_sum(acc);
+        if (lane == 0) { S.G[i * SB_KLD + j] = acc; S.G[j * SB_KLD + i] = acc; }
+    }
+    // Mc = [[-C_sym, I], [I, 0]]
+    for (int idx = tid; idx < m * m; idx += nt) {
+        const int i = idx / m, j = idx % m;
+        double v = 0.0;
+        if (i < k && j < k) v = -0.5 * (C[i * SB_KLD + j] + C[j * SB_KLD + i]);
+        else if (i < k && j == i + k) v = 1.0;
+        else if (j < k && i == j + k) v = 1.0;
+        S.Mc[i * SB_KLD + j] = v;
+    }
+    __syncthreads();
+    if (warp == 0) sbs_jacobi_warp(S.G, m, S.E, S.w, S.perm);     // G = E diag(w) E^T, ascending
+    __syncthreads();
+    if (tid == 0) {
+        // keep directions with w_i > tol * w_max (numerical rank of F)
+        const double wmax = S.w[m - 1];
+        int lo = 0;
+        while (lo < m && !(S.w[lo] > 1e-24 * wmax && S.w[lo] > 0.0)) ++lo;
+        const int r = m - lo;
+        S.rank = r;
+        // T = D^{1/2} E^T restricted: T[i][a] = sqrt(w_{lo+i}) E[a][lo+i]
+        for (int i = 0; i < r; ++i)
+            for (int a = 0; a < m; ++a) S.T[i * SB_KLD + a] = sqrt(S.w[lo + i]) * S.E[a * SB_KLD + lo + i];
+        // K = T Mc T^T
+        for (int i = 0; i < r; ++i)
+            for (int bq = 0; bq < m; ++bq) {
+                double acc = 0.0;
+                for (int a = 0; a < m; ++a) acc += S.T[i * SB_KLD + a] * S.Mc[a * SB_KLD + bq];
+                S.A[i * SB_KLD + bq] = acc;
+            }
+        for (int i = 0; i < r; ++i)
+            for (int j = 0; j < r; ++j) {
+                double acc = 0.0;
+                for (int bq = 0; bq < m; ++bq) acc += S.A[i * SB_KLD + bq] * S.T[j * SB_KLD + bq];
+                S.K[i * SB_KLD + j] = acc;
+            }
+        for (int i = 0; i < r; ++i)
+            for (int j = i + 1; j < r; ++j) {
+                const double v = 0.5 * (S.K[i * SB_KLD + j] + S.K[j * SB_KLD + i]);
+                S.K[i * SB_KLD + j] = v; S.K[j * SB_KLD + i] = v;
+            }
+        // orthonormal basis coefficients: q_i = sum_a F_a E[a][lo+i] / sqrt(w)  -> keep in T
+        for (int i = 0; i < r; ++i)
+            for (int a = 0; a < m; ++a) S.T[i * SB_KLD + a] = S.E[a * SB_KLD + lo + i] / sqrt(S.w[lo + i]);
+    }
+    __syncthreads();
+    const int r = S.rank;
+    if (r == 0) { if (tid == 0) nterm[b] = 0; return; }
+    if (warp == 0) sbs_jacobi_warp(S.K, r, S.Y, S.sg, S.perm);    // K = Y diag(sg) Y^T
+    __syncthreads();
+    // p_t = sum_i Y[i][t] q_i = sum_a F_a (sum_i T[i][a] Y[i][t])   -> A[a][t]
+    for (int idx = tid; idx < m * r; idx += nt) {
+        const int a = idx / r, t = idx % r;
+        double acc = 0.0;
+        for (int i = 0; i < r; ++i) acc += S.T[i * SB_KLD + a] * S.Y[i * SB_KLD + t];
+        S.A[a * SB_KLD + t] = acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < n; e += nt) {
+        double f[SB_KMAX];
+        for (int a = 0; a < m; ++a) f[a] = F(a)[e];
+        for (int t = 0; t < r; ++t) {
+            double acc = 0.0;
+            for (int a = 0; a < m; ++a) acc = fma(f[a], S.A[a * SB_KLD + t], acc);
+            P[(size_t)t * n + e] = acc;
+        }
+    }
+    if (tid < r) sig_[(size_t)b * 2 * kcap + tid] = S.sg[tid];
+    if (tid == 0) nterm[b] = r;
+}
+
+// ------------------------------------------------------------------------------
+// One secular root of  f(lam) = 1 + rho * sum_i y_i^2 / (e_i - lam),  rho > 0,
+// e ascending, in (e_j, e_{j+1})  (j = r-1: (e_{r-1}, e_{r-1} + rho*|y|^2)).
+// Returns the pole index `org` and the offset mu with lam = e[org] + mu.
+__device__ void secular_root(const double* __restrict__ e, const double* __restrict__ y2, int r, double rho, int j,
+                             double ysum, int* org_out, double* mu_out) {
+    const double left = e[j];
+    const double gap = (j + 1 < r) ? (e[j + 1] - e[j]) : rho * ysum;
+    // decide the origin from the sign of f at the midpoint
+    int org = j;
+    if (j + 1 < r) {
+        const double mid = 0.5 * gap;
+        double fm = 1.0;
+        for (int i = 0; i < r; ++i) fm += rho * y2[i] / ((e[i] - left) - mid);
+        if (fm < 0.0) org = j + 1;         // root in the right half: measure from e_{j+1}
+    }
+    const double eo = e[org];
+    // bracket in mu
+    double lo, hi;
+    if (org == j) { lo = 0.0; hi = (j + 1 < r) ? 0.5 * gap : gap; }
+    else { lo = -0.5 * gap; hi = 0.0; }
+    // f is increasing in mu on the bracket; f(lo+) < 0 < f(hi-) (open ends are poles /
+    // bounds).  Safeguarded Newton with (geometric) bisection fallback.
+    double mu = (org == j) ? ((j + 1 < r) ? 0.25 * gap : 0.5 * gap) : -0.25 * gap;
+    for (int it = 0; it < 200; ++it) {
+        double f = 1.0, df = 0.0;
+        for (int i = 0; i < r; ++i) {
+            const double den = (e[i] - eo) - mu;
+            const double q = y2[i] / den;
+            f += rho * q;
+            df += rho * q / den;
+        }
+        if (f == 0.0) break;
+        if (f < 0.0) lo = mu; else hi = mu;
+        double next = mu - f / df;
+        if (!(next > lo && next < hi)) {
+            // bisection; geometric when the bracket spans orders of magnitude next to the pole
+            if (org == j) {
+                if (lo > 0.0 && hi > 4.0 * lo) next = sqrt(lo) * sqrt(hi);
+                else if (lo == 0.0) next = (hi > 1e-290) ? hi * 0.0625 : 0.5 * hi;
+                else next = 0.5 * (lo + hi);
+            } else {
+                if (hi < 0.0 && lo < 4.0 * hi) next = -sqrt(-lo) * sqrt(-hi);
+                else if (hi == 0.0) next = (lo < -1e-290) ? lo * 0.0625 : 0.5 * lo;
+                else next = 0.5 * (lo + hi);
+            }
+        }
+        if (fabs(next - mu) <= 2.0 * SEC_EPS * fabs(next) || next == mu) { mu = next; break; }
+        mu = next;
+        if (hi - lo <= 2.0 * SEC_EPS * fmax(fabs(lo), fabs(hi))) break;
+    }
+    *org_out = org;
+    *mu_out = mu;
+}
+
+struct SecShared {
+    double scratch[SB_SCRATCH_DOUBLES];
+    int r, nrot, flag;
+    double rho;
+};
+
+// Sequential application of `nrot` plane rotations (rows ia[q], ib[q] of Vt):
+//   x' = c x + s y ;  y' = c y - s x        (LAPACK drot on the two eigenvectors)
+template <int CPT>
+__device__ void apply_rotations(double* __restrict__ Vt, int n, const int* __restrict__ ia, const int* __restrict__ ib,
+                                const double* __restrict__ rc, const double* __restrict__ rs, int nrot) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double carry[CPT];
+    int carried = -1;
+    for (int q = 0; q < nrot; ++q) {
+        const int a = ia[q], bb = ib[q];
+        const double c = rc[q], s = rs[q];
+        if (carried != a) {
+            if (carried >= 0) {
+#pragma unroll
+                for (int u = 0; u < CPT; ++u) { const int col = tid + u * nt; if (col < n) Vt[(size_t)carried * n + col] = carry[u]; }
+            }
+#pragma unroll
+            for (int u = 0; u < CPT; ++u) { const int col = tid + u * nt; carry[u] = col < n ? Vt[(size_t)a * n + col] : 0.0; }
+        }
+#pragma unroll
+        for (int u = 0; u < CPT; ++u) {
+            const int col = tid + u * nt;
+            if (col < n) {
+                const double x = carry[u], y = Vt[(size_t)bb * n + col];
+                Vt[(size_t)a * n + col] = c * x + s * y;
+                carry[u] = c * y - s * x;
+            }
+        }
+        carried = bb;
+    }
+    if (carried >= 0) {
+#pragma unroll
+        for (int u = 0; u < CPT; ++u) { const int col = tid + u * nt; if (col < n) Vt[(size_t)carried * n + col] = carry[u]; }
+    }
+}
+
+// Applies nterm[b] rank-one updates (sig, Z = Vt P^T) to (evals, Vt).
+// Zs: [b, zcap, n] (row t = V^T p_t in the CURRENT row order of Vt), work: [b, n, n],
+// qwork: [b, n, n].  On exit evals ascending, Vt rows permuted accordingly.
+template <int CPT>
+__global__ void __launch_bounds__(SEC_THREADS)
+secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, double* __restrict__ Z_, int zcap,
+                      const double* __restrict__ sig_, const int* __restrict__ nterm, int n,
+                      double* __restrict__ work_, double* __restrict__ qwork_, int* __restrict__ status,
+                      const int* __restrict__ skip) {
+    const int b = blockIdx.x;
+    if (skip[b]) return;
+    const int nterms = nterm[b];
+    if (nterms == 0) return;
+    extern __shared__ double sm[];
+    SecShared& S = *reinterpret_cast<SecShared*>(sm);
+    double* d = sm + (sizeof(SecShared) + 7) / 8;   // current eigenvalues, row order
+    double* z = d + n;               // current z, row order
+    double* dd = z + n;              // non-deflated poles (ascending; mirrored when rho<0)
+    double* y2 = dd + n;             // squared weights of the non-deflated
+    double* zh = y2 + n;             // recomputed z (Gu-Eisenstat)
+    double* mu = zh + n;             // root offsets
+    double* rc = mu + n;             // rotation cosines
+    double* rs = rc + n;             // rotation sines
+    int* ord = reinterpret_cast<int*>(rs + n);   // sorted position -> row
+    int* nd = ord + n;               // non-deflated rows, ascending d
+    int* org = nd + n;               // origin pole index of each root
+    int* ia = org + n;               // rotation row a
+    int* ib = ia + n;                // rotation row b
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double* Vt = Vt_ + (size_t)b * n * n;
+    double* Z = Z_ + (size_t)b * zcap * n;
+    double* work = work_ + (size_t)b * n * n;
+    double* Qh = qwork_ + (size_t)b * n * n;
+
+    for (int i = tid; i < n; i += nt) { d[i] = evals_[(size_t)b * n + i]; ord[i] = i; }   // sorted on entry
+    __syncthreads();
+
+    for (int t = 0; t < nterms; ++t) {
+        double* zt = Z + (size_t)t * n;
+        double acc = 0.0;
+        for (int i = tid; i < n; i += nt) { const double v = zt[i]; z[i] = v; acc = fma(v, v, acc); }
+        const double znorm2 = sb_block_sum(acc, S.scratch);
+        double rho = sig_[(size_t)b * zcap + t] * znorm2;
+        if (znorm2 == 0.0 || rho == 0.0) continue;
+        const double zinv = 1.0 / sqrt(znorm2);
+        double dmax = 0.0, zmax = 0.0;
+        for (int i = tid; i < n; i += nt) { z[i] *= zinv; dmax = fmax(dmax, fabs(d[i])); zmax = fmax(zmax, fabs(z[i])); }
+        dmax = sb_warp_max(dmax); zmax = sb_warp_max(zmax);
+        __syncthreads();
+        if ((tid & 31) == 0) { S.scratch[40 + (tid >> 5)] = dmax; S.scratch[52 + (tid >> 5)] = zmax; }
+        __syncthreads();
+        dmax = 0.0; zmax = 0.0;
+        for (int w = 0; w < nt / 32; ++w) { dmax = fmax(dmax, S.scratch[40 + w]); zmax = fmax(zmax, S.scratch[52 + w]); }
+        const double tol = 8.0 * SEC_EPS * fmax(dmax, fabs(rho));
+        if (fabs(rho) * zmax <= tol) continue;          // the whole term is negligible
+        // ---------------- deflation (serial scan in ascending order of d)
+        if (tid == 0) {
+            int r = 0, nrot = 0, prev = -1;
+            for (int p = 0; p < n; ++p) {
+                const int i = ord[p];
+                if (fabs(rho * z[i]) <= tol) continue;              // eigenpair unchanged
+                if (prev < 0) { prev = i; continue; }
+                double s = z[prev], c = z[i];
+                const double tau = hypot(c, s);
+                const double tt = d[i] - d[prev];
+                c /= tau; s = -s / tau;
+                if (fabs(tt * c * s) <= tol) {
+                    z[i] = tau; z[prev] = 0.0;
+                    ia[nrot] = prev; ib[nrot] = i; rc[nrot] = c; rs[nrot] = s; ++nrot;
+                    const double tnew = d[prev] * c * c + d[i] * s * s;
+                    d[i] = d[prev] * s * s + d[i] * c * c;
+                    d[prev] = tnew;
+                    prev = i;
+                } else {
+                    nd[r++] = prev;
+                    prev = i;
+                }
+            }
+            if (prev >= 0) nd[r++] = prev;
+            S.r = r; S.nrot = nrot; S.rho = rho;
+        }
+        __syncthreads();
+        const int r = S.r, nrot = S.nrot;
+        if (nrot > 0) {
+            apply_rotations<CPT>(Vt, n, ia, ib, rc, rs, nrot);
+            // pending z vectors of later terms see the same rotations
+            for (int s2 = t + 1 + tid; s2 < nterms; s2 += nt) {
+                double* zp = Z + (size_t)s2 * n;
+                for (int q = 0; q < nrot; ++q) {
+                    const double x = zp[ia[q]], y = zp[ib[q]];
+                    zp[ia[q]] = rc[q] * x + rs[q] * y;
+                    zp[ib[q]] = rc[q] * y - rs[q] * x;
+                }
+            }
+        }
+        __syncthreads();
+        if (r == 0) continue;
+        // non-deflated d may be slightly out of order after rotations changed d: insertion sort (r small shifts)
+        if (tid == 0) {
+            for (int a = 1; a < r; ++a) {
+                const int row = nd[a];
+                int p = a - 1;
+                while (p >= 0 && d[nd[p]] > d[row]) { nd[p + 1] = nd[p]; --p; }
+                nd[p + 1] = row;
+            }
+        }
+        __syncthreads();
+        // ---------------- secular equation on the r non-deflated poles
+        const bool neg = rho < 0.0;
+        const double arho = fabs(rho);
+        acc = 0.0;
+        for (int j = tid; j < r; j += nt) {
+            const int src = neg ? nd[r - 1 - j] : nd[j];
+            dd[j] = neg ? -d[src] : d[src];
+            const double v = z[src];
+            y2[j] = v * v;
+            acc += v * v;
+        }
+        const double ysum = sb_block_sum(acc, S.scratch);
+        for (int j = tid; j < r; j += nt) {
+            int o; double m;
+            if (r == 1) { o = 0; m = arho * y2[0]; }
+            else secular_root(dd, y2, r, arho, j, ysum, &o, &m);
+            org[j] = o; mu[j] = m;
+        }
+        __syncthreads();
+        // Gu-Eisenstat: zh_i^2 = (lam_i - dd_i)/rho * prod_{j != i} (lam_j - dd_i)/(dd_j - dd_i)
+        for (int i = tid; i < r; i += nt) {
+            double prod = ((dd[org[i]] - dd[i]) + mu[i]) / arho;
+            for (int j = 0; j < r; ++j) {
+                if (j == i) continue;
+                prod *= ((dd[org[j]] - dd[i]) + mu[j]) / (dd[j] - dd[i]);
+            }
+            const int src = neg ? nd[r - 1 - i] : nd[i];
+            zh[i] = copysign(sqrt(fabs(prod)), z[src]);
+        }
+        __syncthreads();
+        // eigenvector matrix (mirrored index space): Qh[i*r + j] = zh_i / (dd_i - lam_j), columns normalised
+        for (int j = tid; j < r; j += nt) {
+            double nrm = 0.0;
+            for (int i = 0; i < r; ++i) {
+                const double q = zh[i] / ((dd[i] - dd[org[j]]) - mu[j]);
+                Qh[(size_t)i * r + j] = q;
+                nrm = fma(q, q, nrm);
+            }
+            nrm = 1.0 / sqrt(nrm);
+            for (int i = 0; i < r; ++i) Qh[(size_t)i * r + j] *= nrm;
+        }
+        __syncthreads();
+        // ---------------- new eigenvectors: row_new(j) = sum_i Qh[i][j] row_old(i)   (mirrored index i,j)
+        {
+            auto rowof = [&](int i) { return neg ? nd[r - 1 - i] : nd[i]; };
+            constexpr int JB = 8;
+            for (int j0 = 0; j0 < r; j0 += JB) {
+                const int jb = min(JB, r - j0);
+#pragma unroll
+                for (int u = 0; u < CPT; ++u) {
+                    const int col = tid + u * nt;
+                    if (col >= n) continue;
+                    double a8[JB];
+#pragma unroll
+                    for (int q = 0; q < JB; ++q) a8[q] = 0.0;
+                    for (int i = 0; i < r; ++i) {
+                        const double x = Vt[(size_t)rowof(i) * n + col];
+                        const double* qrow = Qh + (size_t)i * r + j0;
+#pragma unroll
+                        for (int q = 0; q < JB; ++q)
+                            if (q < jb) a8[q] = fma(qrow[q], x, a8[q]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < JB; ++q)
+                        if (q < jb) work[(size_t)(j0 + q) * n + col] = a8[q];
+                }
+            }
+            __syncthreads();
+            for (int j = 0; j < r; ++j) {
+                const int row = rowof(j);
+                for (int col = tid; col < n; col += nt) Vt[(size_t)row * n + col] = work[(size_t)j * n + col];
+            }
+            // pending z vectors: z_s[row(j)] <- sum_i Qh[i][j] z_s[row(i)]
+            for (int s2 = t + 1; s2 < nterms; ++s2) {
+                double* zp = Z + (size_t)s2 * n;
+                __syncthreads();
+                for (int j = tid; j < r; j += nt) {
+                    double a = 0.0;
+                    for (int i = 0; i < r; ++i) a = fma(Qh[(size_t)i * r + j], zp[rowof(i)], a);
+                    zh[j] = a;                // reuse zh as temp (roots already consumed)
+                }
+                __syncthreads();
+                for (int j = tid; j < r; j += nt) zp[rowof(j)] = zh[j];
+            }
+            __syncthreads();
+            // new eigenvalues (undo the mirror)
+            for (int j = tid; j < r; j += nt) {
+                const double lam = dd[org[j]] + mu[j];
+                d[rowof(j)] = neg ? -lam : lam;
+            }
+        }
+        __syncthreads();
+        // ---------------- ascending order of the rows for the next term
+        for (int i = tid; i < n; i += nt) {
+            const double di = d[i];
+            int rank = 0;
+            for (int j = 0; j < n; ++j) { const double dj = d[j]; rank += (dj < di) || (dj == di && j < i); }
+            ord[rank] = i;
+        }
+        __syncthreads();
+    }
+    // ---------------- write back: evals ascending, rows of Vt permuted (new[p] = old[ord[p]])
+    for (int p = tid; p < n; p += nt) evals_[(size_t)b * n + p] = d[ord[p]];
+    int* leader = nd;           // reuse
+    for (int start = tid; start < n; start += nt) {
+        int j = ord[start];
+        int isl = (j != start);
+        while (isl && j != start) { if (j < start) isl = 0; j = ord[j]; }
+        leader[start] = isl;
+    }
+    __syncthreads();
+    for (int col = tid; col < n; col += nt) {
+        for (int start = 0; start < n; ++start) {
+            if (!leader[start]) continue;
+            const double tmp = Vt[(size_t)start * n + col];
+            int cur = start, nxt = ord[cur];
+            while (nxt != start) {
+                Vt[(size_t)cur * n + col] = Vt[(size_t)nxt * n + col];
+                cur = nxt; nxt = ord[cur];
+            }
+            Vt[(size_t)cur * n + col] = tmp;
+        }
+    }
+    (void)status;
+}
+
+}  // namespace
+
+extern "C" int sb_lowrank_factor_impl(const double* U, const double* J, const double* Cmat, int kcap, const int* kvec,
+                                      int n, double* P, double* sig, int* nterm, const int* skip, int batch,
+                                      cudaStream_t st) {
+    const size_t smem = sizeof(FactorShared);
+    cudaFuncSetAttribute(lowrank_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SB_COUNT(1);
+    lowrank_factor_kernel<<<batch, SEC_THREADS, smem, st>>>(U, J, Cmat, kcap, kvec, n, P, sig, nterm, skip);
+    return SB_LAUNCH_CHECK();
+}
+
+extern "C" int sb_secular_update_impl(double* evals, double* Vt, double* Z, int zcap, const double* sig,
+                                      const int* nterm, int n, double* work, double* qwork, int* status,
+                                      const int* skip, int batch, cudaStream_t st) {
+    const size_t smem = (size_t)n * (8 * sizeof(double) + 5 * sizeof(int)) + sizeof(SecShared) + 64;
+    const int cpt = (n + SEC_THREADS - 1) / SEC_THREADS;
+    SB_COUNT(1);
+#define SB_SEC_LAUNCH(C)                                                                                          \
+    cudaFuncSetAttribute(secular_update_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    secular_update_kernel<C><<<batch, SEC_THREADS, smem, st>>>(evals, Vt, Z, zcap, sig, nterm, n, work, qwork,  \
+                                                               status, skip)
+    if (cpt <= 1) { SB_SEC_LAUNCH(1); }
+    else if (cpt <= 2) { SB_SEC_LAUNCH(2); }
+    else if (cpt <= 4) { SB_SEC_LAUNCH(4); }
+    else if (cpt <= 8) { SB_SEC_LAUNCH(8); }
+    else return -2;
+#undef SB_SEC_LAUNCH
+    return SB_LAUNCH_CHECK();
+}

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(UP_THREADS)
 update_mid_kernel(const double* __restrict__ S_, const double* __restrict__ Yt_, const double* __restrict__ BS_,
                   const double* __restrict__ aBS_, double* __restrict__ U_, double* __restrict__ J_,
                   double* __restrict__ W_, double* __restrict__ Xw_, int kcap, const int* __restrict__ kvec, int n,
-                  int method, const int* __restrict__ skip, int* __restrict__ status) {
+                  int method, const int* __restrict__ skip, int* __restrict__ status, double* __restrict__ Cout) {
     const int b = blockIdx.x;
     if (skip[b]) return;
     extern __shared__ unsigned char raw[];
@@ -214,6 +214,9 @@ update_mid_kernel(const double* __restrict__ S_, const double* __restrict__ Yt_,
     __syncthreads();
     gram_block_u(J, S, k, k, n, M.C);             // C = J^T S
     __syncthreads();
+    if (Cout)
+        for (int i = tid; i < k * k; i += nt)
+            Cout[(size_t)b * SB_KMAT + (i / k) * SB_KLD + (i % k)] = M.C[(i / k) * SB_KLD + (i % k)];
     // W[:, c] = sum_a U[:, a] C[a][c]
     for (int e = tid; e < n; e += nt) {
         double u[SB_KMAX];
@@ -319,12 +322,13 @@ extern "C" int sb_abs_scale_impl(const double* VtS, const double* evals, double*
 
 extern "C" int sb_update_mid_impl(const double* S, const double* Ytil, const double* BS, const double* aBS,
                                   double* U, double* J, double* W, double* Xw, int kcap, const int* kvec, int n,
-                                  int method, const int* skip, int* status, int batch, cudaStream_t st) {
+                                  int method, const int* skip, int* status, double* Cout, int batch,
+                                  cudaStream_t st) {
     const size_t smem = sizeof(MidShared);
     cudaFuncSetAttribute(update_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     SB_COUNT(1);
     update_mid_kernel<<<batch, UP_THREADS, smem, st>>>(S, Ytil, BS, aBS, U, J, W, Xw, kcap, kvec, n, method,
-                                                       skip, status);
+                                                       skip, status, Cout);
     return SB_LAUNCH_CHECK();
 }
 

@@ -98,3 +98,33 @@ def mgs(X, Y=None, eps1=1e-15, eps2=1e-6, maxiter=100, active=None):
     call("sb_mgs", _p(X), I(nx), _p(Y), _p(Ywork), I(ny), I(n), D(eps1), D(eps2), I(maxiter),
          _p(nkept), _p(status), _p(_mask(active)), I(b), _stream())
     return nkept, status
+
+
+def eigh_update(evals, Vt, U, J, C, active=None):
+    """(evals, Vt) of B  ->  (evals, Vt) of B + U J^T + J U^T - U sym(C) U^T, in place.
+
+    U, J: [b, k, n] (k <= 16), C: [b, k, k].  Secular-equation update (secular.cu)."""
+    require_cuda()
+    check_f64(evals, Vt, U, J)
+    b, k, n = U.shape
+    dev = U.device
+    Cmat = torch.zeros((b, 32, 33), dtype=torch.float64, device=dev)
+    Cmat[:, :k, :k] = C
+    Cmat = Cmat.reshape(b, 32 * 33).contiguous()
+    P = torch.zeros((b, 2 * k, n), dtype=torch.float64, device=dev)
+    Z = torch.zeros_like(P)
+    sig = torch.zeros((b, 2 * k), dtype=torch.float64, device=dev)
+    nterm = torch.zeros(b, dtype=torch.int32, device=dev)
+    skip = torch.zeros(b, dtype=torch.int32, device=dev)
+    if active is not None:
+        skip = (1 - _mask(active)).to(torch.int32)
+    status = torch.zeros(b, dtype=torch.int32, device=dev)
+    work = torch.empty((b, n, n), dtype=torch.float64, device=dev)
+    qwork = torch.empty((b, n, n), dtype=torch.float64, device=dev)
+    kvec = torch.full((b,), k, dtype=torch.int32, device=dev)
+    call("sb_lowrank_factor", _p(U.contiguous()), _p(J.contiguous()), _p(Cmat), I(k), _p(kvec), I(n), _p(P),
+         _p(sig), _p(nterm), _p(skip), I(b), _stream())
+    hv_ld(Vt, P, Z, 2 * k)
+    call("sb_secular_update", _p(evals), _p(Vt), _p(Z), I(2 * k), _p(sig), _p(nterm), I(n), _p(work),
+         _p(qwork), _p(status), _p(skip), I(b), _stream())
+    return evals, Vt, status

@@ -100,3 +100,40 @@ def test_eigh_mask_leaves_inactive_untouched():
     K.eigh(to_dev(A), active=to_dev(act), evals=w0, Vt=V0)
     assert torch.all(w0[1] == -5.0) and torch.all(V0[3] == -5.0)
     np.testing.assert_allclose(w0[0].cpu().numpy(), np.linalg.eigvalsh(A[0]), atol=1e-12)
+
+
+@pytest.mark.parametrize("n,k", [(24, 1), (96, 1), (96, 3), (384, 1), (384, 5)])
+def test_eigh_update_secular(n, k):
+    """Secular-equation update of an eigendecomposition after a symmetric rank-2k
+    change, chained three times, against numpy.linalg.eigh of the updated matrix."""
+    from sella_b200 import kernels as K
+    rng = np.random.RandomState(7 * n + k)
+    b = 4
+    B = rand_sym(rng, b, n)
+    B[0] = 0.8 * np.eye(n)                          # fully degenerate start (first Sella update)
+    u = rng.normal(size=(n, 3))
+    B[1] = 0.5 * np.eye(n) + u @ np.diag([1.0, -2.0, 0.3]) @ u.T     # identity + low rank
+    w0 = np.empty((b, n)); V0 = np.empty((b, n, n))
+    for i in range(b):
+        w0[i], v = np.linalg.eigh(B[i]); V0[i] = v.T
+    evals, Vt = to_dev(w0), to_dev(V0)
+    for rep in range(3):
+        U = rng.normal(size=(b, k, n)) / np.sqrt(n)
+        J = rng.normal(size=(b, k, n)) / np.sqrt(n)
+        C = rng.normal(size=(b, k, k))
+        if rep == 1:
+            J[2] = 2.0 * U[2]                       # rank-deficient [U J]
+        Csym = 0.5 * (C + C.transpose(0, 2, 1))
+        Delta = (np.einsum("bki,bkj->bij", U, J) + np.einsum("bki,bkj->bij", J, U)
+                 - np.einsum("bki,bkl,blj->bij", U, Csym, U))
+        B = B + Delta
+        _, _, status = K.eigh_update(evals, Vt, to_dev(U), to_dev(J), to_dev(C))
+        assert int(status.abs().sum()) == 0
+        w, V = evals.cpu().numpy(), Vt.cpu().numpy()
+        for i in range(b):
+            wref = np.linalg.eigvalsh(B[i])
+            scale = max(1.0, np.abs(wref).max())
+            np.testing.assert_allclose(w[i], wref, rtol=0, atol=2e-12 * scale, err_msg="rep %d sys %d" % (rep, i))
+            Vi = V[i].T
+            np.testing.assert_allclose(Vi.T @ Vi, np.eye(n), atol=2e-12, err_msg="orth rep %d sys %d" % (rep, i))
+            np.testing.assert_allclose(B[i] @ Vi, Vi * w[i][None, :], atol=5e-12 * scale)
