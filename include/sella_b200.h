@@ -144,6 +144,9 @@ int sb_update_apply(double* B, const double* U, const double* J, const double* W
 int sb_lowrank_factor(const double* U, const double* J, const double* Cmat, int kcap,
                       const int32_t* kvec, int n, double* P, double* sig, int32_t* nterm,
                       const int32_t* skip, int batch, void* stream);
+/* diagnostic: cycles spent per phase of sb_secular_update, summed over CTAs (host array
+ * of 16 uint64; synchronises the device).                                              */
+int sb_secular_profile(unsigned long long* out16, int reset);
 int sb_secular_update(double* evals, double* Vt, double* Z, int zcap, const double* sig,
                       const int32_t* nterm, int n, double* work, double* qwork, int32_t* status,
                       const int32_t* skip, int batch, void* stream);

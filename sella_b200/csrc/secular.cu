@@ -140,37 +140,38 @@ lowrank_factor_kernel(const double* __restrict__ U_, const double* __restrict__ 
 // Returns the pole index `org` and the offset mu with lam = e[org] + mu.
 __device__ void secular_root(const double* __restrict__ e, const double* __restrict__ y2, int r, double rho, int j,
                              double ysum, int* org_out, double* mu_out) {
+    // executed by one full warp: lanes split the r terms of the secular function
+    const int lane = threadIdx.x & 31;
     const double left = e[j];
     const double gap = (j + 1 < r) ? (e[j + 1] - e[j]) : rho * ysum;
-    // decide the origin from the sign of f at the midpoint
     int org = j;
     if (j + 1 < r) {
         const double mid = 0.5 * gap;
-        double fm = 1.0;
-        for (int i = 0; i < r; ++i) fm += rho * y2[i] / ((e[i] - left) - mid);
+        double fm = 0.0;
+        for (int i = lane; i < r; i += 32) fm += rho * y2[i] / ((e[i] - left) - mid);
+        fm = 1.0 + sb_warp_sum(fm);
         if (fm < 0.0) org = j + 1;         // root in the right half: measure from e_{j+1}
     }
     const double eo = e[org];
-    // bracket in mu
     double lo, hi;
     if (org == j) { lo = 0.0; hi = (j + 1 < r) ? 0.5 * gap : gap; }
     else { lo = -0.5 * gap; hi = 0.0; }
-    // f is increasing in mu on the bracket; f(lo+) < 0 < f(hi-) (open ends are poles /
-    // bounds).  Safeguarded Newton with (geometric) bisection fallback.
+    // f is increasing in mu on the bracket; safeguarded Newton with (geometric) bisection
     double mu = (org == j) ? ((j + 1 < r) ? 0.25 * gap : 0.5 * gap) : -0.25 * gap;
     for (int it = 0; it < 200; ++it) {
-        double f = 1.0, df = 0.0;
-        for (int i = 0; i < r; ++i) {
+        double f = 0.0, df = 0.0;
+        for (int i = lane; i < r; i += 32) {
             const double den = (e[i] - eo) - mu;
             const double q = y2[i] / den;
             f += rho * q;
             df += rho * q / den;
         }
+        f = 1.0 + sb_warp_sum(f);
+        df = sb_warp_sum(df);
         if (f == 0.0) break;
         if (f < 0.0) lo = mu; else hi = mu;
         double next = mu - f / df;
         if (!(next > lo && next < hi)) {
-            // bisection; geometric when the bracket spans orders of magnitude next to the pole
             if (org == j) {
                 if (lo > 0.0 && hi > 4.0 * lo) next = sqrt(lo) * sqrt(hi);
                 else if (lo == 0.0) next = (hi > 1e-290) ? hi * 0.0625 : 0.5 * hi;
@@ -188,6 +189,17 @@ __device__ void secular_root(const double* __restrict__ e, const double* __restr
     *org_out = org;
     *mu_out = mu;
 }
+
+// optional in-kernel phase profile (cycles, summed over CTAs by thread 0)
+__device__ unsigned long long sec_prof[16];
+#define SEC_MARK(ph)                                                        \
+    do {                                                                    \
+        if (tid == 0) {                                                     \
+            const long long now_ = clock64();                               \
+            atomicAdd(&sec_prof[ph], (unsigned long long)(now_ - tmark_)); \
+            tmark_ = now_;                                                  \
+        }                                                                   \
+    } while (0)
 
 struct SecShared {
     double scratch[SB_SCRATCH_DOUBLES];
@@ -239,7 +251,7 @@ __global__ void __launch_bounds__(SEC_THREADS)
 secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, double* __restrict__ Z_, int zcap,
                       const double* __restrict__ sig_, const int* __restrict__ nterm, int n,
                       double* __restrict__ work_, double* __restrict__ qwork_, int* __restrict__ status,
-                      const int* __restrict__ skip) {
+                      const int* __restrict__ skip, int tile_doubles) {
     const int b = blockIdx.x;
     if (skip[b]) return;
     const int nterms = nterm[b];
@@ -259,12 +271,14 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
     int* org = nd + n;               // origin pole index of each root
     int* ia = org + n;               // rotation row a
     int* ib = ia + n;                // rotation row b
+    double* tile = reinterpret_cast<double*>(ib + n + (n & 1));   // staging tile for the row update
     const int tid = threadIdx.x, nt = blockDim.x;
     double* Vt = Vt_ + (size_t)b * n * n;
     double* Z = Z_ + (size_t)b * zcap * n;
     double* work = work_ + (size_t)b * n * n;
     double* Qh = qwork_ + (size_t)b * n * n;
 
+    long long tmark_ = clock64();
     for (int i = tid; i < n; i += nt) { d[i] = evals_[(size_t)b * n + i]; ord[i] = i; }   // sorted on entry
     __syncthreads();
 
@@ -286,12 +300,151 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
         for (int w = 0; w < nt / 32; ++w) { dmax = fmax(dmax, S.scratch[40 + w]); zmax = fmax(zmax, S.scratch[52 + w]); }
         const double tol = 8.0 * SEC_EPS * fmax(dmax, fabs(rho));
         if (fabs(rho) * zmax <= tol) continue;          // the whole term is negligible
-        // ---------------- deflation (serial scan in ascending order of d)
+        SEC_MARK(0);
+        // ---------------- deflation, stage 1: rows whose z is negligible keep their
+        // eigenpair; runs of (numerically) equal eigenvalues among the rest are an exact
+        // eigenspace, so ONE Householder reflection of those eigenvectors can move all
+        // of z's weight onto a single row (instead of a chain of plane rotations).
         if (tid == 0) {
-            int r = 0, nrot = 0, prev = -1;
+            int na = 0;
             for (int p = 0; p < n; ++p) {
                 const int i = ord[p];
-                if (fabs(rho * z[i]) <= tol) continue;              // eigenpair unchanged
+                if (fabs(rho * z[i]) > tol) nd[na++] = i;           // candidates, ascending d
+            }
+            int nc = 0, ncand = 0;
+            const double tolc = 8.0 * SEC_EPS * dmax;
+            int a = 0;
+            while (a < na) {
+                int e = a;
+                while (e + 1 < na && d[nd[e + 1]] - d[nd[a]] <= tolc) ++e;
+                if (e > a) { ia[nc] = a; ib[nc] = e - a + 1; ++nc; }   // cluster [a, e] in nd
+                // the survivor's eigenvalue moves up for rho > 0 and down for rho < 0: take the
+                // row at that end of the run so that it does not have to cross the cluster
+                org[ncand++] = rho > 0.0 ? nd[e] : nd[a];
+                a = e + 1;
+            }
+            S.r = ncand; S.nrot = nc; S.flag = na;
+        }
+        __syncthreads();
+        SEC_MARK(1);
+        {
+            const int nclus = S.nrot;
+            for (int c = 0; c < nclus; ++c) {
+                const int a0 = ia[c], m = ib[c];
+                const int piv = rho > 0.0 ? m - 1 : 0;
+                const int last = nd[a0 + piv];
+                // w = z_c - alpha e_piv, alpha = -sign(z_piv) |z_c|
+                double part = 0.0;
+                for (int i = tid; i < m; i += nt) { const double v = z[nd[a0 + i]]; part = fma(v, v, part); }
+                const double beta = sqrt(sb_block_sum(part, S.scratch));
+                const double zl = z[last];
+                const double alpha = zl > 0.0 ? -beta : beta;
+                const double wl = zl - alpha;
+                const double wn2 = beta * beta - zl * zl + wl * wl;
+                const double coef = 2.0 / wn2;
+                for (int i = tid; i < m; i += nt) zh[i] = (i == piv) ? wl : z[nd[a0 + i]];   // w in cluster order
+                __syncthreads();
+                // y = coef * sum_i w_i row_i ; row_i -= w_i y.   Warps own rows, lanes own
+                // columns (8 per lane and chunk): every row access is one coalesced burst
+                // and each lane keeps 8 independent loads in flight.
+                {
+                    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+                    constexpr int LPC = 8;                       // columns per lane per chunk
+                    const int chunk = 32 * LPC;
+                    double* ypart = tile;                        // [nw][chunk]
+                    double* ysum_ = tile + (size_t)nw * chunk;   // [chunk]
+                    for (int c0 = 0; c0 < n; c0 += chunk) {
+                        double yp[LPC];
+#pragma unroll
+                        for (int q = 0; q < LPC; ++q) yp[q] = 0.0;
+                        {
+                            constexpr int RU = 4;                // rows in flight per warp
+                            for (int i0 = warp; i0 < m; i0 += nw * RU) {
+                                double v[RU][LPC];
+                                double wv[RU];
+#pragma unroll
+                                for (int u = 0; u < RU; ++u) {
+                                    const int i = i0 + u * nw;
+                                    const bool live = i < m;
+                                    wv[u] = live ? zh[i] : 0.0;
+                                    const double* row = Vt + (size_t)nd[a0 + (live ? i : 0)] * n + c0;
+#pragma unroll
+                                    for (int q = 0; q < LPC; ++q) {
+                                        const int cc = lane + 32 * q;
+                                        v[u][q] = (live && c0 + cc < n) ? row[cc] : 0.0;
+                                    }
+                                }
+#pragma unroll
+                                for (int u = 0; u < RU; ++u)
+#pragma unroll
+                                    for (int q = 0; q < LPC; ++q) yp[q] = fma(wv[u], v[u][q], yp[q]);
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < LPC; ++q) ypart[warp * chunk + lane + 32 * q] = yp[q];
+                        __syncthreads();
+                        for (int cc = tid; cc < chunk; cc += nt) {
+                            double a = 0.0;
+                            for (int w2 = 0; w2 < nw; ++w2) a += ypart[w2 * chunk + cc];
+                            ysum_[cc] = a * coef;
+                        }
+                        __syncthreads();
+#pragma unroll
+                        for (int q = 0; q < LPC; ++q) yp[q] = ysum_[lane + 32 * q];
+                        {
+                            constexpr int RU = 4;
+                            for (int i0 = warp; i0 < m; i0 += nw * RU) {
+                                double v[RU][LPC];
+#pragma unroll
+                                for (int u = 0; u < RU; ++u) {
+                                    const int i = i0 + u * nw;
+                                    const bool live = i < m;
+                                    const double* row = Vt + (size_t)nd[a0 + (live ? i : 0)] * n + c0;
+#pragma unroll
+                                    for (int q = 0; q < LPC; ++q) {
+                                        const int cc = lane + 32 * q;
+                                        v[u][q] = (live && c0 + cc < n) ? row[cc] : 0.0;
+                                    }
+                                }
+#pragma unroll
+                                for (int u = 0; u < RU; ++u) {
+                                    const int i = i0 + u * nw;
+                                    if (i >= m) continue;
+                                    const double wi = zh[i];
+                                    double* row = Vt + (size_t)nd[a0 + i] * n + c0;
+#pragma unroll
+                                    for (int q = 0; q < LPC; ++q) {
+                                        const int cc = lane + 32 * q;
+                                        if (c0 + cc < n) row[cc] = fma(-wi, yp[q], v[u][q]);
+                                    }
+                                }
+                            }
+                        }
+                        __syncthreads();
+                    }
+                }
+                // pending z vectors of later terms
+                for (int s2 = t + 1 + tid; s2 < nterms; s2 += nt) {
+                    double* zp = Z + (size_t)s2 * n;
+                    double dot = 0.0;
+                    for (int i = 0; i < m; ++i) dot = fma(zh[i], zp[nd[a0 + i]], dot);
+                    dot *= coef;
+                    for (int i = 0; i < m; ++i) zp[nd[a0 + i]] = fma(-zh[i], dot, zp[nd[a0 + i]]);
+                }
+                __syncthreads();
+                for (int i = tid; i < m; i += nt) z[nd[a0 + i]] = (i == piv) ? alpha : 0.0;
+                __syncthreads();
+            }
+        }
+        SEC_MARK(2);
+        // ---------------- deflation, stage 2 (LAPACK dlaed2): neighbouring survivors whose
+        // eigenvalues are close enough are combined by a plane rotation
+        if (tid == 0) {
+            const int ncand = S.r;
+            int r = 0, nrot = 0, prev = -1;
+            for (int p = 0; p < ncand; ++p) {
+                const int i = org[p];
+                if (fabs(rho * z[i]) <= tol) continue;
                 if (prev < 0) { prev = i; continue; }
                 double s = z[prev], c = z[i];
                 const double tau = hypot(c, s);
@@ -338,6 +491,7 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
             }
         }
         __syncthreads();
+        SEC_MARK(3);
         // ---------------- secular equation on the r non-deflated poles
         const bool neg = rho < 0.0;
         const double arho = fabs(rho);
@@ -350,11 +504,11 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
             acc += v * v;
         }
         const double ysum = sb_block_sum(acc, S.scratch);
-        for (int j = tid; j < r; j += nt) {
+        for (int j = tid >> 5; j < r; j += nt >> 5) {      // one warp per root
             int o; double m;
             if (r == 1) { o = 0; m = arho * y2[0]; }
             else secular_root(dd, y2, r, arho, j, ysum, &o, &m);
-            org[j] = o; mu[j] = m;
+            if ((tid & 31) == 0) { org[j] = o; mu[j] = m; }
         }
         __syncthreads();
         // Gu-Eisenstat: zh_i^2 = (lam_i - dd_i)/rho * prod_{j != i} (lam_j - dd_i)/(dd_j - dd_i)
@@ -380,9 +534,45 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
             for (int i = 0; i < r; ++i) Qh[(size_t)i * r + j] *= nrm;
         }
         __syncthreads();
+        SEC_MARK(4);
         // ---------------- new eigenvectors: row_new(j) = sum_i Qh[i][j] row_old(i)   (mirrored index i,j)
         {
             auto rowof = [&](int i) { return neg ? nd[r - 1 - i] : nd[i]; };
+            // out[j][col] = sum_i Qh[i][j] old[rowof(i)][col], column chunks staged in smem
+            int cw = tile_doubles / r;
+            cw = (cw / 32) * 32;
+            if (cw > n) cw = ((n + 31) / 32) * 32;
+            if (cw >= 32) {
+                constexpr int RB = 8;
+                for (int c0 = 0; c0 < n; c0 += cw) {
+                    const int wcols = min(cw, n - c0);
+                    __syncthreads();
+                    for (int idx = tid; idx < r * wcols; idx += nt) {
+                        const int i = idx / wcols, cc = idx % wcols;
+                        tile[i * cw + cc] = Vt[(size_t)rowof(i) * n + c0 + cc];
+                    }
+                    __syncthreads();
+                    // work items: (j-block, column)
+                    const int njb = (r + RB - 1) / RB;
+                    for (int item = tid; item < njb * wcols; item += nt) {
+                        const int jb0 = (item / wcols) * RB, cc = item % wcols;
+                        const int jb = min(RB, r - jb0);
+                        double a8[RB];
+#pragma unroll
+                        for (int q = 0; q < RB; ++q) a8[q] = 0.0;
+                        for (int i = 0; i < r; ++i) {
+                            const double x = tile[i * cw + cc];
+                            const double* qrow = Qh + (size_t)i * r + jb0;
+#pragma unroll
+                            for (int q = 0; q < RB; ++q)
+                                if (q < jb) a8[q] = fma(qrow[q], x, a8[q]);
+                        }
+#pragma unroll
+                        for (int q = 0; q < RB; ++q)
+                            if (q < jb) work[(size_t)(jb0 + q) * n + c0 + cc] = a8[q];
+                    }
+                }
+            } else {
             constexpr int JB = 8;
             for (int j0 = 0; j0 < r; j0 += JB) {
                 const int jb = min(JB, r - j0);
@@ -405,11 +595,13 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
                         if (q < jb) work[(size_t)(j0 + q) * n + col] = a8[q];
                 }
             }
-            __syncthreads();
-            for (int j = 0; j < r; ++j) {
-                const int row = rowof(j);
-                for (int col = tid; col < n; col += nt) Vt[(size_t)row * n + col] = work[(size_t)j * n + col];
             }
+            __syncthreads();
+            for (int idx = tid; idx < r * n; idx += nt) {
+                const int j = idx / n, col = idx % n;
+                Vt[(size_t)rowof(j) * n + col] = work[(size_t)j * n + col];
+            }
+            SEC_MARK(5);
             // pending z vectors: z_s[row(j)] <- sum_i Qh[i][j] z_s[row(i)]
             for (int s2 = t + 1; s2 < nterms; ++s2) {
                 double* zp = Z + (size_t)s2 * n;
@@ -430,6 +622,7 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
             }
         }
         __syncthreads();
+        SEC_MARK(6);
         // ---------------- ascending order of the rows for the next term
         for (int i = tid; i < n; i += nt) {
             const double di = d[i];
@@ -439,32 +632,82 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
         }
         __syncthreads();
     }
+    SEC_MARK(7);
     // ---------------- write back: evals ascending, rows of Vt permuted (new[p] = old[ord[p]])
-    for (int p = tid; p < n; p += nt) evals_[(size_t)b * n + p] = d[ord[p]];
-    int* leader = nd;           // reuse
-    for (int start = tid; start < n; start += nt) {
-        int j = ord[start];
-        int isl = (j != start);
-        while (isl && j != start) { if (j < start) isl = 0; j = ord[j]; }
-        leader[start] = isl;
+    // Rows with equal eigenvalues are interchangeable: a row that already sits in a slot
+    // whose sorted value equals its own eigenvalue stays put, only the others are matched
+    // (in ascending order) to the remaining slots.  This keeps a degenerate cluster in
+    // place when one row crosses it, instead of shifting every member by one.
+    for (int p = tid; p < n; p += nt) dd[p] = d[ord[p]];            // sorted values
+    __syncthreads();
+    for (int p = tid; p < n; p += nt) {
+        evals_[(size_t)b * n + p] = dd[p];
+        org[p] = (d[p] == dd[p]) ? 1 : 0;                             // fixed point
     }
     __syncthreads();
-    for (int col = tid; col < n; col += nt) {
-        for (int start = 0; start < n; ++start) {
-            if (!leader[start]) continue;
-            const double tmp = Vt[(size_t)start * n + col];
-            int cur = start, nxt = ord[cur];
-            while (nxt != start) {
-                Vt[(size_t)cur * n + col] = Vt[(size_t)nxt * n + col];
-                cur = nxt; nxt = ord[cur];
-            }
-            Vt[(size_t)cur * n + col] = tmp;
+    for (int p = tid; p < n; p += nt) {
+        if (org[p]) continue;
+        int kslot = 0;
+        for (int q = 0; q < p; ++q) kslot += !org[q];
+        ia[kslot] = p;                                                // kslot-th free slot
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+        if (org[i]) { ib[i] = i; continue; }
+        const double di = d[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            if (org[j]) continue;
+            const double dj = d[j];
+            rank += (dj < di) || (dj == di && j < i);
+        }
+        ib[ia[rank]] = i;                                             // slot -> row
+    }
+    __syncthreads();
+    for (int p = tid; p < n; p += nt) ord[p] = ib[p];
+    if (tid == 0) S.flag = 0;
+    __syncthreads();
+    for (int p2 = tid; p2 < n; p2 += nt)
+        if (ord[p2] != p2) {
+            nd[atomicAdd(&S.flag, 1)] = p2;          // destinations that change
+            const int dist = abs(ord[p2] - p2);
+            atomicAdd(&sec_prof[11], (unsigned long long)dist);
+            if (dist == 1) atomicAdd(&sec_prof[12], 1ull);
+            if (d[ord[p2]] == d[p2]) atomicAdd(&sec_prof[13], 1ull);   // moved although eigenvalue equal to the old occupant
+        }
+    __syncthreads();
+    {
+        const int nm = S.flag;
+        if (tid == 0) { atomicAdd(&sec_prof[9], (unsigned long long)nm); atomicAdd(&sec_prof[10], 1ull); }
+        const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+        for (int e = warp; e < nm; e += nw) {
+            const double* src = Vt + (size_t)ord[nd[e]] * n;
+            double* dst = work + (size_t)e * n;
+            for (int col = lane; col < n; col += 32) dst[col] = src[col];
+        }
+        __syncthreads();
+        for (int e = warp; e < nm; e += nw) {
+            const double* src = work + (size_t)e * n;
+            double* dst = Vt + (size_t)nd[e] * n;
+            for (int col = lane; col < n; col += 32) dst[col] = src[col];
         }
     }
+    __syncthreads();
+    SEC_MARK(8);
     (void)status;
 }
 
 }  // namespace
+
+extern "C" int sb_secular_profile_impl(unsigned long long* out16, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out16, sec_prof, sizeof(unsigned long long) * 16);
+    if (e != cudaSuccess) return (int)e;
+    if (reset) {
+        unsigned long long z[16] = {0};
+        e = cudaMemcpyToSymbol(sec_prof, z, sizeof(z));
+    }
+    return (int)e;
+}
 
 extern "C" int sb_lowrank_factor_impl(const double* U, const double* J, const double* Cmat, int kcap, const int* kvec,
                                       int n, double* P, double* sig, int* nterm, const int* skip, int batch,
@@ -479,13 +722,21 @@ extern "C" int sb_lowrank_factor_impl(const double* U, const double* J, const do
 extern "C" int sb_secular_update_impl(double* evals, double* Vt, double* Z, int zcap, const double* sig,
                                       const int* nterm, int n, double* work, double* qwork, int* status,
                                       const int* skip, int batch, cudaStream_t st) {
-    const size_t smem = (size_t)n * (8 * sizeof(double) + 5 * sizeof(int)) + sizeof(SecShared) + 64;
+    const size_t base = (size_t)n * (8 * sizeof(double) + 5 * sizeof(int)) + sizeof(SecShared) + 64;
+    int dev = 0, optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    size_t tile_bytes = 64 * 1024;
+    if (base + tile_bytes > (size_t)optin) tile_bytes = base < (size_t)optin ? ((size_t)optin - base) / 1024 * 1024 : 0;
+    const int tile_doubles = (int)(tile_bytes / sizeof(double));
+    if (tile_doubles < (SEC_THREADS / 32 + 1) * 256) return -2;   // n too large for this build
+    const size_t smem = base + tile_bytes;
     const int cpt = (n + SEC_THREADS - 1) / SEC_THREADS;
     SB_COUNT(1);
 #define SB_SEC_LAUNCH(C)                                                                                          \
     cudaFuncSetAttribute(secular_update_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
     secular_update_kernel<C><<<batch, SEC_THREADS, smem, st>>>(evals, Vt, Z, zcap, sig, nterm, n, work, qwork,  \
-                                                               status, skip)
+                                                               status, skip, tile_doubles)
     if (cpt <= 1) { SB_SEC_LAUNCH(1); }
     else if (cpt <= 2) { SB_SEC_LAUNCH(2); }
     else if (cpt <= 4) { SB_SEC_LAUNCH(4); }
