@@ -161,6 +161,13 @@ int sb_qn_ras(const double* Vg, const double* evals, const double* Vt, const dou
               int order, int n, double* s, double* smag, double* alpha, int32_t* status,
               const int32_t* active, int batch, void* stream);
 
+/* s = V c and |B| s = V(|lam| * c) from ONE transposed pass over Vt: pack the two
+ * coefficient vectors [b,2,n], run sb_hv_ld(transposed, nvec=2), unpack.               */
+int sb_pack_coef(const double* coef, const double* evals, double* out2, int n,
+                 const int32_t* active, int batch, void* stream);
+int sb_unpack2(const double* in2, double* s, double* absBs, int n, const int32_t* active,
+               int batch, void* stream);
+
 /* ---- per-step bookkeeping (sella/peswrapper.py:578-602, optimize/optimize.py:362-434) ----
  * dpar = {rho_inc, rho_dec, sigma_inc, sigma_dec, delta_min} (host array of 5 doubles),
  * ipar = {order, eig, nsteps_per_diag, diag_every_n(<0: never)} (host array of 4 ints). */

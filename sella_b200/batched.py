@@ -147,6 +147,7 @@ class BatchedSella:
         self.up1 = {k: z(b, 1, n) for k in ("Ytil", "BS", "VtS", "aC", "aBS", "U", "J", "W", "Xw")}
         self.upk = {k: z(b, kc, n) for k in ("Ytil", "BS", "VtS", "aC", "aBS", "U", "J", "W", "Xw")}
         self.lam0, self.skip = z(b), zi(b)
+        self.c2, self.s2 = z(b, 2, n), z(b, 2, n)
         if self.eig_mode == "update":
             self.sec1 = dict(P=z(b, 2, n), Z=z(b, 2, n), sig=z(b, 2))
             self.seck = dict(P=z(b, 2 * kc, n), Z=z(b, 2 * kc, n), sig=z(b, 2 * kc))
@@ -161,7 +162,7 @@ class BatchedSella:
         call("sb_eigh", _p(self.B), _p(self.evals), _p(self.Vt), _p(self.eig_ws.work),
              _p(self.eig_ws.small), _p(self.status), _p(active), I(self.batch), I(self.n), _stream())
 
-    def _update(self, S, Y, bufs, kvec, nv, active, bs_ready=False):
+    def _update(self, S, Y, bufs, kvec, nv, active, bs_ready=False, abs_ready=False):
         """ApproximateHessian.update (linalg.py:274-304) for S, Y of shape [b,kc,n]."""
         b, n = self.batch, self.n
         kc = S.shape[1]
@@ -175,7 +176,9 @@ class BatchedSella:
             bs_ready = False
         if not bs_ready:
             K.hv_ld(self.B, S, bufs["BS"], nv, active=active)
-        if self.update_method == 0:
+        if first:
+            abs_ready = False
+        if self.update_method == 0 and not abs_ready:
             K.hv_ld(self.Vt, S, bufs["VtS"], nv, active=active)
             call("sb_abs_scale", _p(bufs["VtS"]), _p(self.evals), _p(bufs["aC"]), I(kc), I(n), _p(self.skip),
                  I(b), _stream())
@@ -274,8 +277,13 @@ class BatchedSella:
         if self.rs == "tr":
             call("sb_qn_tr", _p(self.Vg), _p(self.evals), _p(self.delta), I(self.order), I(n), _p(self.coef),
                  _p(self.smag), _p(self.alpha), _p(self.status), _p(active), I(b), _stream())
-            K.hv_ld(self.Vt, self.coef.view(b, 1, n), self.s.view(b, 1, n), 1, transposed=True, active=active)
+            # s = V c and |B| s = V(|lam| c) (needed by the TS-BFGS update) in one pass over Vt
+            call("sb_pack_coef", _p(self.coef), _p(self.evals), _p(self.c2), I(n), _p(active), I(b), _stream())
+            K.hv_ld(self.Vt, self.c2, self.s2, 2, transposed=True, active=active)
+            call("sb_unpack2", _p(self.s2), _p(self.s), _p(self.up1["aBS"]), I(n), _p(active), I(b), _stream())
+            abs_ready = True
         else:
+            abs_ready = False
             call("sb_qn_ras", _p(self.Vg), _p(self.evals), _p(self.Vt), _p(self.delta), I(self.order), I(n),
                  _p(self.s), _p(self.smag), _p(self.alpha), _p(self.status), _p(active), I(b), _stream())
         # ---- re-diagonalise?  (spectrum of the Hessian before this step's update)
@@ -289,7 +297,7 @@ class BatchedSella:
         call("sb_kick_finish", _p(self.x), _p(self.f), _p(self.g), _p(self.xnew), _p(self.fnew), _p(self.gnew),
              _p(self.s), _p(self.up1["BS"]), _p(self.smag), _p(self.dg), _p(self.delta), _p(self.rho),
              _p(self.nsteps), self._dpar, self._ipar, I(n), _p(active), I(b), _stream())
-        self._update(S1, self.dg.view(b, 1, n), self.up1, None, 1, active, bs_ready=True)
+        self._update(S1, self.dg.view(b, 1, n), self.up1, None, 1, active, bs_ready=True, abs_ready=abs_ready)
         if self.eig and int(self.ev.sum().item()) > 0:
             self._diag(self.ev)
 

@@ -44,6 +44,8 @@ extern "C" int sb_qn_tr_impl(const double*, const double*, const double*, int, i
 extern "C" int sb_qn_ras_impl(const double*, const double*, const double*, const double*, int, int, double*,
                               double*, double*, int*, const int*, int, cudaStream_t);
 extern "C" int sb_axpy_impl(const double*, const double*, double*, int, const int*, int, cudaStream_t);
+extern "C" int sb_pack_coef_impl(const double*, const double*, double*, int, const int*, int, cudaStream_t);
+extern "C" int sb_unpack2_impl(const double*, double*, double*, int, const int*, int, cudaStream_t);
 extern "C" int sb_kick_finish_impl(double*, double*, double*, const double*, const double*, const double*,
                                    const double*, const double*, const double*, double*, double*, double*, int*,
                                    const double*, const int*, int, const int*, int, cudaStream_t);
@@ -216,6 +218,14 @@ int sb_qn_ras(const double* Vg, const double* evals, const double* Vt, const dou
               void* stream) {
     if (n % 3) return -1;
     return sb_qn_ras_impl(Vg, evals, Vt, delta, order, n, s, smag, alpha, status, active, batch, ST);
+}
+int sb_pack_coef(const double* coef, const double* evals, double* out2, int n, const int32_t* active, int batch,
+                 void* stream) {
+    return sb_pack_coef_impl(coef, evals, out2, n, active, batch, ST);
+}
+int sb_unpack2(const double* in2, double* s, double* absBs, int n, const int32_t* active, int batch,
+               void* stream) {
+    return sb_unpack2_impl(in2, s, absBs, n, active, batch, ST);
 }
 int sb_axpy(const double* x, const double* s, double* out, int n, const int32_t* active, int batch, void* stream) {
     return sb_axpy_impl(x, s, out, n, active, batch, ST);

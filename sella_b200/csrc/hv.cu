@@ -92,24 +92,36 @@ hv_tma_kernel(const double* __restrict__ A, const double* __restrict__ X, double
             sb_mbar_wait(&full[s], ph);
             const double* tile = stage_base + (size_t)s * stage_d;
             const double* xs = tile + tile_d;
-            for (int r = warp; r < rows; r += NCW) {
-                double acc[NV];
+            // each warp takes rows (warp, warp+NCW) together: the vector is read once for
+            // both rows and every row has two accumulators -> four independent FMA chains
+            for (int r = warp; r < rows; r += 2 * NCW) {
+                const int r2 = r + NCW;
+                const bool two = r2 < rows;
+                double a0[NV], a1[NV], b0[NV], b1[NV];
 #pragma unroll
-                for (int v = 0; v < NV; ++v) acc[v] = 0.0;
-                const double2* row2 = reinterpret_cast<const double2*>(tile + (size_t)r * n);
+                for (int v = 0; v < NV; ++v) { a0[v] = 0.0; a1[v] = 0.0; b0[v] = 0.0; b1[v] = 0.0; }
+                const double2* rowa = reinterpret_cast<const double2*>(tile + (size_t)r * n);
+                const double2* rowb = reinterpret_cast<const double2*>(tile + (size_t)(two ? r2 : r) * n);
                 for (int j = lane; j < (n >> 1); j += 32) {
-                    const double2 a = row2[j];
+                    const double2 a = rowa[j];
+                    const double2 bq = rowb[j];
 #pragma unroll
                     for (int v = 0; v < NV; ++v) {
                         const double2 x = reinterpret_cast<const double2*>(xs + (size_t)v * n)[j];
-                        acc[v] = fma(a.x, x.x, acc[v]);
-                        acc[v] = fma(a.y, x.y, acc[v]);
+                        a0[v] = fma(a.x, x.x, a0[v]);
+                        a1[v] = fma(a.y, x.y, a1[v]);
+                        b0[v] = fma(bq.x, x.x, b0[v]);
+                        b1[v] = fma(bq.y, x.y, b1[v]);
                     }
                 }
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
-                    const double tot = sb_warp_sum(acc[v]);
-                    if (lane == 0) Y[((size_t)b * ldv + v) * n + r0 + r] = tot;
+                    const double ta = sb_warp_sum(a0[v] + a1[v]);
+                    const double tb = sb_warp_sum(b0[v] + b1[v]);
+                    if (lane == 0) {
+                        Y[((size_t)b * ldv + v) * n + r0 + r] = ta;
+                        if (two) Y[((size_t)b * ldv + v) * n + r0 + r2] = tb;
+                    }
                 }
             }
             __syncwarp();
@@ -302,9 +314,10 @@ void query_device() {
 
 HvPlan plan_hv(int n, int nvec, bool transposed) {
     HvPlan p;
-    const int target = 32 * 1024;                 // bytes of A per stage
+    const int target = 48 * 1024;                 // bytes of A per stage
     int R = target / (n * 8);
-    if (R >= NCW) R = (R / NCW) * NCW;
+    if (R >= 2 * NCW) R = (R / (2 * NCW)) * (2 * NCW);
+    else if (R >= NCW) R = NCW;
     if (R < 1) R = 1;
     if (R > n) R = n;
     p.rows = R;

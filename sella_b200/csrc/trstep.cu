@@ -191,6 +191,30 @@ qn_ras_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_,
     (void)scratch;
 }
 
+// out[b,0,:] = coef,  out[b,1,:] = |evals| * coef   (coefficients of s and |B| s in the
+// eigenbasis: one transposed pass over Vt then yields both vectors)
+__global__ void pack_coef_kernel(const double* __restrict__ coef, const double* __restrict__ evals,
+                                 double* __restrict__ out, int n, const int* __restrict__ active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double c = coef[(size_t)b * n + i];
+    out[((size_t)b * 2) * n + i] = c;
+    out[((size_t)b * 2 + 1) * n + i] = fabs(evals[(size_t)b * n + i]) * c;
+}
+
+// s = in[b,0,:], absBs = in[b,1,:]
+__global__ void unpack2_kernel(const double* __restrict__ in, double* __restrict__ s, double* __restrict__ a,
+                               int n, const int* __restrict__ active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    s[(size_t)b * n + i] = in[((size_t)b * 2) * n + i];
+    a[(size_t)b * n + i] = in[((size_t)b * 2 + 1) * n + i];
+}
+
 // ------------------------------------------------------------------ step bookkeeping
 // x_new = x + s
 __global__ void axpy_kernel(const double* __restrict__ x, const double* __restrict__ s, double* __restrict__ out,
@@ -313,6 +337,22 @@ extern "C" int sb_qn_ras_impl(const double* Vg, const double* evals, const doubl
     cudaFuncSetAttribute(qn_ras_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     SB_COUNT(1);
     qn_ras_kernel<<<batch, TR_THREADS, smem, st>>>(Vg, evals, Vt, delta, order, n, s, smag, alpha, status, active);
+    return SB_LAUNCH_CHECK();
+}
+
+extern "C" int sb_pack_coef_impl(const double* coef, const double* evals, double* out, int n, const int* active,
+                                 int batch, cudaStream_t st) {
+    dim3 grid((n + 255) / 256, batch);
+    SB_COUNT(1);
+    pack_coef_kernel<<<grid, 256, 0, st>>>(coef, evals, out, n, active);
+    return SB_LAUNCH_CHECK();
+}
+
+extern "C" int sb_unpack2_impl(const double* in, double* s, double* a, int n, const int* active, int batch,
+                               cudaStream_t st) {
+    dim3 grid((n + 255) / 256, batch);
+    SB_COUNT(1);
+    unpack2_kernel<<<grid, 256, 0, st>>>(in, s, a, n, active);
     return SB_LAUNCH_CHECK();
 }
 

@@ -264,7 +264,11 @@ update_apply_kernel(double* __restrict__ B_, const double* __restrict__ U_, cons
             cw[i] = W[(size_t)a0 * n + i];
         }
         __syncthreads();
-        for (int i = r0; i < r1; ++i) {
+        // warps own rows, lanes own columns (8 per lane and chunk, all loads issued
+        // before the arithmetic): coalesced 2 KB bursts, 8 independent loads per lane
+        const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+        constexpr int LPC = 8;
+        for (int i = r0 + warp; i < r1; i += nw) {
             double ui[KC], ji[KC], wi[KC];
 #pragma unroll
             for (int a = 0; a < KC; ++a) {
@@ -273,19 +277,30 @@ update_apply_kernel(double* __restrict__ B_, const double* __restrict__ U_, cons
                 wi[a] = a < kc ? cw[(size_t)a * n + i] : 0.0;
             }
             double* row = B + (size_t)i * n;
-            for (int j = tid; j < n; j += nt) {
-                double inc = 0.0;
+            for (int c0 = 0; c0 < n; c0 += 32 * LPC) {
+                double bv[LPC];
 #pragma unroll
-                for (int a = 0; a < KC; ++a) {
-                    if (a < kc) {
-                        const double uj = cu[(size_t)a * n + j], jj = cj[(size_t)a * n + j], wj = cw[(size_t)a * n + j];
-                        const double p1 = __dmul_rn(ui[a], jj), p2 = __dmul_rn(ji[a], uj);
-                        const double q1 = __dmul_rn(wi[a], uj), q2 = __dmul_rn(ui[a], wj);
-                        const double t = __dadd_rn(__dadd_rn(p1, p2), __dmul_rn(-0.5, __dadd_rn(q1, q2)));
-                        inc = __dadd_rn(inc, t);
-                    }
+                for (int q = 0; q < LPC; ++q) {
+                    const int j = c0 + lane + 32 * q;
+                    bv[q] = j < n ? row[j] : 0.0;
                 }
-                row[j] = __dadd_rn(row[j], inc);
+#pragma unroll
+                for (int q = 0; q < LPC; ++q) {
+                    const int j = c0 + lane + 32 * q;
+                    if (j >= n) continue;
+                    double inc = 0.0;
+#pragma unroll
+                    for (int a = 0; a < KC; ++a) {
+                        if (a < kc) {
+                            const double uj = cu[(size_t)a * n + j], jj = cj[(size_t)a * n + j], wj = cw[(size_t)a * n + j];
+                            const double p1 = __dmul_rn(ui[a], jj), p2 = __dmul_rn(ji[a], uj);
+                            const double q1 = __dmul_rn(wi[a], uj), q2 = __dmul_rn(ui[a], wj);
+                            const double t = __dadd_rn(__dadd_rn(p1, p2), __dmul_rn(-0.5, __dadd_rn(q1, q2)));
+                            inc = __dadd_rn(inc, t);
+                        }
+                    }
+                    row[j] = __dadd_rn(bv[q], inc);
+                }
             }
         }
     }
