@@ -157,6 +157,12 @@ int sb_secular_update(double* evals, double* Vt, double* Z, int zcap, const doub
 int sb_qn_tr(const double* Vg, const double* evals, const double* delta, int order, int n,
              double* coef, double* smag, double* alpha, int32_t* status, const int32_t* active,
              int batch, void* stream);
+/* rational-function models (sella/optimize/stepper.py:114-185) with the spherical trust
+ * region: mode 0 = rfo, 1 = prfo (Sella's default for saddles).  The bordered-matrix
+ * eigenproblem per alpha is solved as an arrow-head secular equation in the eigenbasis. */
+int sb_rfo_tr(const double* Vg, const double* evals, const double* delta, int order, int n, int mode,
+              double* coef, double* smag, double* alpha, int32_t* status, const int32_t* active,
+              int batch, void* stream);
 int sb_qn_ras(const double* Vg, const double* evals, const double* Vt, const double* delta,
               int order, int n, double* s, double* smag, double* alpha, int32_t* status,
               const int32_t* active, int batch, void* stream);

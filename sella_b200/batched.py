@@ -70,10 +70,15 @@ class BatchedSella:
         dev = x0.device
         self.dev = dev
         self.order = int(order)
-        method = d["method"] if method is None else method
-        if method.lower() not in _QN_NAMES:
-            raise NotImplementedError(
-                "step model %r: only the quasi-Newton model is on the batched path yet" % method)
+        method = (d["method"] if method is None else method).lower()
+        if method in _QN_NAMES:
+            self.method = "qn"
+        elif method in ("rfo", "rational function optimization"):
+            self.method = "rfo"
+        elif method in ("prfo", "p-rfo", "partitioned rational function optimization"):
+            self.method = "prfo"
+        else:
+            raise ValueError("Unknown stepper name: {}".format(method))
         rs = "ras" if rs is None else rs
         if rs in _TR_NAMES:
             self.rs = "tr"
@@ -83,6 +88,8 @@ class BatchedSella:
                 raise ValueError("restricted atomic step needs 3N coordinates")
         else:
             raise ValueError("Unknown restricted step name: {}".format(rs))
+        if self.method != "qn" and self.rs != "tr":
+            raise NotImplementedError("rfo/prfo are on the batched path with rs='tr' only (ras: next)")
         self.eig = d["eig"] if eig is None else bool(eig)
         self.eta = float(eta)
         self.gamma = float(gamma)
@@ -156,6 +163,21 @@ class BatchedSella:
             self.qwork = z(b, n, n)
         self.initialized = False
         self.ndiag = 0
+        self.prof = None          # set to {} to collect CUDA-event timings of selected kernels
+
+    def _timed(self, name, fn):
+        if self.prof is None:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self.prof.setdefault(name, []).append((e0, e1))
+        return out
+
+    def prof_summary(self):
+        torch.cuda.synchronize()
+        return {k: (len(v), sum(a.elapsed_time(z) for a, z in v) / len(v)) for k, v in (self.prof or {}).items()}
 
     # ------------------------------------------------------------------ helpers
     def _eigh(self, active=None):
@@ -188,8 +210,9 @@ class BatchedSella:
              _p(bufs["aBS"] if self.update_method == 0 else None), _p(bufs["U"]), _p(bufs["J"]), _p(bufs["W"]),
              _p(bufs["Xw"]), I(kc), _p(kvec), I(n), I(self.update_method), _p(self.skip), _p(self.status),
              _p(self.Cmat if track else None), I(b), _stream())
-        call("sb_update_apply", _p(self.B), _p(bufs["U"]), _p(bufs["J"]), _p(bufs["W"]), I(kc), _p(kvec),
-             I(n), _p(self.skip), I(b), _stream())
+        self._timed("update_apply_k%d" % kc, lambda: call(
+            "sb_update_apply", _p(self.B), _p(bufs["U"]), _p(bufs["J"]), _p(bufs["W"]), I(kc), _p(kvec),
+            I(n), _p(self.skip), I(b), _stream()))
         self._updates_since_refresh += 1
         if track and not (self.eig_refresh_every and self._updates_since_refresh >= self.eig_refresh_every):
             # B+ = B + Delta: carry the eigenpairs along instead of a fresh eigensolve
@@ -197,9 +220,10 @@ class BatchedSella:
             call("sb_lowrank_factor", _p(bufs["U"]), _p(bufs["J"]), _p(self.Cmat), I(kc), _p(kvec), I(n),
                  _p(sec["P"]), _p(sec["sig"]), _p(self.nterm), _p(self.skip), I(b), _stream())
             K.hv_ld(self.Vt, sec["P"], sec["Z"], 2 * nv, active=active)
-            call("sb_secular_update", _p(self.evals), _p(self.Vt), _p(sec["Z"]), I(2 * kc), _p(sec["sig"]),
-                 _p(self.nterm), I(n), _p(self.eig_ws.work), _p(self.qwork), _p(self.status), _p(self.skip),
-                 I(b), _stream())
+            self._timed("secular_update_k%d" % kc, lambda: call(
+                "sb_secular_update", _p(self.evals), _p(self.Vt), _p(sec["Z"]), I(2 * kc), _p(sec["sig"]),
+                _p(self.nterm), I(n), _p(self.eig_ws.work), _p(self.qwork), _p(self.status), _p(self.skip),
+                I(b), _stream()))
             self.eig_valid = True
         else:
             self.eig_valid = False
@@ -275,8 +299,13 @@ class BatchedSella:
             self.eig_valid = True
         K.hv_ld(self.Vt, self.g.view(b, 1, n), self.Vg.view(b, 1, n), 1, active=active)
         if self.rs == "tr":
-            call("sb_qn_tr", _p(self.Vg), _p(self.evals), _p(self.delta), I(self.order), I(n), _p(self.coef),
-                 _p(self.smag), _p(self.alpha), _p(self.status), _p(active), I(b), _stream())
+            if self.method == "qn":
+                call("sb_qn_tr", _p(self.Vg), _p(self.evals), _p(self.delta), I(self.order), I(n), _p(self.coef),
+                     _p(self.smag), _p(self.alpha), _p(self.status), _p(active), I(b), _stream())
+            else:
+                call("sb_rfo_tr", _p(self.Vg), _p(self.evals), _p(self.delta), I(self.order), I(n),
+                     I(1 if self.method == "prfo" else 0), _p(self.coef), _p(self.smag), _p(self.alpha),
+                     _p(self.status), _p(active), I(b), _stream())
             # s = V c and |B| s = V(|lam| c) (needed by the TS-BFGS update) in one pass over Vt
             call("sb_pack_coef", _p(self.coef), _p(self.evals), _p(self.c2), I(n), _p(active), I(b), _stream())
             K.hv_ld(self.Vt, self.c2, self.s2, 2, transposed=True, active=active)

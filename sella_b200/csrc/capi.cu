@@ -44,6 +44,8 @@ extern "C" int sb_qn_tr_impl(const double*, const double*, const double*, int, i
 extern "C" int sb_qn_ras_impl(const double*, const double*, const double*, const double*, int, int, double*,
                               double*, double*, int*, const int*, int, cudaStream_t);
 extern "C" int sb_axpy_impl(const double*, const double*, double*, int, const int*, int, cudaStream_t);
+extern "C" int sb_rfo_tr_impl(const double*, const double*, const double*, int, int, int, double*, double*, double*,
+                              int*, const int*, int, cudaStream_t);
 extern "C" int sb_pack_coef_impl(const double*, const double*, double*, int, const int*, int, cudaStream_t);
 extern "C" int sb_unpack2_impl(const double*, double*, double*, int, const int*, int, cudaStream_t);
 extern "C" int sb_kick_finish_impl(double*, double*, double*, const double*, const double*, const double*,
@@ -212,6 +214,11 @@ int sb_update_apply(double* B, const double* U, const double* J, const double* W
 int sb_qn_tr(const double* Vg, const double* evals, const double* delta, int order, int n, double* coef,
              double* smag, double* alpha, int32_t* status, const int32_t* active, int batch, void* stream) {
     return sb_qn_tr_impl(Vg, evals, delta, order, n, coef, smag, alpha, status, active, batch, ST);
+}
+int sb_rfo_tr(const double* Vg, const double* evals, const double* delta, int order, int n, int mode, double* coef,
+              double* smag, double* alpha, int32_t* status, const int32_t* active, int batch, void* stream) {
+    if (mode < 0 || mode > 1 || order < 0) return -1;
+    return sb_rfo_tr_impl(Vg, evals, delta, order, n, mode, coef, smag, alpha, status, active, batch, ST);
 }
 int sb_qn_ras(const double* Vg, const double* evals, const double* Vt, const double* delta, int order, int n,
               double* s, double* smag, double* alpha, int32_t* status, const int32_t* active, int batch,
