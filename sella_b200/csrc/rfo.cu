@@ -2,8 +2,7 @@
 //   RationalFunctionOptimization   sella/optimize/stepper.py:114-157
 //   PartitionedRFO (Sella's default for saddles)   sella/optimize/stepper.py:160-185
 // combined with the restricted-step search of sella/optimize/restricted_step.py:78-121
-// (newton_safe = False: Newton for the first iterations, then bisection down to a
-// collapsed bracket, tol = 1e-15) and the spherical trust region (:136-142).
+// and the spherical trust region (:136-142).
 //
 // The reference diagonalises the (m+1)x(m+1) bordered matrix [[a^2 H, a g],[a g^T, 0]]
 // with a dense eigh for EVERY alpha (its slowest piece: 53 ms at 3N=384 per
@@ -15,53 +14,87 @@
 // with ds/da from implicit differentiation of F.  One root = O(n) work; no n^2 pass is
 // needed during the alpha search for the spherical trust region (|V s| = |s|).
 //
-// One WARP per system (shuffle reductions, no block barriers).
+// The alpha search: the reference (newton_safe = False, tol = 1e-15) falls back to pure
+// bisection after five Newton steps and stops when the bracket has collapsed, i.e. at
+// the root of |s(alpha)| = delta to the last bit.  Here the same root is found by a
+// bracketed Newton iteration with the exact derivative (a handful of evaluations instead
+// of ~55); the step agrees to rounding.
+//
+// One WARP per system; eigenvalues and gradient components live in registers.
 #include "common.cuh"
 
 namespace {
 
-constexpr int RFO_WARPS = 4;
+constexpr int RFO_WARPS = 8;
 constexpr double RFO_EPS = 2.220446049250313e-16;
 
-// Root number `idx` (0..m) of F(mu) = mu + sum_{i<m} z2_i/(d_i - mu), d ascending:
-// idx = 0: (-inf, d_0); idx = m: (d_{m-1}, inf); else (d_{idx-1}, d_idx).
-// Returns the pole index `org` (or -1 when m == 0) and tt with mu = d[org] + tt.
-__device__ void arrow_root(const double* __restrict__ d, const double* __restrict__ z2, int m, int idx, double znorm,
-                           int* org_out, double* tt_out) {
+template <int NPL>
+struct Sys {
+    double lam[NPL], g2[NPL], g[NPL];
+    int n;
+};
+
+// Root of F(mu) = mu + a2 * sum_{i in [i0,i1)} g2_i / (a2*lam_i - mu) in the interval
+// selected by `which`: 0 = below the lowest pole of the block, 1 = above the highest,
+// 2 = between poles (idx-1, idx) (absolute indices).  mu = a2*lam[org] + tt.
+// tt_guess (0 = none) warm-starts Newton.
+template <int NPL>
+__device__ void arrow_root(const Sys<NPL>& S, int i0, int i1, int which, int idx, double a2, double gnorm2,
+                           double tt_guess, int* org_out, double* tt_out) {
     const int lane = threadIdx.x & 31;
-    if (m == 0) { *org_out = -1; *tt_out = 0.0; return; }
+    auto lam_at = [&](int i) {            // broadcast lam[i] from the owning lane
+        const int q = i >> 5, src = i & 31;
+        double v = 0.0;
+#pragma unroll
+        for (int u = 0; u < NPL; ++u) if (u == q) v = S.lam[u];
+        return __shfl_sync(0xffffffffu, v, src);
+    };
     int org;
-    double lo, hi;           // bracket of tt (offset from d[org])
-    if (idx == 0) {
-        org = 0; hi = 0.0; lo = -(fabs(d[0]) + znorm);
-    } else if (idx == m) {
-        org = m - 1; lo = 0.0; hi = fabs(d[m - 1]) + znorm;
+    double lo, hi;
+    const double znorm = sqrt(a2 * gnorm2);
+    if (which == 0) {
+        org = i0;
+        const double d0 = a2 * lam_at(i0);
+        hi = 0.0; lo = -(fabs(d0) + znorm);
+    } else if (which == 1) {
+        org = i1 - 1;
+        const double d1 = a2 * lam_at(i1 - 1);
+        lo = 0.0; hi = fabs(d1) + znorm;
     } else {
-        const double gap = d[idx] - d[idx - 1];
+        const double la = lam_at(idx - 1), lb = lam_at(idx);
+        const double gap = a2 * (lb - la);
+        const double half = 0.5 * gap;
         double fm = 0.0;
-        const double mid = d[idx - 1] + 0.5 * gap;
-        for (int i = lane; i < m; i += 32) fm += z2[i] / (d[i] - mid);
-        fm = mid + sb_warp_sum(fm);
-        if (fm > 0.0) { org = idx - 1; lo = 0.0; hi = 0.5 * gap; }     // root in the left half
-        else { org = idx; lo = -0.5 * gap; hi = 0.0; }
+#pragma unroll
+        for (int u = 0; u < NPL; ++u) {
+            const int i = lane + 32 * u;
+            if (i >= i0 && i < i1) fm += a2 * S.g2[u] / (a2 * (S.lam[u] - la) - half);
+        }
+        fm = (a2 * la + half) + sb_warp_sum(fm);
+        if (fm > 0.0) { org = idx - 1; lo = 0.0; hi = half; }
+        else { org = idx; lo = -half; hi = 0.0; }
     }
-    const double dorg = d[org];
-    double tt = 0.5 * (lo + hi);
+    const double lorg = lam_at(org);
+    double tt = (tt_guess > lo && tt_guess < hi) ? tt_guess : 0.5 * (lo + hi);
     for (int it = 0; it < 200; ++it) {
         double f = 0.0, df = 0.0;
-        for (int i = lane; i < m; i += 32) {
-            const double den = (d[i] - dorg) - tt;
-            const double q = z2[i] / den;
-            f += q;
-            df += q / den;
+#pragma unroll
+        for (int u = 0; u < NPL; ++u) {
+            const int i = lane + 32 * u;
+            if (i >= i0 && i < i1) {
+                const double den = a2 * (S.lam[u] - lorg) - tt;
+                const double r = 1.0 / den;
+                const double q = a2 * S.g2[u] * r;
+                f += q;
+                df = fma(q, r, df);
+            }
         }
-        f = (dorg + tt) + sb_warp_sum(f);
+        f = (a2 * lorg + tt) + sb_warp_sum(f);
         df = 1.0 + sb_warp_sum(df);
         if (f == 0.0) break;
         if (f < 0.0) lo = tt; else hi = tt;
         double next = tt - f / df;
         if (!(next > lo && next < hi)) {
-            // bisection, geometric next to the pole the offset is measured from
             if (lo >= 0.0) {
                 if (lo > 0.0 && hi > 4.0 * lo) next = sqrt(lo) * sqrt(hi);
                 else if (lo == 0.0) next = (hi > 1e-290) ? hi * 0.0625 : 0.5 * hi;
@@ -82,107 +115,127 @@ __device__ void arrow_root(const double* __restrict__ d, const double* __restric
     *tt_out = tt;
 }
 
-// One RFO block on entries [i0, i0+m): writes s (the block of the step in the
-// eigenbasis) and ds/dalpha; returns sum s^2 and sum s*ds via pointers.
-__device__ void rfo_block(const double* __restrict__ lam, const double* __restrict__ gh, int i0, int m, int idx,
-                          double alpha, double* __restrict__ dwork, double* __restrict__ zwork,
-                          double* __restrict__ s, double* __restrict__ ds, double* ss_out, double* sds_out) {
+// One RFO block on entries [i0, i1).  Accumulates sum s^2 and sum s*ds; optionally
+// stores s into sreg.  `guess` in/out: tt / alpha^2 of this block's root (0 = none).
+template <int NPL>
+__device__ void rfo_block(const Sys<NPL>& S, int i0, int i1, int which, int idx, double alpha, double* guess,
+                          double* ss_out, double* sds_out, double* sreg) {
     const int lane = threadIdx.x & 31;
-    double zn = 0.0;
-    for (int i = lane; i < m; i += 32) {
-        const double di = alpha * alpha * lam[i0 + i];
-        const double zi = alpha * gh[i0 + i];
-        dwork[i] = di;
-        zwork[i] = zi * zi;
-        zn += zi * zi;
+    if (i1 <= i0) { *ss_out = 0.0; *sds_out = 0.0; return; }
+    const double a2 = alpha * alpha;
+    double gn = 0.0;
+#pragma unroll
+    for (int u = 0; u < NPL; ++u) {
+        const int i = lane + 32 * u;
+        if (i >= i0 && i < i1) gn += S.g2[u];
     }
-    zn = sqrt(sb_warp_sum(zn));
-    __syncwarp();
+    gn = sb_warp_sum(gn);
     int org; double tt;
-    arrow_root(dwork, zwork, m, idx, zn, &org, &tt);
-    // Dn_i = a^2 lam_i - mu = (d_i - d_org) - tt
+    arrow_root<NPL>(S, i0, i1, which, idx, a2, gn, (*guess) * a2, &org, &tt);
+    if (which != 2) *guess = (a2 > 0.0) ? tt / a2 : 0.0;
+    double lorg;
+    {
+        const int q = org >> 5, src = org & 31;
+        double v = 0.0;
+#pragma unroll
+        for (int u = 0; u < NPL; ++u) if (u == q) v = S.lam[u];
+        lorg = __shfl_sync(0xffffffffu, v, src);
+    }
+    // Dn_i = a^2 lam_i - mu
     double q2 = 0.0;
-    for (int i = lane; i < m; i += 32) {
-        const double Dn = (dwork[i] - dwork[org]) - tt;
-        const double g = gh[i0 + i];
-        q2 += g * g / (Dn * Dn);
+#pragma unroll
+    for (int u = 0; u < NPL; ++u) {
+        const int i = lane + 32 * u;
+        if (i >= i0 && i < i1) {
+            const double Dn = a2 * (S.lam[u] - lorg) - tt;
+            q2 += S.g2[u] / (Dn * Dn);
+        }
     }
     q2 = sb_warp_sum(q2);
-    const double mu = (m > 0) ? dwork[org] + tt : 0.0;
-    const double dmu = 2.0 * alpha * mu * q2 / (1.0 + alpha * alpha * q2);
+    const double mu = a2 * lorg + tt;
+    const double dmu = 2.0 * alpha * mu * q2 / (1.0 + a2 * q2);
     double ss = 0.0, sds = 0.0;
-    for (int i = lane; i < m; i += 32) {
-        const double Dn = (dwork[i] - dwork[org]) - tt;
-        const double g = gh[i0 + i];
-        const double si = -alpha * alpha * g / Dn;
-        const double dsi = (-2.0 * alpha * g * Dn + alpha * alpha * g * (2.0 * alpha * lam[i0 + i] - dmu)) / (Dn * Dn);
-        s[i0 + i] = si;
-        ds[i0 + i] = dsi;
-        ss += si * si;
-        sds += si * dsi;
+#pragma unroll
+    for (int u = 0; u < NPL; ++u) {
+        const int i = lane + 32 * u;
+        if (i >= i0 && i < i1) {
+            const double Dn = a2 * (S.lam[u] - lorg) - tt;
+            const double g = S.g[u];
+            const double si = -a2 * g / Dn;
+            const double dsi = (-2.0 * alpha * g * Dn + a2 * g * (2.0 * alpha * S.lam[u] - dmu)) / (Dn * Dn);
+            if (sreg) sreg[u] = si;
+            ss += si * si;
+            sds += si * dsi;
+        }
     }
     *ss_out = sb_warp_sum(ss);
     *sds_out = sb_warp_sum(sds);
-    __syncwarp();
 }
 
 // mode 0: rfo (one arrow-head over all n entries, eigenvector index `order`);
 // mode 1: prfo (maximise along the lowest `order` modes, minimise along the rest).
-// Spherical trust region.  coef[b,:] = step in the eigenbasis (s = V coef).
+template <int NPL>
 __global__ void __launch_bounds__(RFO_WARPS * 32)
 rfo_tr_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_, const double* __restrict__ delta_,
-              int order, int n, int mode, double* __restrict__ coef_, double* __restrict__ smag, double* __restrict__ alpha_out,
-              int* __restrict__ status, const int* __restrict__ active, int batch) {
+              int order, int n, int mode, double* __restrict__ coef_, double* __restrict__ smag,
+              double* __restrict__ alpha_out, int* __restrict__ status, const int* __restrict__ active, int batch) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wpc = blockDim.x >> 5;
-    const int b = blockIdx.x * wpc + warp;
+    const int b = blockIdx.x * RFO_WARPS + warp;
     if (b >= batch) return;
     if (active && !active[b]) return;
-    extern __shared__ double sm[];
-    double* lam = sm + (size_t)warp * 6 * n;
-    double* gh = lam + n;
-    double* dwork = gh + n;
-    double* zwork = dwork + n;
-    double* s = zwork + n;
-    double* ds = s + n;
-    for (int i = lane; i < n; i += 32) { lam[i] = evals_[(size_t)b * n + i]; gh[i] = Vg_[(size_t)b * n + i]; }
-    __syncwarp();
+    Sys<NPL> S;
+    S.n = n;
+#pragma unroll
+    for (int u = 0; u < NPL; ++u) {
+        const int i = lane + 32 * u;
+        S.lam[u] = i < n ? evals_[(size_t)b * n + i] : 0.0;
+        S.g[u] = i < n ? Vg_[(size_t)b * n + i] : 0.0;
+        S.g2[u] = S.g[u] * S.g[u];
+    }
     const double delta = delta_[b];
     const int mo = order < n ? order : n;
-    auto eval = [&](double alpha, double* val, double* dval) {
+    double guess_a = 0.0, guess_b = 0.0;
+    double sreg[NPL];
+    auto eval = [&](double alpha, double* val, double* dval, bool store) {
         double ss, sds;
         if (mode == 0) {
-            rfo_block(lam, gh, 0, n, mo, alpha, dwork, zwork, s, ds, &ss, &sds);
+            const int which = mo == 0 ? 0 : (mo == n ? 1 : 2);
+            rfo_block<NPL>(S, 0, n, which, mo, alpha, &guess_a, &ss, &sds, store ? sreg : nullptr);
         } else {
             double s1, d1, s2, d2;
-            rfo_block(lam, gh, 0, mo, mo, alpha, dwork, zwork, s, ds, &s1, &d1);
-            rfo_block(lam, gh, mo, n - mo, 0, alpha, dwork, zwork, s, ds, &s2, &d2);
+            rfo_block<NPL>(S, 0, mo, 1, mo, alpha, &guess_a, &s1, &d1, store ? sreg : nullptr);
+            rfo_block<NPL>(S, mo, n, 0, mo, alpha, &guess_b, &s2, &d2, store ? sreg : nullptr);
             ss = s1 + s2; sds = d1 + d2;
         }
         *val = sqrt(ss);
         *dval = sds / fmax(*val, 1e-12);
     };
-    // restricted_step.py:78-121 with alpha0 = 1, [0, 1], slope = +1, newton_safe = False, tol = 1e-15
+    // restricted_step.py:78-121 with alpha0 = 1 on [0, 1], slope = +1
     double alpha = 1.0, val, dval;
-    eval(alpha, &val, &dval);
-    bool interior = val < delta;
+    eval(alpha, &val, &dval, false);
+    const bool interior = val < delta;
     int st = 0;
     if (!interior) {
         double err = val - delta, lo = 0.0, hi = 1.0;
-        int it = 0;
-        for (;; ++it) {
+        for (int it = 0;; ++it) {
             if (fabs(err) <= 1e-15) break;
             if (nextafter(lo, hi) >= hi) break;
-            if (it >= 1000) { st = SB_ST_TR_NOCONV; break; }
+            if (it >= 200) { st = SB_ST_TR_NOCONV; break; }
             if (err > 0.0) hi = alpha; else lo = alpha;
-            const double a1 = alpha - err / dval;
-            if (isnan(a1) || a1 <= lo || a1 >= hi || it > 4) alpha = 0.5 * (lo + hi);
-            else alpha = a1;
-            eval(alpha, &val, &dval);
+            double a1 = alpha - err / dval;
+            if (isnan(a1) || a1 <= lo || a1 >= hi) a1 = 0.5 * (lo + hi);
+            if (a1 == alpha) break;
+            alpha = a1;
+            eval(alpha, &val, &dval, false);
             err = val - delta;
         }
     }
-    for (int i = lane; i < n; i += 32) coef_[(size_t)b * n + i] = s[i];
+    eval(alpha, &val, &dval, true);
+#pragma unroll
+    for (int u = 0; u < NPL; ++u) {
+        const int i = lane + 32 * u;
+        if (i < n) coef_[(size_t)b * n + i] = sreg[u];
+    }
     if (lane == 0) {
         smag[b] = interior ? val : delta;
         alpha_out[b] = alpha;
@@ -195,13 +248,20 @@ rfo_tr_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_,
 extern "C" int sb_rfo_tr_impl(const double* Vg, const double* evals, const double* delta, int order, int n, int mode,
                               double* coef, double* smag, double* alpha, int* status, const int* active, int batch,
                               cudaStream_t st) {
-    int wpc = RFO_WARPS;
-    while (wpc > 1 && (size_t)wpc * 6 * n * sizeof(double) > 200 * 1024) wpc >>= 1;
-    const size_t smem = (size_t)wpc * 6 * n * sizeof(double);
-    if (smem > 220 * 1024) return -2;
-    cudaFuncSetAttribute(rfo_tr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int grid = (batch + RFO_WARPS - 1) / RFO_WARPS;
+    const int npl = (n + 31) / 32;
     SB_COUNT(1);
-    rfo_tr_kernel<<<(batch + wpc - 1) / wpc, wpc * 32, smem, st>>>(
-        Vg, evals, delta, order, n, mode, coef, smag, alpha, status, active, batch);
+#define SB_RFO(N)                                                                                                    \
+    rfo_tr_kernel<N><<<grid, RFO_WARPS * 32, 0, st>>>(Vg, evals, delta, order, n, mode, coef, smag, alpha, status, \
+                                                      active, batch)
+    if (npl <= 4) SB_RFO(4);
+    else if (npl <= 8) SB_RFO(8);
+    else if (npl <= 12) SB_RFO(12);
+    else if (npl <= 16) SB_RFO(16);
+    else if (npl <= 24) SB_RFO(24);
+    else if (npl <= 32) SB_RFO(32);
+    else if (npl <= 48) SB_RFO(48);
+    else return -2;      // n > 1536 not supported by this build
+#undef SB_RFO
     return SB_LAUNCH_CHECK();
 }
