@@ -1,0 +1,43 @@
+"""CUDA mirror of the reference's device seam sella/_gpu.py (gpu_eigh :70-84,
+gpu_eigh_t :87-97, gpu_project :114-132, to_gpu :55-67): same names and return
+conventions, backed by the hand-written kernels instead of torch.linalg.
+
+There is deliberately no CPU fallback and no size threshold: the reference's
+``SELLA_GPU_MIN_DIM`` / OOM bookkeeping exists to fall back to LAPACK, which this
+package does not do."""
+import numpy as np
+import torch
+
+from . import kernels as K
+from ._host import up, up_mat, raise_status
+
+
+def to_gpu(A):
+    return up(A)
+
+
+def gpu_eigh_t(A_gpu):
+    """(evals, evecs) as CUDA tensors; eigenvectors in COLUMNS like torch.linalg.eigh."""
+    w, Vt, status = K.eigh(A_gpu.unsqueeze(0).contiguous())
+    raise_status(status, "eigh")
+    return w[0], Vt[0].T.contiguous()
+
+
+def gpu_eigh(A, A_gpu=None):
+    w, V = gpu_eigh_t(A_gpu if A_gpu is not None else up(A))
+    return w.cpu().numpy(), V.cpu().numpy()
+
+
+def gpu_project(H, U, H_gpu=None):
+    """U.T @ H @ U (sella/_gpu.py:114-132) through the batched H.V kernel."""
+    Hd = (H_gpu if H_gpu is not None else up(H)).unsqueeze(0).contiguous()
+    U = np.asarray(U, dtype=np.float64)
+    n, m = U.shape
+    Ut = up(U.T).unsqueeze(0).contiguous()            # [1, m, n] vector-major
+    HU = torch.empty_like(Ut)
+    done = 0
+    while done < m:                                    # sb_hv handles any nvec in chunks
+        c = min(32, m - done)
+        HU[:, done:done + c] = K.hv(Hd, Ut[:, done:done + c].contiguous())
+        done += c
+    return (Ut[0] @ HU[0].T).cpu().numpy()            # small (m x m) Gram product
