@@ -1,0 +1,192 @@
+"""`Sella(atoms, ...).run(fmax, steps)` — the reference's user-facing optimiser
+(sella/optimize/optimize.py:42-502) on top of the CUDA engine, for ONE search.
+
+The calculator stays where ASE puts it (on the host): every surface evaluation moves the
+positions to the host, calls ``atoms.get_potential_energy()/get_forces()`` and moves
+energy and gradient back; everything else (Davidson, Hessian update, restricted step)
+runs on the device through ``sella_b200.batched.BatchedSella`` with a batch of one.
+
+If ASE is importable the class derives from ``ase.optimize.optimize.Optimizer`` (so
+``run``/``irun``/logging/trajectory attachment are ASE's); otherwise a minimal base
+class with the same ``run(fmax, steps)`` loop is used.
+
+Scope (raises NotImplementedError otherwise, never falls back to the CPU): Cartesian
+coordinates, no constraints (``proj_trans=False, proj_rot=False`` must be passed for
+non-periodic systems, because the reference would otherwise add translation/rotation
+constraints), ``threepoint=False``, no ``hessian_function``, no cell optimisation.
+"""
+import warnings
+from time import localtime, strftime
+
+import numpy as np
+import torch
+
+from ..batched import BatchedSella
+from .._host import dev
+
+try:                                            # pragma: no cover - ASE is not in this image
+    from ase.optimize.optimize import Optimizer as _Base
+    _HAVE_ASE = True
+except Exception:
+    _HAVE_ASE = False
+
+    class _Base:
+        """Stand-in for ase.optimize.optimize.Optimizer: the run loop only."""
+
+        def __init__(self, atoms, restart=None, logfile=None, trajectory=None, master=None, **kw):
+            self.atoms = atoms
+            self.optimizable = atoms
+            self.nsteps = 0
+            self.max_steps = 0
+            self.fmax = None
+            self.logfile = None
+            if logfile == '-':
+                import sys
+                self.logfile = sys.stdout
+            elif logfile is not None and hasattr(logfile, "write"):
+                self.logfile = logfile
+
+        def closelater(self, f):
+            return f
+
+        def run(self, fmax=0.05, steps=100000000):
+            self.fmax = fmax
+            self.max_steps = steps
+            self.log()
+            while not self.converged() and self.nsteps < steps:
+                self.step()
+                self.nsteps += 1
+                self.log()
+            return self.converged()
+
+
+class _CalculatorSurface:
+    """PES plug-in that evaluates the user's ASE calculator on the host (batch of one)."""
+
+    def __init__(self, atoms):
+        self.atoms = atoms
+        self.neval = 0
+
+    def evaluate(self, x, f_out, g_out, active=None):
+        self.neval += 1
+        old = self.atoms.positions.copy()
+        self.atoms.positions = x[0].cpu().numpy().reshape((-1, 3))
+        f = float(self.atoms.get_potential_energy())
+        g = -np.asarray(self.atoms.get_forces(), dtype=np.float64).ravel()
+        self.atoms.positions = old
+        f_out.copy_(torch.tensor([f], dtype=torch.float64))
+        g_out.copy_(torch.from_numpy(g).view(1, -1))
+
+
+class _PESView:
+    """The public bits of the reference's ``dyn.pes`` that user scripts and tests touch."""
+
+    def __init__(self, opt):
+        self._o = opt
+
+    @property
+    def neval(self):
+        return self._o._surface.neval
+
+    def get_x(self):
+        return self._o._eng.x[0].cpu().numpy()
+
+    def get_f(self):
+        return float(self._o._eng.f[0])
+
+    def get_g(self):
+        return self._o._eng.g[0].cpu().numpy()
+
+    def converged(self, fmax, cmax=1e-5):
+        e = self._o._eng
+        e.converged(fmax)
+        f1 = float(e.fmax[0])
+        return f1 < fmax, f1, 0.0
+
+    class _H:
+        def __init__(self, eng):
+            self._e = eng
+
+        @property
+        def B(self):
+            return self._e.B[0].cpu().numpy() if self._e.H_initialized else None
+
+        @property
+        def evals(self):
+            return self._e.evals[0].cpu().numpy() if self._e.H_initialized else None
+
+    @property
+    def H(self):
+        return _PESView._H(self._o._eng)
+
+
+class Sella(_Base):
+    def __init__(self, atoms, restart=None, logfile='-', trajectory=None, master=None, delta0=None,
+                 sigma_inc=None, sigma_dec=None, rho_dec=None, rho_inc=None, order=1, eig=None, eta=1e-4,
+                 method=None, gamma=0.1, threepoint=False, constraints=None, constraints_tol=1e-5, v0=None,
+                 internal=False, append_trajectory=False, rs=None, nsteps_per_diag=3, diag_every_n=None,
+                 hessian_function=None, optimize_cell=False, **kwargs):
+        if internal:
+            raise NotImplementedError("internal coordinates are not on the CUDA path yet")
+        if optimize_cell or hessian_function is not None or threepoint or v0 is not None:
+            raise NotImplementedError("optimize_cell / hessian_function / threepoint / v0 are not on the CUDA path")
+        pbc = np.asarray(getattr(atoms, "pbc", [False] * 3))
+        proj_trans = kwargs.pop("proj_trans", None)
+        proj_rot = kwargs.pop("proj_rot", None)
+        if constraints is not None or proj_trans is not False or (proj_rot is not False and not pbc.any()):
+            raise NotImplementedError(
+                "constraints (including the translation/rotation projections the reference adds by default) "
+                "are not on the CUDA path yet: pass proj_trans=False, proj_rot=False")
+        eigensolver = kwargs.pop("eigensolver", "jd0")
+        if kwargs:
+            raise TypeError("unsupported keyword arguments: %s" % sorted(kwargs))
+        _Base.__init__(self, atoms, restart=restart, logfile=logfile, trajectory=None, master=master)
+        self._surface = _CalculatorSurface(atoms)
+        x0 = torch.from_numpy(np.asarray(atoms.positions, dtype=np.float64).reshape(1, -1).copy()).to(dev())
+        if rs is None:
+            rs = 'ras'
+        if order != 0 and eig is False:
+            warnings.warn("Saddle point optimizations with eig=False will most likely fail!\n Proceeding anyway, "
+                          "but you shouldn't be optimistic.")
+        self._eng = BatchedSella(self._surface, x0, order=order, delta0=delta0, sigma_inc=sigma_inc,
+                                 sigma_dec=sigma_dec, rho_dec=rho_dec, rho_inc=rho_inc, eig=eig, eta=eta,
+                                 method=method, gamma=gamma, rs=rs, nsteps_per_diag=nsteps_per_diag,
+                                 diag_every_n=diag_every_n, eigensolver=eigensolver, kcap=16)
+        self.pes = _PESView(self)
+        self.ord = order
+        self.eta = eta
+        self.constraints_tol = constraints_tol
+        self.fmax = None
+
+    # attributes the reference exposes
+    delta = property(lambda self: float(self._eng.delta[0]))
+    rho = property(lambda self: float(self._eng.rho[0]))
+    nsteps_since_diag = property(lambda self: int(self._eng.since_diag[0]))
+
+    def step(self):
+        self._eng.step()
+        self._eng.check_status()
+        self.atoms.positions = self._eng.x[0].cpu().numpy().reshape((-1, 3))
+
+    def converged(self, forces=None):
+        fmax = self.fmax if self.fmax is not None else 0.05
+        if not self._eng.initialized:
+            # the reference evaluates the surface once before the first convergence test
+            self._eng.surface.evaluate(self._eng.x, self._eng.f, self._eng.g)
+        return bool(self.pes.converged(fmax)[0])
+
+    def gradient_converged(self, gradient=None):
+        return self.converged()
+
+    def log(self, forces=None):
+        if self.logfile is None:
+            return
+        fmax = self.fmax if self.fmax is not None else 0.05
+        _, f1, c1 = self.pes.converged(fmax)
+        name = self.__class__.__name__
+        T = strftime("%H:%M:%S", localtime())
+        if self.nsteps == 0:
+            self.logfile.write(" " * len(name) + "{:>4s} {:>8s} {:>15s} {:>12s} {:>12s} {:>12s} {:>12s}\n"
+                               .format("Step", "Time", "Energy", "fmax", "cmax", "rtrust", "rho"))
+        self.logfile.write("{} {:>3d} {:>8s} {:>15.6f} {:>12.4f} {:>12.4f} {:>12.4f} {:>12.4f}\n"
+                           .format(name, self.nsteps, T, self.pes.get_f(), f1, c1, self.delta, self.rho))

@@ -147,3 +147,44 @@ def test_gpu_seam():
     np.testing.assert_allclose(A @ V, V * w[None, :], atol=1e-11)
     U = np.linalg.qr(rng.normal(size=(60, 20)))[0]
     np.testing.assert_allclose(gpu_project(A, U), U.T @ A @ U, atol=1e-12)
+
+
+class _Atoms:
+    """Minimal ASE-Atoms duck: positions + a host 'calculator'."""
+    def __init__(self, func, x0):
+        self.func = func
+        self.positions = np.array(x0, dtype=float).reshape((-1, 3))
+        self.pbc = np.array([True, True, True])
+        self.constraints = []
+    def __len__(self): return len(self.positions)
+    def get_potential_energy(self): return self.func(self.positions.ravel())[0]
+    def get_forces(self): return -self.func(self.positions.ravel())[1].reshape((-1, 3))
+
+
+def test_sella_drop_in_single_search():
+    """Sella(atoms, ...).run() with a host calculator vs the CPU oracle."""
+    from sella_b200 import Sella
+    from sella_b200.synthetic import quadratic_system, quadratic_func
+    from oracle.pes import CartesianPES
+    from oracle.driver import SaddleSearch
+    n = 48
+    A, xs, x0 = quadratic_system(5, n)
+    func = quadratic_func(A, xs)
+    with pytest.raises(NotImplementedError):      # defaults prfo + ras: ras with rfo models is "next"
+        Sella(_Atoms(func, x0), logfile=None, proj_trans=False, proj_rot=False)
+    with pytest.raises(NotImplementedError):      # default projections need constraint support
+        Sella(_Atoms(func, x0), logfile=None)
+    # the path that is on the device: prfo/tr and qn/ras
+    for method, rs in (("prfo", "tr"), ("qn", "ras")):
+        atoms = _Atoms(func, x0)
+        dyn = Sella(atoms, logfile=None, proj_trans=False, proj_rot=False, method=method, rs=rs)
+        p = CartesianPES(func, x0)
+        o = SaddleSearch(p, method=method, rs=rs)
+        for t in range(8):
+            dyn.step(); o.step()
+            np.testing.assert_allclose(atoms.positions.ravel(), p.get_x(), rtol=0, atol=1e-8)
+        assert dyn.pes.neval == p.neval
+        conv = dyn.run(fmax=1e-4, steps=40)
+        assert conv and dyn.pes.converged(1e-4)[0]
+        # index-1 saddle: exactly one negative eigenvalue of the model Hessian (test_morse_cluster.py:42-46 analogue)
+        assert int((dyn.pes.H.evals < 0).sum()) == 1
