@@ -163,6 +163,9 @@ int sb_qn_tr(const double* Vg, const double* evals, const double* delta, int ord
 int sb_rfo_tr(const double* Vg, const double* evals, const double* delta, int order, int n, int mode,
               double* coef, double* smag, double* alpha, int32_t* status, const int32_t* active,
               int batch, void* stream);
+int sb_rfo_ras(const double* Vg, const double* evals, const double* Vt, const double* delta,
+               int order, int n, int mode, double* s, double* smag, double* alpha, int32_t* status,
+               const int32_t* active, int batch, void* stream);
 int sb_qn_ras(const double* Vg, const double* evals, const double* Vt, const double* delta,
               int order, int n, double* s, double* smag, double* alpha, int32_t* status,
               const int32_t* active, int batch, void* stream);

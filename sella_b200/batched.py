@@ -88,8 +88,6 @@ class BatchedSella:
                 raise ValueError("restricted atomic step needs 3N coordinates")
         else:
             raise ValueError("Unknown restricted step name: {}".format(rs))
-        if self.method != "qn" and self.rs != "tr":
-            raise NotImplementedError("rfo/prfo are on the batched path with rs='tr' only (ras: next)")
         self.eig = d["eig"] if eig is None else bool(eig)
         self.eta = float(eta)
         self.gamma = float(gamma)
@@ -311,6 +309,11 @@ class BatchedSella:
             K.hv_ld(self.Vt, self.c2, self.s2, 2, transposed=True, active=active)
             call("sb_unpack2", _p(self.s2), _p(self.s), _p(self.up1["aBS"]), I(n), _p(active), I(b), _stream())
             abs_ready = True
+        elif self.method != "qn":
+            abs_ready = False
+            call("sb_rfo_ras", _p(self.Vg), _p(self.evals), _p(self.Vt), _p(self.delta), I(self.order), I(n),
+                 I(1 if self.method == "prfo" else 0), _p(self.s), _p(self.smag), _p(self.alpha),
+                 _p(self.status), _p(active), I(b), _stream())
         else:
             abs_ready = False
             call("sb_qn_ras", _p(self.Vg), _p(self.evals), _p(self.Vt), _p(self.delta), I(self.order), I(n),

@@ -220,6 +220,14 @@ int sb_rfo_tr(const double* Vg, const double* evals, const double* delta, int or
     if (mode < 0 || mode > 1 || order < 0) return -1;
     return sb_rfo_tr_impl(Vg, evals, delta, order, n, mode, coef, smag, alpha, status, active, batch, ST);
 }
+extern "C" int sb_rfo_ras_impl(const double*, const double*, const double*, const double*, int, int, int, double*,
+                               double*, double*, int*, const int*, int, cudaStream_t);
+int sb_rfo_ras(const double* Vg, const double* evals, const double* Vt, const double* delta, int order, int n,
+               int mode, double* s, double* smag, double* alpha, int32_t* status, const int32_t* active, int batch,
+               void* stream) {
+    if (n % 3 || mode < 0 || mode > 1) return -1;
+    return sb_rfo_ras_impl(Vg, evals, Vt, delta, order, n, mode, s, smag, alpha, status, active, batch, ST);
+}
 int sb_qn_ras(const double* Vg, const double* evals, const double* Vt, const double* delta, int order, int n,
               double* s, double* smag, double* alpha, int32_t* status, const int32_t* active, int batch,
               void* stream) {

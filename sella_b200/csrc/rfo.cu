@@ -243,6 +243,160 @@ rfo_tr_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_,
     }
 }
 
+// Restricted atomic step (max per-atom displacement, restricted_step.py:172-183) with
+// the rfo / prfo models: warp 0 solves the arrow-head problems for the current alpha
+// (coefficients s_hat, ds_hat in the eigenbasis), then the whole CTA streams Vt once to
+// form the Cartesian step and its derivative (s = V s_hat), as qn_ras_kernel does.
+template <int NPL>
+__global__ void __launch_bounds__(256)
+rfo_ras_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_, const double* __restrict__ Vt_,
+               const double* __restrict__ delta_, int order, int n, int mode, double* __restrict__ s_out,
+               double* __restrict__ smag, double* __restrict__ alpha_out, int* __restrict__ status,
+               const int* __restrict__ active) {
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    extern __shared__ double sm[];
+    double* c1 = sm;            // s_hat
+    double* c2 = c1 + n;        // ds_hat
+    double* s = c2 + n;
+    double* ds = s + n;
+    __shared__ double best_val[8];
+    __shared__ int best_idx[8];
+    __shared__ double sh_alpha, sh_val, sh_dval;
+    __shared__ int sh_go;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const double* Vt = Vt_ + (size_t)b * n * n;
+    const double delta = delta_[b];
+    const int natoms = n / 3;
+    const int mo = order < n ? order : n;
+    Sys<NPL> S;
+    S.n = n;
+    double guess_a = 0.0, guess_b = 0.0;
+    if (warp == 0) {
+#pragma unroll
+        for (int u = 0; u < NPL; ++u) {
+            const int i = lane + 32 * u;
+            S.lam[u] = i < n ? evals_[(size_t)b * n + i] : 0.0;
+            S.g[u] = i < n ? Vg_[(size_t)b * n + i] : 0.0;
+            S.g2[u] = S.g[u] * S.g[u];
+        }
+    }
+    double alpha = 1.0, lo = 0.0, hi = 1.0, val = 0.0, dval = 0.0;
+    bool interior = false, first = true;
+    int st = 0;
+    for (int it = 0;; ++it) {
+        // ---- coefficients at the current alpha (warp 0)
+        if (warp == 0) {
+            double sreg[NPL], dreg[NPL];
+            const double a2 = alpha * alpha;
+            auto block = [&](int i0, int i1, int which, int idx, double* guess) {
+                if (i1 <= i0) return;
+                double gn = 0.0;
+#pragma unroll
+                for (int u = 0; u < NPL; ++u) { const int i = lane + 32 * u; if (i >= i0 && i < i1) gn += S.g2[u]; }
+                gn = sb_warp_sum(gn);
+                int org; double tt;
+                arrow_root<NPL>(S, i0, i1, which, idx, a2, gn, (*guess) * a2, &org, &tt);
+                if (which != 2) *guess = (a2 > 0.0) ? tt / a2 : 0.0;
+                double lorg;
+                {
+                    const int q = org >> 5, src = org & 31;
+                    double v = 0.0;
+#pragma unroll
+                    for (int u = 0; u < NPL; ++u) if (u == q) v = S.lam[u];
+                    lorg = __shfl_sync(0xffffffffu, v, src);
+                }
+                double q2 = 0.0;
+#pragma unroll
+                for (int u = 0; u < NPL; ++u) {
+                    const int i = lane + 32 * u;
+                    if (i >= i0 && i < i1) { const double Dn = a2 * (S.lam[u] - lorg) - tt; q2 += S.g2[u] / (Dn * Dn); }
+                }
+                q2 = sb_warp_sum(q2);
+                const double mu = a2 * lorg + tt;
+                const double dmu = 2.0 * alpha * mu * q2 / (1.0 + a2 * q2);
+#pragma unroll
+                for (int u = 0; u < NPL; ++u) {
+                    const int i = lane + 32 * u;
+                    if (i >= i0 && i < i1) {
+                        const double Dn = a2 * (S.lam[u] - lorg) - tt;
+                        const double g = S.g[u];
+                        sreg[u] = -a2 * g / Dn;
+                        dreg[u] = (-2.0 * alpha * g * Dn + a2 * g * (2.0 * alpha * S.lam[u] - dmu)) / (Dn * Dn);
+                    }
+                }
+            };
+            if (mode == 0) block(0, n, mo == 0 ? 0 : (mo == n ? 1 : 2), mo, &guess_a);
+            else { block(0, mo, 1, mo, &guess_a); block(mo, n, 0, mo, &guess_b); }
+#pragma unroll
+            for (int u = 0; u < NPL; ++u) {
+                const int i = lane + 32 * u;
+                if (i < n) { c1[i] = sreg[u]; c2[i] = dreg[u]; }
+            }
+        }
+        __syncthreads();
+        // ---- s = V c1, ds = V c2
+        for (int j = tid; j < n; j += nt) {
+            double a = 0.0, d = 0.0;
+#pragma unroll 4
+            for (int i = 0; i < n; ++i) {
+                const double v = Vt[(size_t)i * n + j];
+                a = fma(v, c1[i], a);
+                d = fma(v, c2[i], d);
+            }
+            s[j] = a;
+            ds[j] = d;
+        }
+        __syncthreads();
+        double bv = -1.0; int bi = 0;
+        for (int a = tid; a < natoms; a += nt) {
+            const double x = s[3 * a], y = s[3 * a + 1], z = s[3 * a + 2];
+            const double nr = sqrt(x * x + y * y + z * z);
+            if (nr > bv) { bv = nr; bi = a; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { best_val[warp] = bv; best_idx[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            bv = best_val[0]; bi = best_idx[0];
+            for (int w = 1; w < nt / 32; ++w)
+                if (best_val[w] > bv || (best_val[w] == bv && best_idx[w] < bi)) { bv = best_val[w]; bi = best_idx[w]; }
+            val = bv;
+            dval = (ds[3 * bi] * s[3 * bi] + ds[3 * bi + 1] * s[3 * bi + 1] + ds[3 * bi + 2] * s[3 * bi + 2]) /
+                   fmax(bv, 1e-12);
+            int go = 1;
+            if (first && val < delta) { interior = true; go = 0; }
+            else {
+                const double err = val - delta;
+                if (fabs(err) <= 1e-15 || nextafter(lo, hi) >= hi) go = 0;
+                else if (it >= 200) { st = SB_ST_TR_NOCONV; go = 0; }
+                else {
+                    if (err > 0.0) hi = alpha; else lo = alpha;
+                    double a1 = alpha - err / dval;
+                    if (isnan(a1) || a1 <= lo || a1 >= hi) a1 = 0.5 * (lo + hi);
+                    if (a1 == alpha) go = 0;
+                    alpha = a1;
+                }
+            }
+            sh_alpha = alpha; sh_val = val; sh_dval = dval; sh_go = go;
+        }
+        first = false;
+        __syncthreads();
+        alpha = sh_alpha;
+        if (!sh_go) break;
+    }
+    for (int j = tid; j < n; j += nt) s_out[(size_t)b * n + j] = s[j];
+    if (tid == 0) {
+        smag[b] = interior ? sh_val : delta;
+        alpha_out[b] = alpha;
+        if (st && status) atomicOr(&status[b], st);
+    }
+}
+
 }  // namespace
 
 extern "C" int sb_rfo_tr_impl(const double* Vg, const double* evals, const double* delta, int order, int n, int mode,
@@ -263,5 +417,27 @@ extern "C" int sb_rfo_tr_impl(const double* Vg, const double* evals, const doubl
     else if (npl <= 48) SB_RFO(48);
     else return -2;      // n > 1536 not supported by this build
 #undef SB_RFO
+    return SB_LAUNCH_CHECK();
+}
+
+extern "C" int sb_rfo_ras_impl(const double* Vg, const double* evals, const double* Vt, const double* delta, int order,
+                               int n, int mode, double* s, double* smag, double* alpha, int* status,
+                               const int* active, int batch, cudaStream_t st) {
+    const int npl = (n + 31) / 32;
+    const size_t smem = (size_t)4 * n * sizeof(double);
+    SB_COUNT(1);
+#define SB_RFOR(N)                                                                                             \
+    cudaFuncSetAttribute(rfo_ras_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+    rfo_ras_kernel<N><<<batch, 256, smem, st>>>(Vg, evals, Vt, delta, order, n, mode, s, smag, alpha, status, \
+                                                active)
+    if (npl <= 4) { SB_RFOR(4); }
+    else if (npl <= 8) { SB_RFOR(8); }
+    else if (npl <= 12) { SB_RFOR(12); }
+    else if (npl <= 16) { SB_RFOR(16); }
+    else if (npl <= 24) { SB_RFOR(24); }
+    else if (npl <= 32) { SB_RFOR(32); }
+    else if (npl <= 48) { SB_RFOR(48); }
+    else return -2;
+#undef SB_RFOR
     return SB_LAUNCH_CHECK();
 }

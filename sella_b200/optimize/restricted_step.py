@@ -66,14 +66,17 @@ class BaseRestrictedStep:
                      _p(coef), _p(smag), _p(alpha), _p(status), _p(None), I(1), _stream())
             s = K.hv(Vt, coef.view(1, 1, n), transposed=True).view(1, n)
         else:
-            if self.model != "qn":
-                raise NotImplementedError("rfo/prfo with the restricted atomic step are not on the CUDA path yet")
             if getattr(self.pes, "int", None) is not None:
                 raise ValueError("Internal coordinates are not compatible with the RestrictedAtomicStep "
                                  "trust region method.")
             s = zeros(1, n)
-            call("sb_qn_ras", _p(Vg), _p(evals), _p(Vt), _p(d), I(self.order), I(n), _p(s), _p(smag), _p(alpha),
-                 _p(status), _p(None), I(1), _stream())
+            if self.model == "qn":
+                call("sb_qn_ras", _p(Vg), _p(evals), _p(Vt), _p(d), I(self.order), I(n), _p(s), _p(smag), _p(alpha),
+                     _p(status), _p(None), I(1), _stream())
+            else:
+                call("sb_rfo_ras", _p(Vg), _p(evals), _p(Vt), _p(d), I(self.order), I(n),
+                     I(int(self.model == "prfo")), _p(s), _p(smag), _p(alpha), _p(status), _p(None), I(1),
+                     _stream())
         raise_status(status, "restricted step")
         self.alpha = float(alpha[0])
         return s[0].cpu().numpy(), float(smag[0])

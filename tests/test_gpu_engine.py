@@ -84,20 +84,23 @@ def test_engine_matches_oracle_loop(n, rs, eig_mode):
             np.testing.assert_allclose(B[i] @ Vt[i].T, Vt[i].T * w[i][None, :], atol=1e-9)
 
 
+@pytest.mark.parametrize("rs", ["tr", "ras"])
 @pytest.mark.parametrize("method", ["prfo", "rfo"])
 @pytest.mark.parametrize("n", [30, 48, 96])
-def test_engine_rfo_models_match_oracle(n, method):
+def test_engine_rfo_models_match_oracle(n, method, rs):
     """P-RFO (Sella's default for saddles) and RFO through the arrow-head secular
     solver vs the oracle, which diagonalises the bordered matrix for every alpha."""
     from oracle.pes import CartesianPES
     from oracle.driver import SaddleSearch
     from sella_b200.synthetic import quadratic_func
     systems = [0, 1, 2, 3]
-    eng, data = make_engine(n, systems, method=method, rs="tr")
+    if method == "rfo" and rs == "ras":
+        pytest.skip("plain rfo on a saddle with a tiny atomic radius is ill-posed in the reference itself")
+    eng, data = make_engine(n, systems, method=method, rs=rs)
     oracles = []
     for (A, xs, x0) in data:
         p = CartesianPES(quadratic_func(A, xs), x0)
-        oracles.append((p, SaddleSearch(p, method=method, rs="tr")))
+        oracles.append((p, SaddleSearch(p, method=method, rs=rs)))
     for t in range(10):
         eng.step()
         x = eng.x.cpu().numpy(); delta = eng.delta.cpu().numpy()
@@ -116,7 +119,7 @@ def test_engine_matches_reference_golden(golden):
     for i in range(int(G["ncases"])):
         n, b, cc, method, rs, kw = G["meta%d" % i]
         kw = dict(eval(kw))
-        if cc != "0" or (method, rs) not in (("qn", "tr"), ("qn", "ras"), ("rfo", "tr")):
+        if cc != "0" or (method, rs) not in (("qn", "tr"), ("qn", "ras"), ("rfo", "tr"), ("prfo", "ras")):
             continue
         eng, _ = make_engine(int(n), [int(b)], method=method, rs=rs, **kw)
         X = G["x%d" % i]
@@ -138,7 +141,7 @@ def test_engine_matches_reference_golden(golden):
             np.testing.assert_allclose(eng.B[0].cpu().numpy(), G["B%d" % i], rtol=1e-6, atol=1e-7)
         assert eng.surface.neval == int(G["neval%d" % i][-1])
         done += 1
-    assert done >= 9
+    assert done >= 12
 
 
 def test_engine_davidson_k_fixed_384():
