@@ -156,19 +156,43 @@ int sb_secular_update(double* evals, double* Vt, double* Z, int zcap, const doub
  * ras: the Cartesian step itself (max atomic displacement constraint).               */
 int sb_qn_tr(const double* Vg, const double* evals, const double* delta, int order, int n,
              double* coef, double* smag, double* alpha, int32_t* status, const int32_t* active,
-             int batch, void* stream);
+             const double* extra2, int batch, void* stream);
+/* extra2 (may be NULL): |scons|^2 of the constraint-restoring part, added under the norm;
+ * sadd (may be NULL): scons itself, added to the Cartesian step before the atomic norms. */
 /* rational-function models (sella/optimize/stepper.py:114-185) with the spherical trust
  * region: mode 0 = rfo, 1 = prfo (Sella's default for saddles).  The bordered-matrix
  * eigenproblem per alpha is solved as an arrow-head secular equation in the eigenbasis. */
 int sb_rfo_tr(const double* Vg, const double* evals, const double* delta, int order, int n, int mode,
               double* coef, double* smag, double* alpha, int32_t* status, const int32_t* active,
-              int batch, void* stream);
+              const double* extra2, int batch, void* stream);
 int sb_rfo_ras(const double* Vg, const double* evals, const double* Vt, const double* delta,
                int order, int n, int mode, double* s, double* smag, double* alpha, int32_t* status,
-               const int32_t* active, int batch, void* stream);
+               const int32_t* active, const double* sadd, int batch, void* stream);
 int sb_qn_ras(const double* Vg, const double* evals, const double* Vt, const double* delta,
               int order, int n, double* s, double* smag, double* alpha, int32_t* status,
-              const int32_t* active, int batch, void* stream);
+              const int32_t* active, const double* sadd, int batch, void* stream);
+
+/* ---- linear constraints C x = c (sella/peswrapper.py:51-69, 395-407, 429-438, 558-568;
+ * restricted_step.py:28-49).  Thin row-wise matrices R [nr, n]; rstride = nr*n for
+ * per-system data, 0 when the batch shares one matrix.
+ *   sb_rect_dots : out[b,j] = R[j,:].x[b,:] - (c ? c[b,j] : 0)
+ *   sb_rect_comb : out[b,:] = beta*base[b,:] + scale * sum_j coef[b,j] R[j,:]
+ *   sb_scons_measure / sb_combine_step : size of the constraint-restoring step, the
+ *     "violation alone exceeds the radius" branch (NaiveStepper), s_tot = s_free + scons
+ *   sb_converged_cons : fmax over atoms of the projected gradient, cmax = |res|.        */
+int sb_rect_dots(const double* R, long long rstride, int nr, const double* x, long long xstride,
+                 const double* c, double* out, int n, const int32_t* active, int batch, void* stream);
+int sb_rect_comb(const double* R, long long rstride, int nr, const double* coef, double scale,
+                 const double* base, long long bstride, double beta, double* out, long long ostride,
+                 int n, const int32_t* active, int batch, void* stream);
+int sb_scons_measure(const double* scons, const double* delta, int kind, int n, double* scons2,
+                     double* consval, int32_t* naive, int32_t* regular, int batch, void* stream);
+int sb_combine_step(const double* slift, const double* scons, const double* consval,
+                    const double* delta, const int32_t* naive, double* stot, double* smag, int n,
+                    const int32_t* active, int batch, void* stream);
+int sb_converged_cons(const double* pg, const double* res, int nr, int n, double fmax_tol,
+                      double cmax_tol, double* fmax_out, double* cmax_out, int32_t* conv, int batch,
+                      void* stream);
 
 /* s = V c and |B| s = V(|lam| * c) from ONE transposed pass over Vt: pack the two
  * coefficient vectors [b,2,n], run sb_hv_ld(transposed, nvec=2), unpack.               */

@@ -60,7 +60,7 @@ class BatchedSella:
                  rho_dec=None, rho_inc=None, eig=None, eta=1e-4, method=None, gamma=0.1,
                  rs=None, nsteps_per_diag=3, diag_every_n=None, diag_maxiter=None,
                  eigensolver="jd0", update_method="TS-BFGS", kcap=16, eig_mode="update",
-                 eig_refresh_every=0):
+                 eig_refresh_every=0, constraints=None):
         require_cuda()
         d = _DEFAULTS["minimum" if order == 0 else "saddle"]
         self.surface = surface
@@ -159,9 +159,84 @@ class BatchedSella:
             self.Cmat = z(b, 32 * 33)
             self.nterm = zi(b)
             self.qwork = z(b, n, n)
+        self._setup_constraints(constraints)
+        if self.cons is not None and self.rs == "tr":
+            # optimize.py:183-187: the spherical radius scales with the number of free coordinates
+            self.delta.fill_(float(delta0 * self.cons["nfree"]))
         self.initialized = False
         self.ndiag = 0
         self.prof = None          # set to {} to collect CUDA-event timings of selected kernels
+
+    # ------------------------------------------------------------------ constraints
+    def _setup_constraints(self, constraints):
+        """Linear constraints C x = c (what Constraints.fix_translation yields).
+        `constraints` = (C, c) with C [nc, n] shared by the batch or [b, nc, n], c [b, nc] or
+        None (= the constraints hold at x0).  Bases follow peswrapper.py:51-69."""
+        self.cons = None
+        self.evalsB, self.VtB = self.evals, self.Vt            # spectrum of B itself
+        if constraints is None:
+            return
+        from scipy.linalg import qr
+        b, n, dev = self.batch, self.n, self.dev
+        C, c = constraints
+        C = np.asarray(C, dtype=np.float64)
+        shared = C.ndim == 2
+        Cs = C[None] if shared else C
+        nc = Cs.shape[1]
+        if nc == 0:
+            return
+        if self.eig_mode != "update":
+            raise NotImplementedError("constraints need eig_mode='update'")
+        Uc_l, M_l, Q_l, ranks = [], [], [], []
+        for Ci in Cs:
+            Q, R, _ = qr(Ci.T, mode="full", pivoting=True, check_finite=False)
+            dg = np.abs(np.diag(R))
+            rk = int(np.sum(dg > 1e-6 * dg[0])) if (dg.size and dg[0] > 0) else 0
+            Ucons, Ufree = Q[:, :rk], Q[:, rk:]
+            M = Ucons @ np.linalg.pinv(Ci @ Ucons)               # scons = -M res  (peswrapper.py:429-438)
+            Uc_l.append(Ucons.T.copy()); M_l.append(M.T.copy())
+            Q_l.append(np.vstack([Ufree.T, Ucons.T])); ranks.append(rk)
+        if len(set(ranks)) != 1:
+            raise NotImplementedError("all systems of a batch must have the same constraint rank")
+        rk = ranks[0]
+        up = lambda lst: torch.from_numpy(np.ascontiguousarray(np.stack(lst))).to(dev)   # noqa: E731
+        f64 = dict(dtype=torch.float64, device=dev)
+        cons = dict(shared=shared, nc=nc, rank=rk, nfree=n - rk,
+                    C=up(list(Cs)), Uc=up(Uc_l), Mr=up(M_l), Q=up(Q_l),
+                    cstride=0 if shared else nc * n, ustride=0 if shared else rk * n)
+        x0 = self.x
+        if c is None:
+            ctar = torch.einsum("bjn,bn->bj", cons["C"].expand(b, nc, n), x0) if shared else \
+                torch.einsum("bjn,bn->bj", cons["C"], x0)
+        else:
+            ctar = torch.from_numpy(np.ascontiguousarray(np.asarray(c, dtype=np.float64))).to(dev).reshape(b, nc)
+        cons["c"] = ctar.contiguous()
+        cons["res"] = torch.zeros(b, nc, **f64)
+        cons["uw"] = torch.zeros(b, max(rk, 1), **f64)
+        for k in ("scons", "gp", "pg", "slift"):
+            cons[k] = torch.zeros(b, n, **f64)
+        for k in ("scons2", "consval"):
+            cons[k] = torch.zeros(b, **f64)
+        cons["naive"] = torch.zeros(b, dtype=torch.int32, device=dev)
+        cons["regular"] = torch.ones(b, dtype=torch.int32, device=dev)
+        cons["cmax"] = torch.zeros(b, **f64)
+        self.cons = cons
+        # the step model lives on the projected Hessian Bp = P_f B P_f + sigma P_c; B keeps its own spectrum
+        self.evalsB = torch.zeros(b, n, **f64)
+        self.VtB = torch.zeros(b, n, n, **f64)
+
+    def _project_free(self, X, nvec, ld, active=None):
+        """X[b, :nvec, :] <- P_f X  (remove the components along Ucons), in place."""
+        cn = self.cons
+        b, n, rk = self.batch, self.n, cn["rank"]
+        if rk == 0:
+            return
+        for v in range(nvec):
+            xv = X[:, v]                                  # view [b, n], stride ld*n
+            call("sb_rect_dots", _p(cn["Uc"]), LL(cn["ustride"]), I(rk), _p(xv), LL(ld * n), _p(None),
+                 _p(cn["uw"]), I(n), _p(active), I(b), _stream())
+            call("sb_rect_comb", _p(cn["Uc"]), LL(cn["ustride"]), I(rk), _p(cn["uw"]), D(-1.0), _p(xv), LL(ld * n),
+                 D(1.0), _p(xv), LL(ld * n), I(n), _p(active), I(b), _stream())
 
     def _timed(self, name, fn):
         if self.prof is None:
@@ -190,8 +265,14 @@ class BatchedSella:
         call("sb_update_prep", _p(S), _p(Y), _p(bufs["Ytil"]), I(kc), _p(kvec), I(n), I(n), I(int(first)),
              _p(self.lam0), _p(self.skip), _p(self.status), _p(active), I(b), _stream())
         if first:
-            call("sb_fill_scaled_identity", _p(self.B), _p(self.evals), _p(self.Vt), _p(self.lam0), I(n),
+            call("sb_fill_scaled_identity", _p(self.B), _p(self.evalsB), _p(self.VtB), _p(self.lam0), I(n),
                  I(n), _p(self.skip), I(b), _stream())
+            if self.cons is not None:
+                # Bp = lam0 P_f + sigma P_c: eigenvectors = [Ufree; Ucons] rows, sigma > lam0
+                cn = self.cons
+                self.Vt.copy_(cn["Q"].expand(b, n, n) if cn["shared"] else cn["Q"])
+                self.evals[:, :cn["nfree"]] = self.lam0[:, None]
+                self.evals[:, cn["nfree"]:] = 8.0 * torch.clamp(self.lam0, min=1e-3)[:, None]
             self.H_initialized = True
             bs_ready = False
         if not bs_ready:
@@ -199,10 +280,10 @@ class BatchedSella:
         if first:
             abs_ready = False
         if self.update_method == 0 and not abs_ready:
-            K.hv_ld(self.Vt, S, bufs["VtS"], nv, active=active)
-            call("sb_abs_scale", _p(bufs["VtS"]), _p(self.evals), _p(bufs["aC"]), I(kc), I(n), _p(self.skip),
+            K.hv_ld(self.VtB, S, bufs["VtS"], nv, active=active)
+            call("sb_abs_scale", _p(bufs["VtS"]), _p(self.evalsB), _p(bufs["aC"]), I(kc), I(n), _p(self.skip),
                  I(b), _stream())
-            K.hv_ld(self.Vt, bufs["aC"], bufs["aBS"], nv, transposed=True, active=active)
+            K.hv_ld(self.VtB, bufs["aC"], bufs["aBS"], nv, transposed=True, active=active)
         track = self.eig_mode == "update" and (self.eig_valid or first)
         call("sb_update_mid", _p(S), _p(bufs["Ytil"]), _p(bufs["BS"]),
              _p(bufs["aBS"] if self.update_method == 0 else None), _p(bufs["U"]), _p(bufs["J"]), _p(bufs["W"]),
@@ -217,11 +298,21 @@ class BatchedSella:
             sec = self.sec1 if kc == 1 else self.seck
             call("sb_lowrank_factor", _p(bufs["U"]), _p(bufs["J"]), _p(self.Cmat), I(kc), _p(kvec), I(n),
                  _p(sec["P"]), _p(sec["sig"]), _p(self.nterm), _p(self.skip), I(b), _stream())
-            K.hv_ld(self.Vt, sec["P"], sec["Z"], 2 * nv, active=active)
+            K.hv_ld(self.VtB, sec["P"], sec["Z"], 2 * nv, active=active)
             self._timed("secular_update_k%d" % kc, lambda: call(
-                "sb_secular_update", _p(self.evals), _p(self.Vt), _p(sec["Z"]), I(2 * kc), _p(sec["sig"]),
+                "sb_secular_update", _p(self.evalsB), _p(self.VtB), _p(sec["Z"]), I(2 * kc), _p(sec["sig"]),
                 _p(self.nterm), I(n), _p(self.eig_ws.work), _p(self.qwork), _p(self.status), _p(self.skip),
                 I(b), _stream()))
+            if self.cons is not None:
+                # same update seen through the projector: Bp+ = Bp + P_f Delta P_f
+                self._project_free(bufs["U"], nv, kc, active)
+                self._project_free(bufs["J"], nv, kc, active)
+                call("sb_lowrank_factor", _p(bufs["U"]), _p(bufs["J"]), _p(self.Cmat), I(kc), _p(kvec), I(n),
+                     _p(sec["P"]), _p(sec["sig"]), _p(self.nterm), _p(self.skip), I(b), _stream())
+                K.hv_ld(self.Vt, sec["P"], sec["Z"], 2 * nv, active=active)
+                call("sb_secular_update", _p(self.evals), _p(self.Vt), _p(sec["Z"]), I(2 * kc), _p(sec["sig"]),
+                     _p(self.nterm), I(n), _p(self.eig_ws.work), _p(self.qwork), _p(self.status), _p(self.skip),
+                     I(b), _stream())
             self.eig_valid = True
         else:
             self.eig_valid = False
@@ -233,9 +324,19 @@ class BatchedSella:
         call("sb_hvp_prepare", _p(vec), LL(vstride), _p(self.x), _p(self.g), D(self.eta), _p(self.xdisp),
              _p(self.signnorm), I(n), _p(mask), I(maskval), I(b), _stream())
         self.surface.evaluate(self.xdisp, self.fplus, self.gplus, active=active)
+        if self.cons is not None:
+            kslot = self.ksz.clone()                   # slot that hvp_finish is about to fill
         call("sb_hvp_finish", _p(vec), LL(vstride), _p(self.gplus), _p(self.g), _p(self.signnorm), D(self.eta),
              _p(self.AV), _p(self.Vs), _p(self.AVs), I(self.kcap), _p(self.ksz), _p(self.nhist), I(n),
              _p(mask), I(maskval), I(b), _stream())
+        if self.cons is not None:
+            # Uproj^T (H v): the subspace image lives in the free space (linalg.py:92-93); the
+            # operator history (Vs, AVs) keeps the unprojected vector, as the reference does
+            kmax = int(kslot.max().item())
+            for k in range(kmax + 1):
+                m = ((kslot == k) & (active > 0)).to(torch.int32) if active is not None else (kslot == k).to(torch.int32)
+                if int(m.sum().item()):
+                    self._project_free(self.AV[:, k:k + 1], 1, self.kcap, m)
 
     def _diag(self, part=None):
         """PES.diag (peswrapper.py:508-556) for the systems with part[b] != 0."""
@@ -243,7 +344,12 @@ class BatchedSella:
         first = not self.H_initialized          # P = identity, v0 = g
         if not first and not self.eig_valid:
             self._eigh(active=part)             # spectrum of the preconditioner P = B
-        call("sb_davidson_init", _p(self.g), _p(self.evals), _p(self.Vt), I(0 if first else 1), _p(self.V),
+        v0 = self.g
+        if self.cons is not None and first:
+            v0 = self.cons["pg"]
+            v0.copy_(self.g)
+            self._project_free(v0.view(b, 1, n), 1, 1, part)            # Ufree^T g, lifted (peswrapper.py:524)
+        call("sb_davidson_init", _p(v0), _p(self.evals), _p(self.Vt), I(0 if first else 1), _p(self.V),
              I(kc), I(n), _p(self.ksz), _p(self.ninit), _p(self.nhist), _p(self.dav_state), _p(self.status),
              _p(part), I(b), _stream())
         nstart = 1 if first else int(self.ninit.max().item())
@@ -295,31 +401,59 @@ class BatchedSella:
         if not self.eig_valid:
             self._eigh(active)
             self.eig_valid = True
-        K.hv_ld(self.Vt, self.g.view(b, 1, n), self.Vg.view(b, 1, n), 1, active=active)
+        cn = self.cons
+        gvec, extra2, sadd, act_rs = self.g, None, None, active
+        if cn is not None:
+            # scons = -Ucons lstsq(C Ucons, res);  g' = P_f (g + B scons)   (restricted_step.py:28-37)
+            nc = cn["nc"]
+            call("sb_rect_dots", _p(cn["C"]), LL(cn["cstride"]), I(nc), _p(self.x), LL(n), _p(cn["c"]),
+                 _p(cn["res"]), I(n), _p(active), I(b), _stream())
+            call("sb_rect_comb", _p(cn["Mr"]), LL(cn["cstride"]), I(nc), _p(cn["res"]), D(-1.0), _p(None), LL(0),
+                 D(0.0), _p(cn["scons"]), LL(n), I(n), _p(active), I(b), _stream())
+            call("sb_scons_measure", _p(cn["scons"]), _p(self.delta), I(0 if self.rs == "tr" else 1), I(n),
+                 _p(cn["scons2"]), _p(cn["consval"]), _p(cn["naive"]), _p(cn["regular"]), I(b), _stream())
+            K.hv_ld(self.B, cn["scons"].view(b, 1, n), cn["gp"].view(b, 1, n), 1, active=active)
+            call("sb_axpy", _p(self.g), _p(cn["gp"]), _p(cn["gp"]), I(n), _p(active), I(b), _stream())
+            self._project_free(cn["gp"].view(b, 1, n), 1, 1, active)
+            gvec, extra2, sadd = cn["gp"], cn["scons2"], cn["scons"]
+            act_rs = cn["regular"] if active is None else (cn["regular"] * active)
+        K.hv_ld(self.Vt, gvec.view(b, 1, n), self.Vg.view(b, 1, n), 1, active=active)
+        sdst = self.s if cn is None else cn["slift"]
         if self.rs == "tr":
             if self.method == "qn":
                 call("sb_qn_tr", _p(self.Vg), _p(self.evals), _p(self.delta), I(self.order), I(n), _p(self.coef),
-                     _p(self.smag), _p(self.alpha), _p(self.status), _p(active), I(b), _stream())
+                     _p(self.smag), _p(self.alpha), _p(self.status), _p(act_rs), _p(extra2), I(b), _stream())
             else:
                 call("sb_rfo_tr", _p(self.Vg), _p(self.evals), _p(self.delta), I(self.order), I(n),
                      I(1 if self.method == "prfo" else 0), _p(self.coef), _p(self.smag), _p(self.alpha),
-                     _p(self.status), _p(active), I(b), _stream())
-            # s = V c and |B| s = V(|lam| c) (needed by the TS-BFGS update) in one pass over Vt
-            call("sb_pack_coef", _p(self.coef), _p(self.evals), _p(self.c2), I(n), _p(active), I(b), _stream())
-            K.hv_ld(self.Vt, self.c2, self.s2, 2, transposed=True, active=active)
-            call("sb_unpack2", _p(self.s2), _p(self.s), _p(self.up1["aBS"]), I(n), _p(active), I(b), _stream())
-            abs_ready = True
+                     _p(self.status), _p(act_rs), _p(extra2), I(b), _stream())
+            if cn is None:
+                # s = V c and |B| s = V(|lam| c) (needed by the TS-BFGS update) in one pass over Vt
+                call("sb_pack_coef", _p(self.coef), _p(self.evals), _p(self.c2), I(n), _p(active), I(b), _stream())
+                K.hv_ld(self.Vt, self.c2, self.s2, 2, transposed=True, active=active)
+                call("sb_unpack2", _p(self.s2), _p(self.s), _p(self.up1["aBS"]), I(n), _p(active), I(b), _stream())
+                abs_ready = True
+            else:
+                K.hv_ld(self.Vt, self.coef.view(b, 1, n), sdst.view(b, 1, n), 1, transposed=True, active=active)
+                abs_ready = False
         elif self.method != "qn":
             abs_ready = False
             call("sb_rfo_ras", _p(self.Vg), _p(self.evals), _p(self.Vt), _p(self.delta), I(self.order), I(n),
-                 I(1 if self.method == "prfo" else 0), _p(self.s), _p(self.smag), _p(self.alpha),
-                 _p(self.status), _p(active), I(b), _stream())
+                 I(1 if self.method == "prfo" else 0), _p(sdst), _p(self.smag), _p(self.alpha),
+                 _p(self.status), _p(act_rs), _p(sadd), I(b), _stream())
         else:
             abs_ready = False
             call("sb_qn_ras", _p(self.Vg), _p(self.evals), _p(self.Vt), _p(self.delta), I(self.order), I(n),
-                 _p(self.s), _p(self.smag), _p(self.alpha), _p(self.status), _p(active), I(b), _stream())
-        # ---- re-diagonalise?  (spectrum of the Hessian before this step's update)
-        call("sb_ev_decide", _p(self.evals), I(n), I(1), _p(self.since_diag), _p(self.ev), self._dpar,
+                 _p(sdst), _p(self.smag), _p(self.alpha), _p(self.status), _p(act_rs), _p(sadd), I(b), _stream())
+        if cn is not None:
+            if self.rs != "tr":
+                # the ras kernels return the total step (s_free + scons): take scons out again so that
+                # combine_step handles both branches uniformly
+                sdst.sub_(cn["scons"])
+            call("sb_combine_step", _p(sdst), _p(cn["scons"]), _p(cn["consval"]), _p(self.delta), _p(cn["naive"]),
+                 _p(self.s), _p(self.smag), I(n), _p(active), I(b), _stream())
+        # ---- re-diagonalise?  (spectrum of the Hessian itself, before this step's update)
+        call("sb_ev_decide", _p(self.evalsB), I(n), I(1), _p(self.since_diag), _p(self.ev), self._dpar,
              self._ipar, _p(active), I(b), _stream())
         # ---- kick
         call("sb_axpy", _p(self.x), _p(self.s), _p(self.xnew), I(n), _p(active), I(b), _stream())
@@ -333,9 +467,19 @@ class BatchedSella:
         if self.eig and int(self.ev.sum().item()) > 0:
             self._diag(self.ev)
 
-    def converged(self, fmax):
-        call("sb_converged", _p(self.g), I(self.n), D(float(fmax)), _p(self.fmax), _p(self.conv),
-             I(self.batch), _stream())
+    def converged(self, fmax, cmax=1e-5):
+        """PES.converged (peswrapper.py:558-568): max atomic |P_f g| < fmax and |res| < cmax."""
+        b, n = self.batch, self.n
+        cn = self.cons
+        if cn is None:
+            call("sb_converged", _p(self.g), I(n), D(float(fmax)), _p(self.fmax), _p(self.conv), I(b), _stream())
+            return self.conv
+        cn["pg"].copy_(self.g)
+        self._project_free(cn["pg"].view(b, 1, n), 1, 1)
+        call("sb_rect_dots", _p(cn["C"]), LL(cn["cstride"]), I(cn["nc"]), _p(self.x), LL(n), _p(cn["c"]),
+             _p(cn["res"]), I(n), _p(None), I(b), _stream())
+        call("sb_converged_cons", _p(cn["pg"]), _p(cn["res"]), I(cn["nc"]), I(n), D(float(fmax)), D(float(cmax)),
+             _p(self.fmax), _p(cn["cmax"]), _p(self.conv), I(b), _stream())
         return self.conv
 
     def check_status(self):

@@ -40,12 +40,22 @@ extern "C" int sb_secular_update_impl(double*, double*, double*, int, const doub
 extern "C" int sb_update_apply_impl(double*, const double*, const double*, const double*, int, const int*, int,
                                     const int*, int, cudaStream_t);
 extern "C" int sb_qn_tr_impl(const double*, const double*, const double*, int, int, double*, double*, double*, int*,
-                             const int*, int, cudaStream_t);
+                             const int*, const double*, int, cudaStream_t);
 extern "C" int sb_qn_ras_impl(const double*, const double*, const double*, const double*, int, int, double*,
-                              double*, double*, int*, const int*, int, cudaStream_t);
+                              double*, double*, int*, const int*, const double*, int, cudaStream_t);
+extern "C" int sb_rect_dots_impl(const double*, long long, int, const double*, long long, const double*, double*, int,
+                                 const int*, int, cudaStream_t);
+extern "C" int sb_rect_comb_impl(const double*, long long, int, const double*, double, const double*, long long,
+                                 double, double*, long long, int, const int*, int, cudaStream_t);
+extern "C" int sb_scons_measure_impl(const double*, const double*, int, int, double*, double*, int*, int*, int,
+                                     cudaStream_t);
+extern "C" int sb_combine_step_impl(const double*, const double*, const double*, const double*, const int*, double*,
+                                    double*, int, const int*, int, cudaStream_t);
+extern "C" int sb_converged_cons_impl(const double*, const double*, int, int, double, double, double*, double*, int*,
+                                      int, cudaStream_t);
 extern "C" int sb_axpy_impl(const double*, const double*, double*, int, const int*, int, cudaStream_t);
 extern "C" int sb_rfo_tr_impl(const double*, const double*, const double*, int, int, int, double*, double*, double*,
-                              int*, const int*, int, cudaStream_t);
+                              int*, const int*, const double*, int, cudaStream_t);
 extern "C" int sb_pack_coef_impl(const double*, const double*, double*, int, const int*, int, cudaStream_t);
 extern "C" int sb_unpack2_impl(const double*, double*, double*, int, const int*, int, cudaStream_t);
 extern "C" int sb_kick_finish_impl(double*, double*, double*, const double*, const double*, const double*,
@@ -212,27 +222,52 @@ int sb_update_apply(double* B, const double* U, const double* J, const double* W
     return sb_update_apply_impl(B, U, J, W, kcap, kvec, n, skip, batch, ST);
 }
 int sb_qn_tr(const double* Vg, const double* evals, const double* delta, int order, int n, double* coef,
-             double* smag, double* alpha, int32_t* status, const int32_t* active, int batch, void* stream) {
-    return sb_qn_tr_impl(Vg, evals, delta, order, n, coef, smag, alpha, status, active, batch, ST);
+             double* smag, double* alpha, int32_t* status, const int32_t* active, const double* extra2, int batch,
+             void* stream) {
+    return sb_qn_tr_impl(Vg, evals, delta, order, n, coef, smag, alpha, status, active, extra2, batch, ST);
 }
 int sb_rfo_tr(const double* Vg, const double* evals, const double* delta, int order, int n, int mode, double* coef,
-              double* smag, double* alpha, int32_t* status, const int32_t* active, int batch, void* stream) {
+              double* smag, double* alpha, int32_t* status, const int32_t* active, const double* extra2, int batch,
+              void* stream) {
     if (mode < 0 || mode > 1 || order < 0) return -1;
-    return sb_rfo_tr_impl(Vg, evals, delta, order, n, mode, coef, smag, alpha, status, active, batch, ST);
+    return sb_rfo_tr_impl(Vg, evals, delta, order, n, mode, coef, smag, alpha, status, active, extra2, batch, ST);
 }
 extern "C" int sb_rfo_ras_impl(const double*, const double*, const double*, const double*, int, int, int, double*,
-                               double*, double*, int*, const int*, int, cudaStream_t);
+                               double*, double*, int*, const int*, const double*, int, cudaStream_t);
 int sb_rfo_ras(const double* Vg, const double* evals, const double* Vt, const double* delta, int order, int n,
-               int mode, double* s, double* smag, double* alpha, int32_t* status, const int32_t* active, int batch,
-               void* stream) {
+               int mode, double* s, double* smag, double* alpha, int32_t* status, const int32_t* active,
+               const double* sadd, int batch, void* stream) {
     if (n % 3 || mode < 0 || mode > 1) return -1;
-    return sb_rfo_ras_impl(Vg, evals, Vt, delta, order, n, mode, s, smag, alpha, status, active, batch, ST);
+    return sb_rfo_ras_impl(Vg, evals, Vt, delta, order, n, mode, s, smag, alpha, status, active, sadd, batch, ST);
 }
 int sb_qn_ras(const double* Vg, const double* evals, const double* Vt, const double* delta, int order, int n,
-              double* s, double* smag, double* alpha, int32_t* status, const int32_t* active, int batch,
-              void* stream) {
+              double* s, double* smag, double* alpha, int32_t* status, const int32_t* active, const double* sadd,
+              int batch, void* stream) {
     if (n % 3) return -1;
-    return sb_qn_ras_impl(Vg, evals, Vt, delta, order, n, s, smag, alpha, status, active, batch, ST);
+    return sb_qn_ras_impl(Vg, evals, Vt, delta, order, n, s, smag, alpha, status, active, sadd, batch, ST);
+}
+int sb_rect_dots(const double* R, long long rstride, int nr, const double* x, long long xstride, const double* c,
+                 double* out, int n, const int32_t* active, int batch, void* stream) {
+    if (nr <= 0) return 0;
+    return sb_rect_dots_impl(R, rstride, nr, x, xstride, c, out, n, active, batch, ST);
+}
+int sb_rect_comb(const double* R, long long rstride, int nr, const double* coef, double scale, const double* base,
+                 long long bstride, double beta, double* out, long long ostride, int n, const int32_t* active,
+                 int batch, void* stream) {
+    return sb_rect_comb_impl(R, rstride, nr, coef, scale, base, bstride, beta, out, ostride, n, active, batch, ST);
+}
+int sb_scons_measure(const double* scons, const double* delta, int kind, int n, double* scons2, double* consval,
+                     int32_t* naive, int32_t* regular, int batch, void* stream) {
+    return sb_scons_measure_impl(scons, delta, kind, n, scons2, consval, naive, regular, batch, ST);
+}
+int sb_combine_step(const double* slift, const double* scons, const double* consval, const double* delta,
+                    const int32_t* naive, double* stot, double* smag, int n, const int32_t* active, int batch,
+                    void* stream) {
+    return sb_combine_step_impl(slift, scons, consval, delta, naive, stot, smag, n, active, batch, ST);
+}
+int sb_converged_cons(const double* pg, const double* res, int nr, int n, double fmax_tol, double cmax_tol,
+                      double* fmax_out, double* cmax_out, int32_t* conv, int batch, void* stream) {
+    return sb_converged_cons_impl(pg, res, nr, n, fmax_tol, cmax_tol, fmax_out, cmax_out, conv, batch, ST);
 }
 int sb_pack_coef(const double* coef, const double* evals, double* out2, int n, const int32_t* active, int batch,
                  void* stream) {

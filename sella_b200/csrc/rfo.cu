@@ -178,7 +178,8 @@ template <int NPL>
 __global__ void __launch_bounds__(RFO_WARPS * 32)
 rfo_tr_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_, const double* __restrict__ delta_,
               int order, int n, int mode, double* __restrict__ coef_, double* __restrict__ smag,
-              double* __restrict__ alpha_out, int* __restrict__ status, const int* __restrict__ active, int batch) {
+              double* __restrict__ alpha_out, int* __restrict__ status, const int* __restrict__ active, int batch,
+              const double* __restrict__ extra2_) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * RFO_WARPS + warp;
     if (b >= batch) return;
@@ -193,6 +194,7 @@ rfo_tr_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_,
         S.g2[u] = S.g[u] * S.g[u];
     }
     const double delta = delta_[b];
+    const double extra2 = extra2_ ? extra2_[b] : 0.0;
     const int mo = order < n ? order : n;
     double guess_a = 0.0, guess_b = 0.0;
     double sreg[NPL];
@@ -207,7 +209,7 @@ rfo_tr_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_,
             rfo_block<NPL>(S, mo, n, 0, mo, alpha, &guess_b, &s2, &d2, store ? sreg : nullptr);
             ss = s1 + s2; sds = d1 + d2;
         }
-        *val = sqrt(ss);
+        *val = sqrt(ss + extra2);
         *dval = sds / fmax(*val, 1e-12);
     };
     // restricted_step.py:78-121 with alpha0 = 1 on [0, 1], slope = +1
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(256)
 rfo_ras_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_, const double* __restrict__ Vt_,
                const double* __restrict__ delta_, int order, int n, int mode, double* __restrict__ s_out,
                double* __restrict__ smag, double* __restrict__ alpha_out, int* __restrict__ status,
-               const int* __restrict__ active) {
+               const int* __restrict__ active, const double* __restrict__ sadd_) {
     const int b = blockIdx.x;
     if (active && !active[b]) return;
     extern __shared__ double sm[];
@@ -344,7 +346,7 @@ rfo_ras_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_
                 a = fma(v, c1[i], a);
                 d = fma(v, c2[i], d);
             }
-            s[j] = a;
+            s[j] = a + (sadd_ ? sadd_[(size_t)b * n + j] : 0.0);
             ds[j] = d;
         }
         __syncthreads();
@@ -400,14 +402,14 @@ rfo_ras_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_
 }  // namespace
 
 extern "C" int sb_rfo_tr_impl(const double* Vg, const double* evals, const double* delta, int order, int n, int mode,
-                              double* coef, double* smag, double* alpha, int* status, const int* active, int batch,
-                              cudaStream_t st) {
+                              double* coef, double* smag, double* alpha, int* status, const int* active,
+                              const double* extra2, int batch, cudaStream_t st) {
     const int grid = (batch + RFO_WARPS - 1) / RFO_WARPS;
     const int npl = (n + 31) / 32;
     SB_COUNT(1);
 #define SB_RFO(N)                                                                                                    \
     rfo_tr_kernel<N><<<grid, RFO_WARPS * 32, 0, st>>>(Vg, evals, delta, order, n, mode, coef, smag, alpha, status, \
-                                                      active, batch)
+                                                      active, batch, extra2)
     if (npl <= 4) SB_RFO(4);
     else if (npl <= 8) SB_RFO(8);
     else if (npl <= 12) SB_RFO(12);
@@ -422,14 +424,14 @@ extern "C" int sb_rfo_tr_impl(const double* Vg, const double* evals, const doubl
 
 extern "C" int sb_rfo_ras_impl(const double* Vg, const double* evals, const double* Vt, const double* delta, int order,
                                int n, int mode, double* s, double* smag, double* alpha, int* status,
-                               const int* active, int batch, cudaStream_t st) {
+                               const int* active, const double* sadd, int batch, cudaStream_t st) {
     const int npl = (n + 31) / 32;
     const size_t smem = (size_t)4 * n * sizeof(double);
     SB_COUNT(1);
 #define SB_RFOR(N)                                                                                             \
     cudaFuncSetAttribute(rfo_ras_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
     rfo_ras_kernel<N><<<batch, 256, smem, st>>>(Vg, evals, Vt, delta, order, n, mode, s, smag, alpha, status, \
-                                                active)
+                                                active, sadd)
     if (npl <= 4) { SB_RFOR(4); }
     else if (npl <= 8) { SB_RFOR(8); }
     else if (npl <= 12) { SB_RFOR(12); }

@@ -56,7 +56,7 @@ __device__ __forceinline__ bool alpha_next(AlphaSearch& s, double delta, double 
 __global__ void __launch_bounds__(TR_THREADS)
 qn_tr_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_, const double* __restrict__ delta_,
              int order, int n, double* __restrict__ coef_, double* __restrict__ smag, double* __restrict__ alpha_out,
-             int* __restrict__ status, const int* __restrict__ active) {
+             int* __restrict__ status, const int* __restrict__ active, const double* __restrict__ extra2_) {
     const int b = blockIdx.x;
     if (active && !active[b]) return;
     extern __shared__ double sm[];
@@ -71,6 +71,8 @@ qn_tr_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_, 
     }
     __syncthreads();
     const double delta = delta_[b];
+    // |s_tot|^2 = |s_free|^2 + |scons|^2 (scons is orthogonal to the free space)
+    const double extra2 = extra2_ ? extra2_[b] : 0.0;
     AlphaSearch S;
     S.alpha = 0.0; S.lo = 0.0; S.hi = INFINITY; S.iter = 0; S.status = 0;
     const double tol = 1e-10, slope = -1.0;
@@ -86,7 +88,7 @@ qn_tr_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_, 
             c = fma(ci, ci / den, c);
         }
         sb_block_sum2(a, c, scratch);
-        S.val = sqrt(a);
+        S.val = sqrt(a + extra2);
         S.dval = -c / fmax(S.val, 1e-12);
         if (S.iter == 0 && S.alpha == 0.0 && S.val < delta) { interior = true; break; }
         S.err = S.val - delta;
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(TR_THREADS)
 qn_ras_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_, const double* __restrict__ Vt_,
               const double* __restrict__ delta_, int order, int n, double* __restrict__ s_out,
               double* __restrict__ smag, double* __restrict__ alpha_out, int* __restrict__ status,
-              const int* __restrict__ active) {
+              const int* __restrict__ active, const double* __restrict__ sadd_) {
     const int b = blockIdx.x;
     if (active && !active[b]) return;
     extern __shared__ double sm[];
@@ -153,7 +155,7 @@ qn_ras_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_,
                 a = fma(v, c1[i], a);
                 d = fma(v, c2[i], d);
             }
-            s[j] = -a;
+            s[j] = -a + (sadd_ ? sadd_[(size_t)b * n + j] : 0.0);      // + scons (constraint restoring part)
             ds[j] = d;
         }
         __syncthreads();
@@ -321,22 +323,24 @@ converged_kernel(const double* __restrict__ g, int n, double fmax_tol, double* _
 }  // namespace
 
 extern "C" int sb_qn_tr_impl(const double* Vg, const double* evals, const double* delta, int order, int n,
-                             double* coef, double* smag, double* alpha, int* status, const int* active, int batch,
-                             cudaStream_t st) {
+                             double* coef, double* smag, double* alpha, int* status, const int* active,
+                             const double* extra2, int batch, cudaStream_t st) {
     const size_t smem = (size_t)(2 * n + SB_SCRATCH_DOUBLES) * sizeof(double);
     cudaFuncSetAttribute(qn_tr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     SB_COUNT(1);
-    qn_tr_kernel<<<batch, TR_THREADS, smem, st>>>(Vg, evals, delta, order, n, coef, smag, alpha, status, active);
+    qn_tr_kernel<<<batch, TR_THREADS, smem, st>>>(Vg, evals, delta, order, n, coef, smag, alpha, status, active,
+                                                  extra2);
     return SB_LAUNCH_CHECK();
 }
 
 extern "C" int sb_qn_ras_impl(const double* Vg, const double* evals, const double* Vt, const double* delta,
                               int order, int n, double* s, double* smag, double* alpha, int* status,
-                              const int* active, int batch, cudaStream_t st) {
+                              const int* active, const double* sadd, int batch, cudaStream_t st) {
     const size_t smem = (size_t)(6 * n + SB_SCRATCH_DOUBLES) * sizeof(double);
     cudaFuncSetAttribute(qn_ras_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     SB_COUNT(1);
-    qn_ras_kernel<<<batch, TR_THREADS, smem, st>>>(Vg, evals, Vt, delta, order, n, s, smag, alpha, status, active);
+    qn_ras_kernel<<<batch, TR_THREADS, smem, st>>>(Vg, evals, Vt, delta, order, n, s, smag, alpha, status, active,
+                                                   sadd);
     return SB_LAUNCH_CHECK();
 }
 

@@ -60,10 +60,10 @@ class BaseRestrictedStep:
         if self.kind == "tr":
             if self.model == "qn":
                 call("sb_qn_tr", _p(Vg), _p(evals), _p(d), I(self.order), I(n), _p(coef), _p(smag), _p(alpha),
-                     _p(status), _p(None), I(1), _stream())
+                     _p(status), _p(None), _p(None), I(1), _stream())
             else:
                 call("sb_rfo_tr", _p(Vg), _p(evals), _p(d), I(self.order), I(n), I(int(self.model == "prfo")),
-                     _p(coef), _p(smag), _p(alpha), _p(status), _p(None), I(1), _stream())
+                     _p(coef), _p(smag), _p(alpha), _p(status), _p(None), _p(None), I(1), _stream())
             s = K.hv(Vt, coef.view(1, 1, n), transposed=True).view(1, n)
         else:
             if getattr(self.pes, "int", None) is not None:
@@ -72,11 +72,11 @@ class BaseRestrictedStep:
             s = zeros(1, n)
             if self.model == "qn":
                 call("sb_qn_ras", _p(Vg), _p(evals), _p(Vt), _p(d), I(self.order), I(n), _p(s), _p(smag), _p(alpha),
-                     _p(status), _p(None), I(1), _stream())
+                     _p(status), _p(None), _p(None), I(1), _stream())
             else:
                 call("sb_rfo_ras", _p(Vg), _p(evals), _p(Vt), _p(d), I(self.order), I(n),
-                     I(int(self.model == "prfo")), _p(s), _p(smag), _p(alpha), _p(status), _p(None), I(1),
-                     _stream())
+                     I(int(self.model == "prfo")), _p(s), _p(smag), _p(alpha), _p(status), _p(None), _p(None),
+                     I(1), _stream())
         raise_status(status, "restricted step")
         self.alpha = float(alpha[0])
         return s[0].cpu().numpy(), float(smag[0])

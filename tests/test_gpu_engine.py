@@ -161,3 +161,65 @@ def test_engine_davidson_k_fixed_384():
         lam_ref = p.last_rr[0]
         lam = eng.lams[i, :len(lam_ref)].cpu().numpy()
         np.testing.assert_allclose(lam, lam_ref, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("method,rs", [("qn", "tr"), ("qn", "ras"), ("prfo", "ras"), ("prfo", "tr")])
+@pytest.mark.parametrize("n", [30, 48])
+def test_engine_with_fixed_atom_constraints_matches_oracle(n, method, rs):
+    """Linear constraints (two atoms held fixed, as Constraints.fix_translation does):
+    Ufree != I, projected Hessian spectrum carried by its own secular updates."""
+    from oracle.pes import CartesianPES
+    from oracle.driver import SaddleSearch
+    from sella_b200.synthetic import quadratic_func
+    systems = [0, 1, 2]
+    C = np.eye(n)[:6]
+    eng, data = make_engine(n, systems, method=method, rs=rs, constraints=(C, None))
+    oracles = []
+    for (A, xs, x0) in data:
+        p = CartesianPES(quadratic_func(A, xs), x0, C, C @ x0)
+        oracles.append((p, SaddleSearch(p, method=method, rs=rs)))
+    for t in range(10):
+        eng.step()
+        x = eng.x.cpu().numpy(); delta = eng.delta.cpu().numpy()
+        for i, (p, o) in enumerate(oracles):
+            o.step()
+            tight = t < 8        # afterwards rho is a ratio of ~1e-13 numbers (see the golden test above)
+            np.testing.assert_allclose(x[i], p.get_x(), rtol=0, atol=1e-8 if tight else 1e-6,
+                                       err_msg="system %d step %d" % (i, t))
+            if tight:
+                np.testing.assert_allclose(delta[i], o.delta, rtol=1e-8)
+    eng.check_status()
+    x = eng.x.cpu().numpy()
+    for i, (A, xs, x0) in enumerate(data):
+        np.testing.assert_array_equal(x[i, :6], x0[:6])           # fixed coordinates never move
+    conv = eng.converged(1e-3).cpu().numpy()
+    for i, (p, o) in enumerate(oracles):
+        c_ref, f_ref, _ = p.converged(1e-3)
+        assert bool(conv[i]) == bool(c_ref)
+        np.testing.assert_allclose(float(eng.fmax[i]), f_ref, rtol=1e-3, atol=1e-7)
+
+
+def test_engine_constraints_golden(golden):
+    """Constrained cases of tests/golden/loop.npz (reference's own Sella + PES)."""
+    G = golden("loop")
+    done = 0
+    for i in range(int(G["ncases"])):
+        n, b, cc, method, rs, kw = G["meta%d" % i]
+        kw = dict(eval(kw))
+        if cc != "1" or (method, rs) not in (("qn", "tr"), ("qn", "ras"), ("prfo", "ras")):
+            continue
+        n = int(n)
+        C = np.eye(n)[:6]
+        eng, _ = make_engine(n, [int(b)], method=method, rs=rs, constraints=(C, None), **kw)
+        X = G["x%d" % i]
+        for t in range(10):
+            eng.step()
+            # gamma=1e-3 means dozens of Davidson expansions per diagonalisation, which amplify
+            # round-off (reference vs its own restatement differ there too, see DESIGN.md)
+            tight = t < 8 and kw.get("gamma", 0.1) >= 0.1
+            np.testing.assert_allclose(eng.x[0].cpu().numpy(), X[t], rtol=0, atol=1e-8 if tight else 1e-6,
+                                       err_msg="%s step %d" % (G["meta%d" % i], t))
+            if tight:
+                np.testing.assert_allclose(float(eng.delta[0]), G["delta%d" % i][t], rtol=1e-8)
+        done += 1
+    assert done >= 6
