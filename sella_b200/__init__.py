@@ -16,6 +16,9 @@ def __getattr__(name):          # lazy: importing the package must not need torc
     if name == "Sella":
         from .optimize.optimize import Sella
         return Sella
+    if name == "Constraints":
+        from .constraints import Constraints
+        return Constraints
     if name in ("BatchedSella", "QuadraticSurface"):
         from . import batched
         return getattr(batched, name)

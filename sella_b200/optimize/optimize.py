@@ -11,9 +11,11 @@ If ASE is importable the class derives from ``ase.optimize.optimize.Optimizer`` 
 class with the same ``run(fmax, steps)`` loop is used.
 
 Scope (raises NotImplementedError otherwise, never falls back to the CPU): Cartesian
-coordinates, no constraints (``proj_trans=False, proj_rot=False`` must be passed for
-non-periodic systems, because the reference would otherwise add translation/rotation
-constraints), ``threepoint=False``, no ``hessian_function``, no cell optimisation.
+coordinates; translation constraints (``sella_b200.Constraints.fix_translation``, incl.
+the centre-of-geometry projection the reference adds by default, peswrapper.py:233-244);
+no rotation projection (pass ``proj_rot=False`` for non-periodic systems: the reference
+would add the nonlinear ``fix_rotation`` there), ``threepoint=False``, no
+``hessian_function``, no cell optimisation.
 """
 import warnings
 from time import localtime, strftime
@@ -99,9 +101,10 @@ class _PESView:
 
     def converged(self, fmax, cmax=1e-5):
         e = self._o._eng
-        e.converged(fmax)
+        e.converged(fmax, cmax)
         f1 = float(e.fmax[0])
-        return f1 < fmax, f1, 0.0
+        c1 = float(e.cons["cmax"][0]) if e.cons is not None else 0.0
+        return bool(e.conv[0]), f1, c1
 
     class _H:
         def __init__(self, eng):
@@ -133,10 +136,26 @@ class Sella(_Base):
         pbc = np.asarray(getattr(atoms, "pbc", [False] * 3))
         proj_trans = kwargs.pop("proj_trans", None)
         proj_rot = kwargs.pop("proj_rot", None)
-        if constraints is not None or proj_trans is not False or (proj_rot is not False and not pbc.any()):
+        from ..constraints import Constraints
+        if constraints is None:
+            constraints = Constraints(atoms)
+        if not isinstance(constraints, Constraints):
+            raise NotImplementedError("constraints must be a sella_b200.Constraints (translation constraints)")
+        if proj_trans is None:                      # peswrapper.py:233-244
+            proj_trans = not constraints.internals['translations']
+        if proj_trans:
+            try:
+                constraints.fix_translation(replace_ok=False)
+            except ValueError:
+                pass
+        if proj_rot is None:                        # peswrapper.py:246-253
+            proj_rot = not pbc.any()
+        if proj_rot:
             raise NotImplementedError(
-                "constraints (including the translation/rotation projections the reference adds by default) "
-                "are not on the CUDA path yet: pass proj_trans=False, proj_rot=False")
+                "the rotation projection (fix_rotation, nonlinear) is not on the CUDA path yet: pass "
+                "proj_rot=False or use a periodic system")
+        self.constraints = constraints
+        lin = constraints.linear_system() if constraints.ncons else None
         eigensolver = kwargs.pop("eigensolver", "jd0")
         if kwargs:
             raise TypeError("unsupported keyword arguments: %s" % sorted(kwargs))
@@ -151,7 +170,8 @@ class Sella(_Base):
         self._eng = BatchedSella(self._surface, x0, order=order, delta0=delta0, sigma_inc=sigma_inc,
                                  sigma_dec=sigma_dec, rho_dec=rho_dec, rho_inc=rho_inc, eig=eig, eta=eta,
                                  method=method, gamma=gamma, rs=rs, nsteps_per_diag=nsteps_per_diag,
-                                 diag_every_n=diag_every_n, eigensolver=eigensolver, kcap=16)
+                                 diag_every_n=diag_every_n, eigensolver=eigensolver, kcap=16,
+                                 constraints=None if lin is None else (lin[0], lin[1][None, :]))
         self.pes = _PESView(self)
         self.ord = order
         self.eta = eta

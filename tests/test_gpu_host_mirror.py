@@ -170,8 +170,9 @@ def test_sella_drop_in_single_search():
     n = 48
     A, xs, x0 = quadratic_system(5, n)
     func = quadratic_func(A, xs)
-    with pytest.raises(NotImplementedError):      # default projections need constraint support
-        Sella(_Atoms(func, x0), logfile=None)
+    a_np = _Atoms(func, x0); a_np.pbc = np.array([False, False, False])
+    with pytest.raises(NotImplementedError):      # non-periodic default adds fix_rotation (nonlinear): not yet
+        Sella(a_np, logfile=None)
     # the path that is on the device: prfo/tr and qn/ras
     for method, rs in ((None, None), ("prfo", "tr"), ("qn", "ras")):      # (None, None): Sella's defaults prfo + ras
         atoms = _Atoms(func, x0)
@@ -187,3 +188,39 @@ def test_sella_drop_in_single_search():
         assert conv and dyn.pes.converged(1e-4)[0]
         # index-1 saddle: exactly one negative eigenvalue of the model Hessian (test_morse_cluster.py:42-46 analogue)
         assert int((dyn.pes.H.evals < 0).sum()) == 1
+
+
+def test_sella_with_translation_constraints():
+    """README-style usage: some atoms held fixed with Constraints.fix_translation, periodic
+    system (no rotation projection), default prfo + ras; vs the CPU oracle with the same
+    linear constraints."""
+    from sella_b200 import Sella, Constraints
+    from sella_b200.synthetic import quadratic_system, quadratic_func
+    from oracle.pes import CartesianPES
+    from oracle.driver import SaddleSearch
+    n = 48
+    A, xs, x0 = quadratic_system(7, n)
+    func = quadratic_func(A, xs)
+    atoms = _Atoms(func, x0)
+    cons = Constraints(atoms)
+    for i in (0, 5):
+        cons.fix_translation(i)
+    dyn = Sella(atoms, constraints=cons, logfile=None)
+    C, c = cons.linear_system()
+    assert C.shape == (6, n)
+    p = CartesianPES(func, x0, C, c)
+    o = SaddleSearch(p)                      # defaults: prfo + ras
+    for t in range(8):
+        dyn.step(); o.step()
+        np.testing.assert_allclose(atoms.positions.ravel(), p.get_x(), rtol=0, atol=1e-8)
+    np.testing.assert_array_equal(atoms.positions[[0, 5]].ravel(), x0.reshape(-1, 3)[[0, 5]].ravel())
+    # default projection of the mean translation (fix_translation() added automatically)
+    atoms2 = _Atoms(func, x0)
+    dyn2 = Sella(atoms2, logfile=None, method="qn", rs="tr")
+    C2, c2 = dyn2.constraints.linear_system()
+    assert C2.shape == (3, n) and np.allclose(C2.sum(axis=1), 1.0)
+    p2 = CartesianPES(func, x0, C2, c2)
+    o2 = SaddleSearch(p2, method="qn", rs="tr")
+    for t in range(6):
+        dyn2.step(); o2.step()
+        np.testing.assert_allclose(atoms2.positions.ravel(), p2.get_x(), rtol=0, atol=1e-8)
