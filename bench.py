@@ -225,6 +225,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.get_lib()
     lib.sb_launch_count.restype = __import__("ctypes").c_longlong
