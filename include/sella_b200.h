@@ -201,6 +201,23 @@ int sb_pack_coef(const double* coef, const double* evals, double* out2, int n,
 int sb_unpack2(const double* in2, double* s, double* absBs, int n, const int32_t* active,
                int batch, void* stream);
 
+/* ---- internal coordinates (sella/internal.py:58-80, 466-470, 1735-1902, 2189-2575;
+ * sella/linalg.py:601-646).  Topology (int32 index arrays, optional PBC shift vectors) is
+ * shared by the batch; coordinate order: translations (atom, dim), bonds, angles, dihedrals.
+ * Derivatives by forward-mode (hyper-)dual numbers of the reference's primal formulas.
+ *   sb_internals_qB  : q[b,nint] and, if Bmat != NULL (zero-filled), the Wilson B-matrix
+ *                      Bmat[b,nint,n] = dq/dx
+ *   sb_internals_hess: D[b,n,n] += sum_c v[b,c] d2q_c/dx2 (if D != NULL, zero-filled; "ldot"),
+ *                      R[b,c,:] = (d2q_c/dx2) w[b,:]       (if R != NULL, zero-filled; "rdot")  */
+int sb_internals_qB(const int32_t* trans, int nt, const int32_t* bonds, int nb, const int32_t* angles,
+                    int na, const int32_t* diheds, int nd, const double* tb, const double* ta,
+                    const double* td, const double* x, int n, double* q, double* Bmat,
+                    const int32_t* active, int batch, void* stream);
+int sb_internals_hess(const int32_t* trans, int nt, const int32_t* bonds, int nb, const int32_t* angles,
+                      int na, const int32_t* diheds, int nd, const double* tb, const double* ta,
+                      const double* td, const double* x, int n, const double* v, double* D,
+                      const double* w, double* R, const int32_t* active, int batch, void* stream);
+
 /* ---- per-step bookkeeping (sella/peswrapper.py:578-602, optimize/optimize.py:362-434) ----
  * dpar = {rho_inc, rho_dec, sigma_inc, sigma_dec, delta_min} (host array of 5 doubles),
  * ipar = {order, eig, nsteps_per_diag, diag_every_n(<0: never)} (host array of 4 ints). */

@@ -137,7 +137,27 @@ int sb_eigh(const double* A, double* evals, double* Vt, double* work, double* sm
     return sb_eigh_impl(A, evals, Vt, work, small_work, status, active, batch, n, (cudaStream_t)stream);
 }
 
+extern "C" int sb_internals_qB_impl(const int*, int, const int*, int, const int*, int, const int*, int, const double*,
+                                    const double*, const double*, const double*, int, double*, double*, const int*,
+                                    int, cudaStream_t);
+extern "C" int sb_internals_hess_impl(const int*, int, const int*, int, const int*, int, const int*, int,
+                                      const double*, const double*, const double*, const double*, int, const double*,
+                                      double*, const double*, double*, const int*, int, cudaStream_t);
 #define ST ((cudaStream_t)stream)
+int sb_internals_qB(const int32_t* trans, int nt, const int32_t* bonds, int nb, const int32_t* angles, int na,
+                    const int32_t* diheds, int nd, const double* tb, const double* ta, const double* td,
+                    const double* x, int n, double* q, double* Bmat, const int32_t* active, int batch,
+                    void* stream) {
+    return sb_internals_qB_impl(trans, nt, bonds, nb, angles, na, diheds, nd, tb, ta, td, x, n, q, Bmat, active,
+                                batch, ST);
+}
+int sb_internals_hess(const int32_t* trans, int nt, const int32_t* bonds, int nb, const int32_t* angles, int na,
+                      const int32_t* diheds, int nd, const double* tb, const double* ta, const double* td,
+                      const double* x, int n, const double* v, double* D, const double* w, double* R,
+                      const int32_t* active, int batch, void* stream) {
+    return sb_internals_hess_impl(trans, nt, bonds, nb, angles, na, diheds, nd, tb, ta, td, x, n, v, D, w, R, active,
+                                  batch, ST);
+}
 int sb_mgs(double* X, int nx, const double* Y, double* Ywork, int ny, int n, double eps1, double eps2,
            int maxiter, int32_t* nkept, int32_t* status, const int32_t* active, int batch, void* stream) {
     if (batch <= 0 || n <= 0 || nx <= 0) return -1;
