@@ -252,11 +252,16 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = lib.sb_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof_range = bool(os.environ.get("SB_PROFILER_RANGE"))   # ncu --profile-from-start off: timed loop only
+    if prof_range:
+        torch.cuda.cudart().cudaProfilerStart()
     ev0.record()
     for _ in range(args.steps):
         eng.step()
     ev1.record()
     barrier()
+    if prof_range:
+        torch.cuda.cudart().cudaProfilerStop()
     ms = ev0.elapsed_time(ev1)
     launches = lib.sb_launch_count() - l0
     clocks = sampler.stop() if sampler else None
