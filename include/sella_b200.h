@@ -30,6 +30,7 @@ extern "C" {
 #define SB_ST_DAVIDSON_CAP 8
 #define SB_ST_SINGULAR 16
 #define SB_ST_DAVIDSON_STALL 32 /* sella/eigensolvers.py:99-109                 */
+#define SB_ST_CAPACITY 64       /* a vector block is too small for the operation */
 
 /* library / device introspection */
 int sb_version(void);
@@ -94,6 +95,11 @@ int sb_davidson_rr(double* V, double* AV, int kcap, const int32_t* ksz, int n, d
  * rvhat = Pvt @ [r, v]; method 0 = jd0/jd0_alt, 1 = gd.  that[b,n]: t = Pvt.T @ that.  */
 int sb_davidson_jd_coeff(const double* rvhat, const double* pl, const double* theta, double* that,
                          int n, int method, const int32_t* dav_state, int batch, void* stream);
+/* 'mjd0' / 'mjd0_alt' (eigensolvers.py:140-151): correction orthogonal to all ksz[b] Ritz
+ * vectors; Vhat[b,j,:] = Pvt @ V[b,j,:] (sb_hv_ld), rvhat[b,0,:] = Pvt @ r.               */
+int sb_davidson_mjd_coeff(const double* Vhat, int kcap, const int32_t* ksz, const double* rvhat,
+                          const double* pl, const double* theta, double* that, int n,
+                          const int32_t* dav_state, int32_t* status, int batch, void* stream);
 /* normalise / Lanczos fallback / MGS against V / append (eigensolvers.py:90-111);
  * vnew[b,n] = the appended direction.  p_identity: closed form for P = I.           */
 int sb_davidson_expand(const double* t, const double* rv, const double* theta, double* V,
@@ -116,18 +122,26 @@ int sb_history_ritz(double* Vs, double* AVs, int kcap, const int32_t* nhist, int
                     int32_t* nvec_out, const int32_t* dav_state, int32_t* status, int batch, void* stream);
 
 /* ---- quasi-Newton update (sella/hessian_update.py:40-152, sella/linalg.py:274-304) ----
- * method: 0 TS-BFGS, 1 PSB, 2 Greenstadt; kvec may be NULL (one secant pair).         */
+ * sb_update_prep: Ytil = symmetrize_Y(S, Y, symm) with symm in {0,1,2} (:27-37), the
+ *   short-step no-op (:49-52 -> skip[b] = 1) and, if first != 0, lam0 of the scaled-identity
+ *   start (:58-67).  kvec may be NULL (one secant pair).
+ * sb_update_mid: method 0 TS-BFGS, 1 PSB, 2 Greenstadt, 3 DFP, 4 BFGS, 5 SR1, 6 BFGS_auto
+ *   (:77-152).  absBS is needed by 0 and 6; evals (spectrum of B, ascending; may be NULL = "not
+ *   positive definite") by 6; kout[b] (needed by 4 and 6, else may be NULL) = number of
+ *   (U, J, W) triples written: k, or 2k for BFGS, which therefore needs 2k <= kcap.
+ * sb_update_apply: B += sum_a (U_a J_a^T + J_a U_a^T) - 1/2 (W_a U_a^T + U_a W_a^T), i.e. the
+ *   reference's Bplus = (Bplus + Bplus.T)/2 (:109); pass kout as kvec for methods 4/6.       */
 int sb_update_prep(const double* S, const double* Y, double* Ytil, int kcap, const int32_t* kvec,
-                   int n, int ncart, int first, double* lam0, int32_t* skip, int32_t* status,
-                   const int32_t* active, int batch, void* stream);
+                   int n, int ncart, int first, int symm, double* lam0, int32_t* skip,
+                   int32_t* status, const int32_t* active, int batch, void* stream);
 int sb_fill_scaled_identity(double* B, double* evals, double* Vt, const double* lam0, int n,
                             int ncart, const int32_t* skip, int batch, void* stream);
 int sb_abs_scale(const double* VtS, const double* evals, double* out, int kcap, int n,
                  const int32_t* skip, int batch, void* stream);
 int sb_update_mid(const double* S, const double* Ytil, const double* BS, const double* absBS,
                   double* U, double* J, double* W, double* Xwork, int kcap, const int32_t* kvec,
-                  int n, int method, const int32_t* skip, int32_t* status, double* Cout, int batch,
-                  void* stream);
+                  int n, int method, const int32_t* skip, int32_t* status, double* Cout,
+                  const double* evals, int32_t* kout, int batch, void* stream);
 /* Cout (may be NULL): [b, 32*33] receives C = J^T S (k x k, leading dimension 33).     */
 int sb_update_apply(double* B, const double* U, const double* J, const double* W, int kcap,
                     const int32_t* kvec, int n, const int32_t* skip, int batch, void* stream);

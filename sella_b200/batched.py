@@ -27,8 +27,10 @@ _DEFAULTS = dict(
     saddle=dict(delta0=0.1, sigma_inc=1.15, sigma_dec=0.65, rho_inc=1.035,
                 rho_dec=5.0, method="prfo", eig=True),
 )
-_UPDATE_METHODS = {"TS-BFGS": 0, "PSB": 1, "Greenstadt": 2}
-_EIGENSOLVERS = {"jd0": 0, "jd0_alt": 0, "gd": 1, "lanczos": 2}
+# BFGS / BFGS_auto write 2k secant pairs and are served by the one-system mirror
+# (sella_b200.hessian_update.update_H); the batched engine keeps k pairs per update
+_UPDATE_METHODS = {"TS-BFGS": 0, "PSB": 1, "Greenstadt": 2, "DFP": 3, "SR1": 5}
+_EIGENSOLVERS = {"jd0": 0, "jd0_alt": 0, "gd": 1, "lanczos": 2, "mjd0": 3, "mjd0_alt": 3}
 _QN_NAMES = ("qn", "quasi-newton", "quasi newton", "newton", "mmf",
              "minimum mode following", "minimum-mode following", "dimer")
 _TR_NAMES = ("tr", "trust region", "trust-region", "trust radius", "trust-radius")
@@ -60,7 +62,7 @@ class BatchedSella:
                  rho_dec=None, rho_inc=None, eig=None, eta=1e-4, method=None, gamma=0.1,
                  rs=None, nsteps_per_diag=3, diag_every_n=None, diag_maxiter=None,
                  eigensolver="jd0", update_method="TS-BFGS", kcap=16, eig_mode="update",
-                 eig_refresh_every=0, constraints=None):
+                 eig_refresh_every=0, constraints=None, threepoint=False):
         require_cuda()
         d = _DEFAULTS["minimum" if order == 0 else "saddle"]
         self.surface = surface
@@ -91,6 +93,7 @@ class BatchedSella:
         self.eig = d["eig"] if eig is None else bool(eig)
         self.eta = float(eta)
         self.gamma = float(gamma)
+        self.threepoint = bool(threepoint)
         self.diag_maxiter = diag_maxiter
         if eigensolver not in _EIGENSOLVERS:
             raise NotImplementedError("eigensolver %r is not available on the batched path" % eigensolver)
@@ -128,6 +131,8 @@ class BatchedSella:
         self.f, self.g = z(b), z(b, n)
         self.xnew, self.fnew, self.gnew = z(b, n), z(b), z(b, n)
         self.xdisp, self.fplus, self.gplus = z(b, n), z(b), z(b, n)
+        if self.threepoint:
+            self.xminus, self.fminus, self.gminus = z(b, n), z(b), z(b, n)
         # step state
         self.s, self.dg, self.Vg, self.coef = z(b, n), z(b, n), z(b, n), z(b, n)
         self.delta = torch.full((b,), float(delta_init), **f64)
@@ -225,6 +230,18 @@ class BatchedSella:
         self.evalsB = torch.zeros(b, n, **f64)
         self.VtB = torch.zeros(b, n, n, **f64)
 
+    def _identity_model(self):
+        b, n = self.batch, self.n
+        one = torch.ones(b, dtype=torch.float64, device=self.dev)
+        call("sb_fill_scaled_identity", _p(self.B), _p(self.evalsB), _p(self.VtB), _p(one), I(n), I(n), _p(None),
+             I(b), _stream())
+        if self.cons is not None:
+            cn = self.cons
+            self.Vt.copy_(cn["Q"].expand(b, n, n) if cn["shared"] else cn["Q"])
+            self.evals.fill_(1.0)
+            self.evals[:, cn["nfree"]:] = 8.0
+        self.eig_valid = True
+
     def _project_free(self, X, nvec, ld, active=None):
         """X[b, :nvec, :] <- P_f X  (remove the components along Ucons), in place."""
         cn = self.cons
@@ -263,7 +280,7 @@ class BatchedSella:
         kc = S.shape[1]
         first = not self.H_initialized
         call("sb_update_prep", _p(S), _p(Y), _p(bufs["Ytil"]), I(kc), _p(kvec), I(n), I(n), I(int(first)),
-             _p(self.lam0), _p(self.skip), _p(self.status), _p(active), I(b), _stream())
+             I(2), _p(self.lam0), _p(self.skip), _p(self.status), _p(active), I(b), _stream())
         if first:
             call("sb_fill_scaled_identity", _p(self.B), _p(self.evalsB), _p(self.VtB), _p(self.lam0), I(n),
                  I(n), _p(self.skip), I(b), _stream())
@@ -288,7 +305,7 @@ class BatchedSella:
         call("sb_update_mid", _p(S), _p(bufs["Ytil"]), _p(bufs["BS"]),
              _p(bufs["aBS"] if self.update_method == 0 else None), _p(bufs["U"]), _p(bufs["J"]), _p(bufs["W"]),
              _p(bufs["Xw"]), I(kc), _p(kvec), I(n), I(self.update_method), _p(self.skip), _p(self.status),
-             _p(self.Cmat if track else None), I(b), _stream())
+             _p(self.Cmat if track else None), _p(None), _p(None), I(b), _stream())
         self._timed("update_apply_k%d" % kc, lambda: call(
             "sb_update_apply", _p(self.B), _p(bufs["U"]), _p(bufs["J"]), _p(bufs["W"]), I(kc), _p(kvec),
             I(n), _p(self.skip), I(b), _stream()))
@@ -324,9 +341,16 @@ class BatchedSella:
         call("sb_hvp_prepare", _p(vec), LL(vstride), _p(self.x), _p(self.g), D(self.eta), _p(self.xdisp),
              _p(self.signnorm), I(n), _p(mask), I(maskval), I(b), _stream())
         self.surface.evaluate(self.xdisp, self.fplus, self.gplus, active=active)
+        gbase, eta_eff = self.g, self.eta
+        if self.threepoint:
+            # central difference (linalg.py:82-85): second evaluation at x0 - eta v/(sign |v|)
+            call("sb_hvp_prepare", _p(vec), LL(vstride), _p(self.x), _p(self.g), D(-self.eta), _p(self.xminus),
+                 _p(self.signnorm), I(n), _p(mask), I(maskval), I(b), _stream())
+            self.surface.evaluate(self.xminus, self.fminus, self.gminus, active=active)
+            gbase, eta_eff = self.gminus, 2.0 * self.eta
         if self.cons is not None:
             kslot = self.ksz.clone()                   # slot that hvp_finish is about to fill
-        call("sb_hvp_finish", _p(vec), LL(vstride), _p(self.gplus), _p(self.g), _p(self.signnorm), D(self.eta),
+        call("sb_hvp_finish", _p(vec), LL(vstride), _p(self.gplus), _p(gbase), _p(self.signnorm), D(eta_eff),
              _p(self.AV), _p(self.Vs), _p(self.AVs), I(self.kcap), _p(self.ksz), _p(self.nhist), I(n),
              _p(mask), I(maskval), I(b), _stream())
         if self.cons is not None:
@@ -368,6 +392,15 @@ class BatchedSella:
             lanczos = int(self.eigensolver == 2)
             if first or lanczos:
                 tin = None
+            elif self.eigensolver == 3:
+                if not hasattr(self, "Vhat"):
+                    self.Vhat = torch.zeros_like(self.V)
+                K.hv_ld(self.Vt, self.rv, self.rvhat, 1, active=m)
+                K.hv_ld(self.Vt, self.V, self.Vhat, min(rounds, kc), active=m)
+                call("sb_davidson_mjd_coeff", _p(self.Vhat), I(kc), _p(self.ksz), _p(self.rvhat), _p(self.evals),
+                     _p(self.theta), _p(self.that), I(n), _p(self.dav_state), _p(self.status), I(b), _stream())
+                K.hv_ld(self.Vt, self.that.view(b, 1, n), self.t.view(b, 1, n), 1, transposed=True, active=m)
+                tin = self.t
             else:
                 K.hv_ld(self.Vt, self.rv, self.rvhat, 2, active=m)
                 call("sb_davidson_jd_coeff", _p(self.rvhat), _p(self.evals), _p(self.theta), _p(self.that),
@@ -397,7 +430,9 @@ class BatchedSella:
             self.initialized = True
         # ---- _predict_step: restricted step from the spectral model
         if not self.H_initialized:
-            raise NotImplementedError("steps on an uninitialised Hessian (eig=False) are not batched yet")
+            # B is None in the reference: the step model is the identity (linalg.py:319-334,
+            # stepper.py:76-80) until the first update scales it (hessian_update.py:58-67)
+            self._identity_model()
         if not self.eig_valid:
             self._eigh(active)
             self.eig_valid = True

@@ -18,6 +18,8 @@ extern "C" int sb_davidson_jd_coeff_impl(const double*, const double*, const dou
                                          const int*, int, cudaStream_t);
 extern "C" int sb_davidson_expand_impl(const double*, const double*, const double*, double*, double*, int,
                                        const int*, int, int, int, double*, int*, int*, int, cudaStream_t);
+extern "C" int sb_davidson_mjd_coeff_impl(const double*, int, const int*, const double*, const double*, const double*,
+                                          double*, int, const int*, int*, int, cudaStream_t);
 extern "C" int sb_hvp_prepare_impl(const double*, long long, const double*, const double*, double, double*, double*,
                                    int, const int*, int, int, cudaStream_t);
 extern "C" int sb_hvp_finish_impl(const double*, long long, const double*, const double*, const double*, double,
@@ -25,14 +27,14 @@ extern "C" int sb_hvp_finish_impl(const double*, long long, const double*, const
                                   cudaStream_t);
 extern "C" int sb_history_ritz_impl(double*, double*, int, const int*, int, int*, const int*, int*, int,
                                     cudaStream_t);
-extern "C" int sb_update_prep_impl(const double*, const double*, double*, int, const int*, int, int, int, double*,
-                                   int*, int*, const int*, int, cudaStream_t);
+extern "C" int sb_update_prep_impl(const double*, const double*, double*, int, const int*, int, int, int, int,
+                                   double*, int*, int*, const int*, int, cudaStream_t);
 extern "C" int sb_fill_scaled_identity_impl(double*, double*, double*, const double*, int, int, const int*, int,
                                             cudaStream_t);
 extern "C" int sb_abs_scale_impl(const double*, const double*, double*, int, int, const int*, int, cudaStream_t);
 extern "C" int sb_update_mid_impl(const double*, const double*, const double*, const double*, double*, double*,
-                                  double*, double*, int, const int*, int, int, const int*, int*, double*, int,
-                                  cudaStream_t);
+                                  double*, double*, int, const int*, int, int, const int*, int*, double*,
+                                  const double*, int*, int, cudaStream_t);
 extern "C" int sb_lowrank_factor_impl(const double*, const double*, const double*, int, const int*, int, double*,
                                       double*, int*, const int*, int, cudaStream_t);
 extern "C" int sb_secular_update_impl(double*, double*, double*, int, const double*, const int*, int, double*,
@@ -198,16 +200,23 @@ int sb_hvp_finish(const double* vfull, long long vstride, const double* gplus, c
     return sb_hvp_finish_impl(vfull, vstride, gplus, g0, signnorm, eta, AV, Vs, AVs, kcap, ksz, nhist, n, mask,
                               maskval, batch, ST);
 }
+int sb_davidson_mjd_coeff(const double* Vhat, int kcap, const int32_t* ksz, const double* rvhat, const double* pl,
+                          const double* theta, double* that, int n, const int32_t* dav_state, int32_t* status,
+                          int batch, void* stream) {
+    if (kcap > 32 || kcap < 1) return -1;
+    return sb_davidson_mjd_coeff_impl(Vhat, kcap, ksz, rvhat, pl, theta, that, n, dav_state, status, batch, ST);
+}
 int sb_history_ritz(double* Vs, double* AVs, int kcap, const int32_t* nhist, int n, int32_t* nvec_out,
                     const int32_t* dav_state, int32_t* status, int batch, void* stream) {
     if (kcap > 32) return -1;
     return sb_history_ritz_impl(Vs, AVs, kcap, nhist, n, nvec_out, dav_state, status, batch, ST);
 }
 int sb_update_prep(const double* S, const double* Y, double* Ytil, int kcap, const int32_t* kvec, int n, int ncart,
-                   int first, double* lam0, int32_t* skip, int32_t* status, const int32_t* active, int batch,
-                   void* stream) {
+                   int first, int symm, double* lam0, int32_t* skip, int32_t* status, const int32_t* active,
+                   int batch, void* stream) {
     if (kcap > 32 || kcap < 1) return -1;
-    return sb_update_prep_impl(S, Y, Ytil, kcap, kvec, n, ncart, first, lam0, skip, status, active, batch, ST);
+    return sb_update_prep_impl(S, Y, Ytil, kcap, kvec, n, ncart, first, symm, lam0, skip, status, active, batch,
+                               ST);
 }
 int sb_fill_scaled_identity(double* B, double* evals, double* Vt, const double* lam0, int n, int ncart,
                             const int32_t* skip, int batch, void* stream) {
@@ -219,11 +228,10 @@ int sb_abs_scale(const double* VtS, const double* evals, double* out, int kcap, 
 }
 int sb_update_mid(const double* S, const double* Ytil, const double* BS, const double* absBS, double* U, double* J,
                   double* W, double* Xwork, int kcap, const int32_t* kvec, int n, int method, const int32_t* skip,
-                  int32_t* status, double* Cout, int batch, void* stream) {
-    if (method < 0 || method > 2 || kcap > 32) return -1;
-    if (method == 0 && !absBS) return -1;
-    return sb_update_mid_impl(S, Ytil, BS, absBS, U, J, W, Xwork, kcap, kvec, n, method, skip, status, Cout, batch,
-                              ST);
+                  int32_t* status, double* Cout, const double* evals, int32_t* kout, int batch, void* stream) {
+    if (kcap > 32) return -1;
+    return sb_update_mid_impl(S, Ytil, BS, absBS, U, J, W, Xwork, kcap, kvec, n, method, skip, status, Cout, evals,
+                              kout, batch, ST);
 }
 int sb_lowrank_factor(const double* U, const double* J, const double* Cmat, int kcap, const int32_t* kvec, int n,
                       double* P, double* sig, int32_t* nterm, const int32_t* skip, int batch, void* stream) {

@@ -15,6 +15,7 @@
 #define SB_ST_DAVIDSON_CAP 8       // subspace reached the compiled capacity
 #define SB_ST_SINGULAR 16          // tiny dense solve hit a zero pivot
 #define SB_ST_DAVIDSON_STALL 32    // eigensolvers.py:99-109 random-restart branch
+#define SB_ST_CAPACITY 64          // a vector block is too small for the requested operation
 
 __device__ __forceinline__ uint32_t sb_smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);

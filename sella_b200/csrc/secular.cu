@@ -29,14 +29,19 @@ constexpr int SEC_THREADS = 256;
 constexpr double SEC_EPS = 2.220446049250313e-16;
 
 struct FactorShared {
-    double G[SB_KMAT], E[SB_KMAT], K[SB_KMAT], Y[SB_KMAT], Mc[SB_KMAT], T[SB_KMAT], A[SB_KMAT];
-    double w[SB_KMAX], sg[SB_KMAX];
+    double R[SB_KMAT], K[SB_KMAT], Y[SB_KMAT], Mc[SB_KMAT], A[SB_KMAT];
+    double sg[SB_KMAX], c[SB_KMAX];
+    double scratch[SB_SCRATCH_DOUBLES];
     int perm[SB_KMAX];
-    int rank;
 };
 
-// F = [U_0..U_{k-1}, J_0..J_{k-1}] (2k vectors, 2k <= 32).  P[b,t,:] = p_t, sig[b,t],
+// F = [U_0..U_{k-1}, J_0..J_{k-1}] (m = 2k vectors, m <= 32).  P[b,t,:] = p_t, sig[b,t],
 // nterm[b].  Cmat: k x k (ld SB_KLD) = J^T S as written by update_mid.
+//   F = Q R   (classical Gram-Schmidt with one re-orthogonalisation pass, "CGS2": errors of
+//              order eps*cond(F), where a Gram-matrix route would square the condition number --
+//              DFP/SR1-type updates put vectors of very different length into F)
+//   Delta = F Mc F^T = Q (R Mc R^T) Q^T,  Mc = [[-C_sym, I], [I, 0]];  R Mc R^T = Y diag(sig) Y^T
+//   p_t = Q y_t.   Q is built in the output buffer P and rotated in place.
 __global__ void __launch_bounds__(SEC_THREADS)
 lowrank_factor_kernel(const double* __restrict__ U_, const double* __restrict__ J_, const double* __restrict__ Cmat_,
                       int kcap, const int* __restrict__ kvec, int n, double* __restrict__ P_, double* __restrict__ sig_,
@@ -45,6 +50,7 @@ lowrank_factor_kernel(const double* __restrict__ U_, const double* __restrict__ 
     if (skip[b]) { if (threadIdx.x == 0) nterm[b] = 0; return; }
     extern __shared__ unsigned char raw[];
     FactorShared& S = *reinterpret_cast<FactorShared*>(raw);
+    double* xs = reinterpret_cast<double*>(raw + ((sizeof(FactorShared) + 15) / 16) * 16);   // n doubles
     const int k = kvec ? kvec[b] : 1;
     const int m = 2 * k;
     const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
@@ -53,17 +59,7 @@ lowrank_factor_kernel(const double* __restrict__ U_, const double* __restrict__ 
     const double* C = Cmat_ + (size_t)b * SB_KMAT;
     double* P = P_ + (size_t)b * 2 * kcap * n;
     auto F = [&](int a) { return a < k ? U + (size_t)a * n : J + (size_t)(a - k) * n; };
-    // Gram matrix of F
-    for (int pr = warp; pr < m * m; pr += nw) {
-        const int i = pr / m, j = pr % m;
-        if (j < i) continue;
-        const double* x = F(i);
-        const double* y = F(j);
-        double acc = 0.0;
-        for (int e = lane; e < n; e += 32) acc = fma(x[e], y[e], acc);
-        acc = sb_warp_sum(acc);
-        if (lane == 0) { S.G[i * SB_KLD + j] = acc; S.G[j * SB_KLD + i] = acc; }
-    }
+    if (m == 0) { if (tid == 0) nterm[b] = 0; return; }
     // Mc = [[-C_sym, I], [I, 0]]
     for (int idx = tid; idx < m * m; idx += nt) {
         const int i = idx / m, j = idx % m;
@@ -72,61 +68,75 @@ lowrank_factor_kernel(const double* __restrict__ U_, const double* __restrict__ 
         else if (i < k && j == i + k) v = 1.0;
         else if (j < k && i == j + k) v = 1.0;
         S.Mc[i * SB_KLD + j] = v;
+        S.R[i * SB_KLD + j] = 0.0;
     }
     __syncthreads();
-    if (warp == 0) sbs_jacobi_warp(S.G, m, S.E, S.w, S.perm);     // G = E diag(w) E^T, ascending
-    __syncthreads();
-    if (tid == 0) {
-        // keep directions with w_i > tol * w_max (numerical rank of F)
-        const double wmax = S.w[m - 1];
-        int lo = 0;
-        while (lo < m && !(S.w[lo] > 1e-24 * wmax && S.w[lo] > 0.0)) ++lo;
-        const int r = m - lo;
-        S.rank = r;
-        // T = D^{1/2} E^T restricted: T[i][a] = sqrt(w_{lo+i}) E[a][lo+i]
-        for (int i = 0; i < r; ++i)
-            for (int a = 0; a < m; ++a) S.T[i * SB_KLD + a] = sqrt(S.w[lo + i]) * S.E[a * SB_KLD + lo + i];
-        // K = T Mc T^T
-        for (int i = 0; i < r; ++i)
-            for (int bq = 0; bq < m; ++bq) {
-                double acc = 0.0;
-                for (int a = 0; a < m; ++a) acc += S.T[i * SB_KLD + a] * S.Mc[a * SB_KLD + bq];
-                S.A[i * SB_KLD + bq] = acc;
+    int r = 0;
+    for (int a = 0; a < m; ++a) {
+        const double* f = F(a);
+        double acc = 0.0;
+        for (int e = tid; e < n; e += nt) { const double v = f[e]; xs[e] = v; acc = fma(v, v, acc); }
+        const double nrm0 = sqrt(sb_block_sum(acc, S.scratch));
+        if (!(nrm0 > 0.0)) continue;                          // zero column: R[:, a] = 0
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int i = warp; i < r; i += nw) {
+                const double* q = P + (size_t)i * n;
+                double d = 0.0;
+                for (int e = lane; e < n; e += 32) d = fma(q[e], xs[e], d);
+                d = sb_warp_sum(d);
+                if (lane == 0) { S.c[i] = d; S.R[i * SB_KLD + a] += d; }
             }
-        for (int i = 0; i < r; ++i)
-            for (int j = 0; j < r; ++j) {
-                double acc = 0.0;
-                for (int bq = 0; bq < m; ++bq) acc += S.A[i * SB_KLD + bq] * S.T[j * SB_KLD + bq];
-                S.K[i * SB_KLD + j] = acc;
+            __syncthreads();
+            for (int e = tid; e < n; e += nt) {
+                double v = xs[e];
+                for (int i = 0; i < r; ++i) v = fma(-S.c[i], P[(size_t)i * n + e], v);
+                xs[e] = v;
             }
-        for (int i = 0; i < r; ++i)
-            for (int j = i + 1; j < r; ++j) {
-                const double v = 0.5 * (S.K[i * SB_KLD + j] + S.K[j * SB_KLD + i]);
-                S.K[i * SB_KLD + j] = v; S.K[j * SB_KLD + i] = v;
-            }
-        // orthonormal basis coefficients: q_i = sum_a F_a E[a][lo+i] / sqrt(w)  -> keep in T
-        for (int i = 0; i < r; ++i)
-            for (int a = 0; a < m; ++a) S.T[i * SB_KLD + a] = S.E[a * SB_KLD + lo + i] / sqrt(S.w[lo + i]);
+            __syncthreads();
+        }
+        acc = 0.0;
+        for (int e = tid; e < n; e += nt) acc = fma(xs[e], xs[e], acc);
+        const double nrm = sqrt(sb_block_sum(acc, S.scratch));
+        if (!(nrm > 4.0 * SEC_EPS * nrm0)) continue;          // numerically dependent column
+        if (tid == 0) S.R[r * SB_KLD + a] = nrm;
+        const double inv = 1.0 / nrm;
+        for (int e = tid; e < n; e += nt) P[(size_t)r * n + e] = xs[e] * inv;
+        ++r;
+        __syncthreads();
     }
-    __syncthreads();
-    const int r = S.rank;
     if (r == 0) { if (tid == 0) nterm[b] = 0; return; }
+    // K = R Mc R^T  (r x r), symmetrised
+    for (int idx = tid; idx < r * m; idx += nt) {
+        const int i = idx / m, bq = idx % m;
+        double acc = 0.0;
+        for (int a = 0; a < m; ++a) acc = fma(S.R[i * SB_KLD + a], S.Mc[a * SB_KLD + bq], acc);
+        S.A[i * SB_KLD + bq] = acc;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < r * r; idx += nt) {
+        const int i = idx / r, j = idx % r;
+        double acc = 0.0;
+        for (int bq = 0; bq < m; ++bq) acc = fma(S.A[i * SB_KLD + bq], S.R[j * SB_KLD + bq], acc);
+        S.K[i * SB_KLD + j] = acc;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < r * r; idx += nt) {
+        const int i = idx / r, j = idx % r;
+        if (j > i) {
+            const double v = 0.5 * (S.K[i * SB_KLD + j] + S.K[j * SB_KLD + i]);
+            S.K[i * SB_KLD + j] = v; S.K[j * SB_KLD + i] = v;
+        }
+    }
+    __syncthreads();
     if (warp == 0) sbs_jacobi_warp(S.K, r, S.Y, S.sg, S.perm);    // K = Y diag(sg) Y^T
     __syncthreads();
-    // p_t = sum_i Y[i][t] q_i = sum_a F_a (sum_i T[i][a] Y[i][t])   -> A[a][t]
-    for (int idx = tid; idx < m * r; idx += nt) {
-        const int a = idx / r, t = idx % r;
-        double acc = 0.0;
-        for (int i = 0; i < r; ++i) acc += S.T[i * SB_KLD + a] * S.Y[i * SB_KLD + t];
-        S.A[a * SB_KLD + t] = acc;
-    }
-    __syncthreads();
+    // p_t = sum_i Y[i][t] q_i, in place (each thread owns its elements)
     for (int e = tid; e < n; e += nt) {
-        double f[SB_KMAX];
-        for (int a = 0; a < m; ++a) f[a] = F(a)[e];
+        double q[SB_KMAX];
+        for (int i = 0; i < r; ++i) q[i] = P[(size_t)i * n + e];
         for (int t = 0; t < r; ++t) {
             double acc = 0.0;
-            for (int a = 0; a < m; ++a) acc = fma(f[a], S.A[a * SB_KLD + t], acc);
+            for (int i = 0; i < r; ++i) acc = fma(q[i], S.Y[i * SB_KLD + t], acc);
             P[(size_t)t * n + e] = acc;
         }
     }
@@ -712,7 +722,7 @@ extern "C" int sb_secular_profile_impl(unsigned long long* out16, int reset) {
 extern "C" int sb_lowrank_factor_impl(const double* U, const double* J, const double* Cmat, int kcap, const int* kvec,
                                       int n, double* P, double* sig, int* nterm, const int* skip, int batch,
                                       cudaStream_t st) {
-    const size_t smem = sizeof(FactorShared);
+    const size_t smem = ((sizeof(FactorShared) + 15) / 16) * 16 + (size_t)n * sizeof(double);
     cudaFuncSetAttribute(lowrank_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     SB_COUNT(1);
     lowrank_factor_kernel<<<batch, SEC_THREADS, smem, st>>>(U, J, Cmat, kcap, kvec, n, P, sig, nterm, skip);

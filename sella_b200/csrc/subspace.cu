@@ -4,7 +4,7 @@
 //   mgs / modified_gram_schmidt      sella/utilities/math.pyx:74-140, 143-159
 //   symmetrize_Y2                    sella/hessian_update.py:12-24
 //   rayleigh_ritz  (one iteration)   sella/eigensolvers.py:56-112
-//   expand ('jd0'/'jd0_alt'/'gd'/'lanczos')   sella/eigensolvers.py:115-139
+//   expand (all six methods)         sella/eigensolvers.py:115-153
 //   NumericalHessian._matvec         sella/linalg.py:39-95 (sign rule :59-73)
 //   PES.diag tail (re-Ritz of the operator history)   sella/peswrapper.py:541-551
 //
@@ -318,6 +318,54 @@ jd_coeff_kernel(const double* __restrict__ rvhat, const double* __restrict__ pl,
     }
 }
 
+struct MjdShared {
+    double G[SB_KMAT], rhs[SB_KMAT];
+    int ok;
+};
+
+// 'mjd0' / 'mjd0_alt' (eigensolvers.py:140-151): the correction is kept orthogonal to ALL k
+// Ritz vectors.  In the eigenbasis of P:  that = (-rhat + Vhat eps)/(pl - theta) with
+// (Vhat^T D Vhat) eps = Vhat^T D rhat,  D = diag(1/(pl - theta)),  Vhat[b,j,:] = Q^T V_j.
+__global__ void __launch_bounds__(SS_THREADS)
+mjd_coeff_kernel(const double* __restrict__ Vhat_, int kcap, const int* __restrict__ ksz,
+                 const double* __restrict__ rvhat, const double* __restrict__ pl, const double* __restrict__ theta,
+                 double* __restrict__ that, int n, const int* __restrict__ dav_state, int* __restrict__ status) {
+    const int b = blockIdx.x;
+    if (dav_state[b] != DAV_EXPAND) return;
+    extern __shared__ unsigned char mjd_raw[];
+    MjdShared& M = *reinterpret_cast<MjdShared*>(mjd_raw);
+    const int k = ksz[b];
+    const double* Vh = Vhat_ + (size_t)b * kcap * n;
+    const double* rh = rvhat + (size_t)b * 2 * n;
+    const double* lam = pl + (size_t)b * n;
+    const double th = theta[b];
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    for (int pr = warp; pr < k * (k + 1); pr += nw) {
+        const int i = pr / (k + 1), j = pr % (k + 1);
+        if (j < i) continue;
+        const double* a = Vh + (size_t)i * n;
+        const double* c = j < k ? Vh + (size_t)j * n : rh;
+        double acc = 0.0;
+        for (int e = lane; e < n; e += 32) acc = fma(a[e], c[e] / (lam[e] - th), acc);
+        acc = sb_warp_sum(acc);
+        if (lane == 0) {
+            if (j < k) { M.G[i * SB_KLD + j] = acc; M.G[j * SB_KLD + i] = acc; }
+            else M.rhs[i * SB_KLD] = acc;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const bool ok = sbs_solve_serial(M.G, k, M.rhs, 1);
+        if (!ok && status) atomicOr(&status[b], SB_ST_SINGULAR);
+    }
+    __syncthreads();
+    for (int e = tid; e < n; e += nt) {
+        double acc = -rh[e];
+        for (int i = 0; i < k; ++i) acc = fma(M.rhs[i * SB_KLD], Vh[(size_t)i * n + e], acc);
+        that[(size_t)b * n + e] = acc / (lam[e] - th);
+    }
+}
+
 struct ExpShared {
     double scratch[SB_SCRATCH_DOUBLES];
     double tmp[SB_KMAX];
@@ -618,6 +666,16 @@ extern "C" int sb_davidson_jd_coeff_impl(const double* rvhat, const double* pl, 
                                          int n, int method, const int* dav_state, int batch, cudaStream_t st) {
     SB_COUNT(1);
     jd_coeff_kernel<<<batch, SS_THREADS, 0, st>>>(rvhat, pl, theta, that, n, method, dav_state);
+    return SB_LAUNCH_CHECK();
+}
+
+extern "C" int sb_davidson_mjd_coeff_impl(const double* Vhat, int kcap, const int* ksz, const double* rvhat,
+                                          const double* pl, const double* theta, double* that, int n,
+                                          const int* dav_state, int* status, int batch, cudaStream_t st) {
+    const size_t smem = sizeof(MjdShared);
+    cudaFuncSetAttribute(mjd_coeff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SB_COUNT(1);
+    mjd_coeff_kernel<<<batch, SS_THREADS, smem, st>>>(Vhat, kcap, ksz, rvhat, pl, theta, that, n, dav_state, status);
     return SB_LAUNCH_CHECK();
 }
 

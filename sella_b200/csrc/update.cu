@@ -49,7 +49,8 @@ struct PrepShared {
 // first != 0: lam0[b] = exp(mean(log(max(|eig(S^T Ytil)|, 1e-12)))).
 __global__ void __launch_bounds__(UP_THREADS)
 update_prep_kernel(const double* __restrict__ S_, const double* __restrict__ Y_, double* __restrict__ Ytil_,
-                   int kcap, const int* __restrict__ kvec, int n, int ncart, int first, double* __restrict__ lam0,
+                   int kcap, const int* __restrict__ kvec, int n, int ncart, int first, int symm,
+                   double* __restrict__ lam0,
                    int* __restrict__ skip, int* __restrict__ status, const int* __restrict__ active) {
     const int b = blockIdx.x;
     if (active && !active[b]) { if (threadIdx.x == 0) skip[b] = 1; return; }
@@ -73,18 +74,38 @@ update_prep_kernel(const double* __restrict__ S_, const double* __restrict__ Y_,
         bool ok = true;
         for (int i = 0; i < k; ++i)
             for (int j = 0; j < k; ++j) { P.coef[i * SB_KLD + j] = 0.0; P.dYTS[i * SB_KLD + j] = 0.0; }
-        for (int i = 1; i < k; ++i) {
-            for (int r = 0; r < i; ++r) {
-                for (int c = 0; c < i; ++c) P.T1[r * SB_KLD + c] = P.STS[r * SB_KLD + c];
-                P.T2[r * SB_KLD] = P.YTS[i * SB_KLD + r] - P.YTS[r * SB_KLD + i] - P.dYTS[r * SB_KLD + i];
+        if (symm == 2) {
+            for (int i = 1; i < k; ++i) {
+                for (int r = 0; r < i; ++r) {
+                    for (int c = 0; c < i; ++c) P.T1[r * SB_KLD + c] = P.STS[r * SB_KLD + c];
+                    P.T2[r * SB_KLD] = P.YTS[i * SB_KLD + r] - P.YTS[r * SB_KLD + i] - P.dYTS[r * SB_KLD + i];
+                }
+                ok = sbs_solve_serial(P.T1, i, P.T2, 1) && ok;
+                for (int j = 0; j < i; ++j) P.coef[i * SB_KLD + j] = P.T2[j * SB_KLD];
+                for (int a = 0; a < k; ++a) {
+                    double acc = 0.0;
+                    for (int j = 0; j < i; ++j) acc += P.STS[a * SB_KLD + j] * P.T2[j * SB_KLD];
+                    P.dYTS[i * SB_KLD + a] = -acc;
+                }
             }
-            ok = sbs_solve_serial(P.T1, i, P.T2, 1) && ok;
-            for (int j = 0; j < i; ++j) P.coef[i * SB_KLD + j] = P.T2[j * SB_KLD];
-            for (int a = 0; a < k; ++a) {
-                double acc = 0.0;
-                for (int j = 0; j < i; ++j) acc += P.STS[a * SB_KLD + j] * P.T2[j * SB_KLD];
-                P.dYTS[i * SB_KLD + a] = -acc;
-            }
+        } else if (k > 1) {
+            // symm 0: Ytil = Y + S X, X = (S^T S)^-1 tril(S^T Y - Y^T S, -1)^T
+            // symm 1: Ytil = Y + Y X, X = (S^T Y)^-1 (same right-hand side)   hessian_update.py:30-33
+            for (int a = 0; a < k; ++a)
+                for (int c = 0; c < k; ++c) {
+                    P.T1[a * SB_KLD + c] = symm == 0 ? P.STS[a * SB_KLD + c] : P.YTS[c * SB_KLD + a];
+                    P.T2[a * SB_KLD + c] = c > a ? P.YTS[a * SB_KLD + c] - P.YTS[c * SB_KLD + a] : 0.0;
+                }
+            ok = sbs_solve_serial(P.T1, k, P.T2, k);                 // T2 <- X
+            const double* base = symm == 0 ? P.STS : P.YTS;           // (basis vector j) . S_a
+            for (int i = 0; i < k; ++i)
+                for (int j = 0; j < k; ++j) P.coef[i * SB_KLD + j] = -P.T2[j * SB_KLD + i];
+            for (int i = 0; i < k; ++i)
+                for (int a = 0; a < k; ++a) {
+                    double acc = 0.0;
+                    for (int j = 0; j < k; ++j) acc += P.T2[j * SB_KLD + i] * base[j * SB_KLD + a];
+                    P.dYTS[i * SB_KLD + a] = acc;
+                }
         }
         P.ok = ok ? 1 : 0;
         if (!ok && status) atomicOr(&status[b], SB_ST_SINGULAR);
@@ -93,8 +114,11 @@ update_prep_kernel(const double* __restrict__ S_, const double* __restrict__ Y_,
     for (int i = 0; i < k; ++i)
         for (int e = tid; e < n; e += nt) {
             double y = Y[(size_t)i * n + e];
-            if (e < nn)
-                for (int j = 0; j < i; ++j) y = fma(-P.coef[i * SB_KLD + j], S[(size_t)j * n + e], y);
+            if (e < nn) {
+                const int jmax = symm == 2 ? i : k;
+                const double* basis = symm == 1 ? Y : S;
+                for (int j = 0; j < jmax; ++j) y = fma(-P.coef[i * SB_KLD + j], basis[(size_t)j * n + e], y);
+            }
             Yt[(size_t)i * n + e] = y;
         }
     if (first) {
@@ -144,18 +168,26 @@ __global__ void abs_scale_kernel(const double* __restrict__ VtS, const double* _
 
 struct MidShared {
     double G1[SB_KMAT], G2[SB_KMAT], XS[SB_KMAT], Minv[SB_KMAT], C[SB_KMAT];
-    int ok;
+    double w[SB_KMAX];
+    int perm[SB_KMAX];
+    int ok, meth;
 };
 
-// method: 0 TS-BFGS, 1 PSB, 2 Greenstadt.  In: S, Ytil, BS, absBS (TS-BFGS only).
-// Out: U, J, W (each [b,kcap,n]).  Xw: [b,kcap,n] scratch.
+// method: 0 TS-BFGS, 1 PSB, 2 Greenstadt, 3 DFP, 4 BFGS, 5 SR1, 6 BFGS_auto
+// (hessian_update.py:77-101, 114-152).  In: S, Ytil, BS, absBS (TS-BFGS / BFGS_auto),
+// evals (BFGS_auto: spectrum of B, ascending).  Out: kout[b] secant "pairs" (U_a, J_a, W_a),
+// each [b,kcap,n], with  B+ = B + sum_a (U_a J_a^T + J_a U_a^T) - 1/2 (W_a U_a^T + U_a W_a^T).
+// Methods 0-3 are the reference's U J^T + J U^T - U (J^T S) U^T family (k pairs); BFGS and SR1
+// are sums of symmetric terms  X A X^T = sum_a X_a (1/2 sum_c A[a][c] X_c)^T + transpose,
+// written as pairs with W = 0 (BFGS needs 2k <= kcap pairs).  Xw: [b,kcap,n] scratch.
 __global__ void __launch_bounds__(UP_THREADS)
 update_mid_kernel(const double* __restrict__ S_, const double* __restrict__ Yt_, const double* __restrict__ BS_,
                   const double* __restrict__ aBS_, double* __restrict__ U_, double* __restrict__ J_,
                   double* __restrict__ W_, double* __restrict__ Xw_, int kcap, const int* __restrict__ kvec, int n,
-                  int method, const int* __restrict__ skip, int* __restrict__ status, double* __restrict__ Cout) {
+                  int method, const int* __restrict__ skip, int* __restrict__ status, double* __restrict__ Cout,
+                  const double* __restrict__ evals, int* __restrict__ kout) {
     const int b = blockIdx.x;
-    if (skip[b]) return;
+    if (skip[b]) { if (kout && threadIdx.x == 0) kout[b] = 0; return; }
     extern __shared__ unsigned char raw[];
     MidShared& M = *reinterpret_cast<MidShared*>(raw);
     const int k = kvec ? kvec[b] : 1;
@@ -170,8 +202,73 @@ update_mid_kernel(const double* __restrict__ S_, const double* __restrict__ Yt_,
     double* W = W_ + off;
     double* Xw = Xw_ + off;
 
+    int meth = method;
+    if (method == 6) {
+        // BFGS only if B and the pencil (S^T Ytil, S^T S) are both positive definite (:80-87)
+        gram_block_u(S, Yt, k, k, n, M.G1);
+        gram_block_u(S, S, k, k, n, M.G2);
+        __syncthreads();
+        if (tid < 32) {
+            bool pd = evals != nullptr && evals[(size_t)b * n] > 0.0;
+            if (pd) {
+                pd = sbs_gen_eigh_warp(M.G1, M.G2, k, M.XS, M.w, M.Minv, M.perm);
+                if (pd) pd = M.w[0] > 0.0;
+            }
+            if (tid == 0) M.meth = pd ? 4 : 0;
+        }
+        __syncthreads();
+        meth = M.meth;
+        __syncthreads();
+    }
+    if (meth == 4 && 2 * k > kcap) {
+        if (tid == 0) { if (status) atomicOr(&status[b], SB_ST_CAPACITY); if (kout) kout[b] = 0; }
+        return;
+    }
+
     for (int i = tid; i < k * n; i += nt) J[i] = Yt[i] - BS[i];
-    if (method == 0) {
+    if (meth == 4 || meth == 5) {
+        // symmetric-term family
+        const int nblk = meth == 4 ? 2 : 1;
+        __syncthreads();
+        for (int blk = 0; blk < nblk; ++blk) {
+            const double* X = meth == 5 ? J : (blk == 0 ? Yt : BS);
+            const double sgn = blk == 0 ? 0.5 : -0.5;
+            if (meth == 5) gram_block_u(J, S, k, k, n, M.XS);          // J^T S
+            else if (blk == 0) gram_block_u(Yt, S, k, k, n, M.XS);     // Ytil^T S
+            else gram_block_u(S, BS, k, k, n, M.XS);                   // S^T B S
+            __syncthreads();
+            if (tid == 0) {
+                const bool ok = sbs_invert_serial(M.XS, k, M.Minv);
+                if (!ok && status) atomicOr(&status[b], SB_ST_SINGULAR);
+            }
+            __syncthreads();
+            // pair a of this block: U = X_a, J' = sgn * sum_c A[a][c] X_c   (J' staged in Xw / W)
+            double* Jst = blk == 0 ? Xw : W;
+            for (int e = tid; e < n; e += nt) {
+                double x[SB_KMAX];
+                for (int c = 0; c < k; ++c) x[c] = X[(size_t)c * n + e];
+                for (int a = 0; a < k; ++a) {
+                    double acc = 0.0;
+                    for (int c = 0; c < k; ++c) acc = fma(M.Minv[a * SB_KLD + c], x[c], acc);
+                    U[(size_t)(blk * k + a) * n + e] = x[a];
+                    Jst[(size_t)a * n + e] = sgn * acc;
+                }
+            }
+            __syncthreads();
+        }
+        const int kp = nblk * k;
+        for (int i = tid; i < k * n; i += nt) {
+            J[i] = Xw[i];
+            if (nblk == 2) J[(size_t)k * n + i] = W[i];
+        }
+        __syncthreads();
+        for (int i = tid; i < kp * n; i += nt) W[i] = 0.0;
+        if (Cout)
+            for (int i = tid; i < kp * kp; i += nt) Cout[(size_t)b * SB_KMAT + (i / kp) * SB_KLD + (i % kp)] = 0.0;
+        if (kout && tid == 0) kout[b] = kp;
+        return;
+    }
+    if (meth == 0) {
         gram_block_u(S, Yt, k, k, n, M.G1);       // S^T Ytilde
         gram_block_u(S, aBS, k, k, n, M.G2);      // S^T |B|S
         __syncthreads();
@@ -187,12 +284,15 @@ update_mid_kernel(const double* __restrict__ S_, const double* __restrict__ Yt_,
         }
         __syncthreads();
         gram_block_u(Xw, S, k, k, n, M.XS);       // (X1+X2) S
-    } else if (method == 1) {
+    } else if (meth == 1) {
         for (int i = tid; i < k * n; i += nt) Xw[i] = S[i];
         gram_block_u(S, S, k, k, n, M.XS);
-    } else {
+    } else if (meth == 2) {
         for (int i = tid; i < k * n; i += nt) Xw[i] = BS[i];
         gram_block_u(S, BS, k, k, n, M.XS);
+    } else {
+        for (int i = tid; i < k * n; i += nt) Xw[i] = Yt[i];
+        gram_block_u(S, Yt, k, k, n, M.XS);       // DFP: U = Ytil (S^T Ytil)^-T
     }
     __syncthreads();
     if (tid == 0) {
@@ -227,6 +327,7 @@ update_mid_kernel(const double* __restrict__ S_, const double* __restrict__ Yt_,
             W[(size_t)c * n + e] = acc;
         }
     }
+    if (kout && tid == 0) kout[b] = k;
 }
 
 // B += sum_a (U_a J_a^T + J_a U_a^T) - 1/2 sum_a (W_a U_a^T + U_a W_a^T), streaming.
@@ -309,12 +410,13 @@ update_apply_kernel(double* __restrict__ B_, const double* __restrict__ U_, cons
 }  // namespace
 
 extern "C" int sb_update_prep_impl(const double* S, const double* Y, double* Ytil, int kcap, const int* kvec,
-                                   int n, int ncart, int first, double* lam0, int* skip, int* status,
+                                   int n, int ncart, int first, int symm, double* lam0, int* skip, int* status,
                                    const int* active, int batch, cudaStream_t st) {
     const size_t smem = sizeof(PrepShared);
     cudaFuncSetAttribute(update_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     SB_COUNT(1);
-    update_prep_kernel<<<batch, UP_THREADS, smem, st>>>(S, Y, Ytil, kcap, kvec, n, ncart, first, lam0, skip,
+    if (symm < 0 || symm > 2) return -1;
+    update_prep_kernel<<<batch, UP_THREADS, smem, st>>>(S, Y, Ytil, kcap, kvec, n, ncart, first, symm, lam0, skip,
                                                         status, active);
     return SB_LAUNCH_CHECK();
 }
@@ -337,13 +439,16 @@ extern "C" int sb_abs_scale_impl(const double* VtS, const double* evals, double*
 
 extern "C" int sb_update_mid_impl(const double* S, const double* Ytil, const double* BS, const double* aBS,
                                   double* U, double* J, double* W, double* Xw, int kcap, const int* kvec, int n,
-                                  int method, const int* skip, int* status, double* Cout, int batch,
-                                  cudaStream_t st) {
+                                  int method, const int* skip, int* status, double* Cout, const double* evals,
+                                  int* kout, int batch, cudaStream_t st) {
+    if (method < 0 || method > 6) return -1;
+    if ((method == 0 || method == 6) && aBS == nullptr) return -1;
+    if ((method == 4 || method == 6) && kout == nullptr) return -1;
     const size_t smem = sizeof(MidShared);
     cudaFuncSetAttribute(update_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     SB_COUNT(1);
     update_mid_kernel<<<batch, UP_THREADS, smem, st>>>(S, Ytil, BS, aBS, U, J, W, Xw, kcap, kvec, n, method,
-                                                       skip, status, Cout);
+                                                       skip, status, Cout, evals, kout);
     return SB_LAUNCH_CHECK();
 }
 

@@ -6,7 +6,7 @@ kernel) or any operator with ``.shape`` and ``.dot`` (applied on the host, one v
 a time, exactly as the reference calls ``A.dot``; this is how a finite-difference
 ``NumericalHessian`` plugs in).  ``P`` is the dense preconditioner.  Expansion methods on
 the device: 'jd0', 'jd0_alt' (same correction equation, solved in P's eigenbasis), 'gd',
-'lanczos'; 'mjd0'/'mjd0_alt' raise NotImplementedError.  The metric B of the reference is
+'lanczos', 'mjd0', 'mjd0_alt' (again one equation, bordered vs block-eliminated form).  The metric B of the reference is
 the identity at every call site (peswrapper.py:537-539) and is not supported otherwise.
 """
 import numpy as np
@@ -16,7 +16,7 @@ from . import kernels as K
 from ._host import up, up_mat, down_cols, zeros, raise_status
 from ._lib import I, D, _p, _stream, call
 
-_METHOD = {"jd0": 0, "jd0_alt": 0, "gd": 1, "lanczos": 2}
+_METHOD = {"jd0": 0, "jd0_alt": 0, "gd": 1, "lanczos": 2, "mjd0": 3, "mjd0_alt": 3}
 KCAP = 32
 
 
@@ -45,7 +45,7 @@ def rayleigh_ritz(A, gamma, P, B=None, v0=None, vref=None, vreftol=0.99, method=
     if vref is not None:
         raise NotImplementedError("rayleigh_ritz: vref (optbench hook) is not on the CUDA path")
     if method not in _METHOD:
-        raise NotImplementedError("rayleigh_ritz: expansion method %r is not on the CUDA path" % method)
+        raise ValueError("Unknown diagonalization method {}".format(method))
     if gamma <= 0:
         return exact(A, gamma, P)
     if maxiter is None:
@@ -68,9 +68,10 @@ def rayleigh_ritz(A, gamma, P, B=None, v0=None, vref=None, vreftol=0.99, method=
 
     Pd = up_mat(P)
     pl = Pvt = None
-    need_P_spectrum = (v0 is None) or meth in (0, 1)
+    need_P_spectrum = (v0 is None) or meth in (0, 1, 3)
+    Vhat = zeros(1, kcap, n) if meth == 3 else None
     p_identity = bool(np.array_equal(P, np.eye(n)))
-    if need_P_spectrum and not (p_identity and v0 is not None):
+    if need_P_spectrum and not (p_identity and v0 is not None and meth == 0):
         pl, Pvt, st = K.eigh(Pd)
         raise_status(st, "eigh(P)")
     if v0 is not None:
@@ -94,6 +95,13 @@ def rayleigh_ritz(A, gamma, P, B=None, v0=None, vref=None, vreftol=0.99, method=
             tin = None
         elif p_identity and v0 is not None and meth == 0:
             tin = None
+        elif meth == 3:
+            K.hv_ld(Pvt, rv, rvhat, 1)
+            K.hv_ld(Pvt, V, Vhat, k)
+            call("sb_davidson_mjd_coeff", _p(Vhat), I(kcap), _p(ksz), _p(rvhat), _p(pl), _p(theta), _p(that), I(n),
+                 _p(state), _p(status), I(1), _stream())
+            K.hv_ld(Pvt, that.view(1, 1, n), t.view(1, 1, n), 1, transposed=True)
+            tin = t
         else:
             K.hv_ld(Pvt, rv, rvhat, 2)
             call("sb_davidson_jd_coeff", _p(rvhat), _p(pl), _p(theta), _p(that), I(n), I(meth), _p(state), I(1),

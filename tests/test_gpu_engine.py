@@ -111,6 +111,75 @@ def test_engine_rfo_models_match_oracle(n, method, rs):
     eng.check_status()
 
 
+@pytest.mark.parametrize("variant", ["threepoint", "mjd0", "gd", "lanczos", "PSB", "Greenstadt", "DFP", "SR1"])
+def test_engine_variants_match_oracle(variant):
+    """The less-travelled switches of the reference, each against the oracle step by step:
+    central-difference H.v (linalg.py:82-85), the other Davidson expansions
+    (eigensolvers.py:115-153) and the other secant updates (hessian_update.py:128-152)."""
+    from oracle.pes import CartesianPES
+    from oracle.driver import SaddleSearch
+    from sella_b200.synthetic import quadratic_func
+    n, systems = 48, [0, 1, 2]
+    ekw, okw, pkw, upd = {}, {}, {}, None
+    if variant == "threepoint":
+        ekw["threepoint"] = okw["threepoint"] = True
+    elif variant in ("mjd0", "gd", "lanczos"):
+        ekw["eigensolver"] = pkw["eigensolver"] = variant
+    else:
+        ekw["update_method"] = upd = variant
+    # a handful of expansions per diagonalisation, the regime Sella runs in (DESIGN.md section 2)
+    eng, data = make_engine(n, systems, method="qn", rs="tr", diag_every_n=3, diag_maxiter=5, **ekw)
+    oracles = []
+    for (A, xs, x0) in data:
+        p = CartesianPES(quadratic_func(A, xs), x0, **pkw)
+        if upd:
+            p.H.update_method = upd
+        oracles.append((p, SaddleSearch(p, method="qn", rs="tr", diag_every_n=3, diag_maxiter=5, **okw)))
+    for t in range(9):
+        eng.step()
+        x = eng.x.cpu().numpy()
+        for i, (p, o) in enumerate(oracles):
+            o.step()
+            # SR1 divides by (y - Bs).s: the reference's own trajectory moves by 1e-5 under a 1e-13
+            # relative change of x0 once the second diagonalisation has run (measured with the oracle)
+            atol = 1e-8 if variant != "SR1" else (1e-7 if t < 5 else 1e-4)
+            np.testing.assert_allclose(x[i], p.get_x(), rtol=0, atol=atol, err_msg="system %d step %d" % (i, t))
+    eng.check_status()
+
+
+@pytest.mark.parametrize("rs", ["tr", "ras"])
+def test_engine_minimum_search_without_diagonalisation(rs):
+    """order=0 defaults (optimize.py:22-29: qn, eig=False): the first steps run on the
+    identity model of an uninitialised Hessian (linalg.py:276-289, 319-334)."""
+    from oracle.pes import CartesianPES
+    from oracle.driver import SaddleSearch
+    from sella_b200.batched import BatchedSella, QuadraticSurface
+    from sella_b200.synthetic import quadratic_system, quadratic_func
+    n, systems = 30, [0, 1, 2]
+    data = []
+    for b in systems:
+        A, xs, x0 = quadratic_system(b, n)
+        w, v = np.linalg.eigh(A)
+        A = (v * np.abs(w)[None, :]) @ v.T
+        data.append((0.5 * (A + A.T), xs, x0))
+    A = np.stack([d[0] for d in data]); xs = np.stack([d[1] for d in data]); x0 = np.stack([d[2] for d in data])
+    eng = BatchedSella(QuadraticSurface(to_dev(A), to_dev(xs)), to_dev(x0), order=0, rs=rs)
+    assert eng.method == "qn" and not eng.eig
+    oracles = []
+    for (Ai, xsi, x0i) in data:
+        p = CartesianPES(quadratic_func(Ai, xsi), x0i)
+        oracles.append((p, SaddleSearch(p, order=0, rs=rs)))
+    for t in range(12):
+        eng.step()
+        x = eng.x.cpu().numpy(); delta = eng.delta.cpu().numpy()
+        for i, (p, o) in enumerate(oracles):
+            o.step()
+            np.testing.assert_allclose(x[i], p.get_x(), rtol=0, atol=1e-8, err_msg="system %d step %d" % (i, t))
+            np.testing.assert_allclose(delta[i], o.delta, rtol=1e-8)
+    eng.check_status()
+    assert eng.ndiag == 0
+
+
 def test_engine_matches_reference_golden(golden):
     """Unconstrained quasi-Newton cases of tests/golden/loop.npz: trajectories
     produced by the reference's own Sella + PES classes."""

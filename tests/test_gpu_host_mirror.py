@@ -39,21 +39,21 @@ def test_modified_gram_schmidt(golden):
 def test_update_H(golden):
     from sella_b200.hessian_update import update_H, symmetrize_Y
     G = golden("update_H")
-    done = 0
+    done, methods_seen = 0, set()
     for i in range(int(G["ncases"])):
         grp, method, symm, useB, flat = G["meta%d" % i]
         B, S, Y = G["B_g" + grp], G["S_g" + grp], G["Y_g" + grp]
-        if method not in ("TS-BFGS", "PSB", "Greenstadt") or (symm != "2" and S.shape[1] > 1):
-            continue
+        # every method (TS-BFGS, PSB, Greenstadt, DFP, BFGS, SR1, BFGS_auto) x symm 0/1/2
         Sin, Yin = (S.ravel(), Y.ravel()) if flat == "1" else (S, Y)
         out = update_H(B if useB == "1" else None, Sin, Yin, method=method, symm=int(symm))
         ref = G["out%d" % i]
         scale = np.abs(ref).max()
         np.testing.assert_allclose(out, ref, rtol=1e-9, atol=1e-10 * scale, err_msg=str(G["meta%d" % i]))
         # secant condition, reference tests/test_hessian_update.py:33-37
-        np.testing.assert_allclose(out @ S, symmetrize_Y(S, Y, 2), rtol=1e-6, atol=1e-6 * scale)
+        np.testing.assert_allclose(out @ S, symmetrize_Y(S, Y, int(symm)), rtol=1e-6, atol=1e-6 * scale)
+        methods_seen.add((method, symm))
         done += 1
-    assert done >= 20
+    assert done == int(G["ncases"]) and len({m for m, _ in methods_seen}) == 7
     # tiny step hands back B itself (tests/test_hessian_update.py:43-45)
     rng = np.random.RandomState(1)
     B = rng.normal(size=(10, 10)); B = B + B.T
@@ -64,12 +64,10 @@ def test_update_H(golden):
 def test_rayleigh_ritz(golden):
     from sella_b200.eigensolvers import rayleigh_ritz
     G = golden("rayleigh_ritz")
-    done = 0
+    done, methods_seen = 0, set()
     for i in range(int(G["ncases"])):
         n, method, gamma, maxiter, use_v0 = G["meta%d" % i]
-        if method not in ("jd0", "jd0_alt", "gd", "lanczos"):
-            continue
-        ref = G["lams%d" % i]
+        ref = G["lams%d" % i]                       # all six expansion methods
         if len(ref) > 8:
             continue
         A, P, v0 = G["A_" + n], G["P_" + n], G["v0_" + n]
@@ -81,8 +79,20 @@ def test_rayleigh_ritz(golden):
         np.testing.assert_allclose(AV, A @ V, atol=1e-11)
         # reference invariant tests/test_eigensolvers.py:67
         np.testing.assert_allclose(lams, np.linalg.eigh(V.T @ AV)[0], atol=1e-4)
+        methods_seen.add(method)
         done += 1
-    assert done >= 20
+    assert done >= 20 and methods_seen == {"jd0", "jd0_alt", "gd", "lanczos", "mjd0", "mjd0_alt"}
+
+
+def test_symmetrize_Y(golden):
+    from sella_b200.hessian_update import symmetrize_Y
+    G = golden("symmetrize_Y")
+    seen = set()
+    for i in range(int(G["ncases"])):
+        out = symmetrize_Y(G["S%d" % i], G["Y%d" % i], int(G["symm%d" % i]))
+        np.testing.assert_allclose(out, G["out%d" % i], rtol=1e-9, atol=1e-11)
+        seen.add(int(G["symm%d" % i]))
+    assert seen == {0, 1, 2}
 
 
 def test_rayleigh_ritz_with_operator():
