@@ -179,6 +179,9 @@ int sb_qn_tr(const double* Vg, const double* evals, const double* delta, int ord
 int sb_rfo_tr(const double* Vg, const double* evals, const double* delta, int order, int n, int mode,
               double* coef, double* smag, double* alpha, int32_t* status, const int32_t* active,
               const double* extra2, int batch, void* stream);
+/* diagnostic: {alpha evaluations, secular iterations, secular roots, cycles, systems} summed
+ * over the systems sb_rfo_tr has solved (host array of 8 uint64; synchronises the device).  */
+int sb_rfo_profile(unsigned long long* out8, int reset);
 int sb_rfo_ras(const double* Vg, const double* evals, const double* Vt, const double* delta,
                int order, int n, int mode, double* s, double* smag, double* alpha, int32_t* status,
                const int32_t* active, const double* sadd, int batch, void* stream);

@@ -28,6 +28,10 @@ namespace {
 constexpr int RFO_WARPS = 8;
 constexpr double RFO_EPS = 2.220446049250313e-16;
 
+// diagnostic counters (summed over warps by lane 0): 0 alpha evaluations, 1 arrow-head root
+// iterations, 2 arrow-head roots, 3 cycles, 4 systems
+__device__ unsigned long long rfo_prof[8];
+
 template <int NPL>
 struct Sys {
     double lam[NPL], g2[NPL], g[NPL];
@@ -40,7 +44,7 @@ struct Sys {
 // tt_guess (0 = none) warm-starts Newton.
 template <int NPL>
 __device__ void arrow_root(const Sys<NPL>& S, int i0, int i1, int which, int idx, double a2, double gnorm2,
-                           double tt_guess, int* org_out, double* tt_out) {
+                           double tt_guess, int* org_out, double* tt_out, int* iters = nullptr) {
     const int lane = threadIdx.x & 31;
     auto lam_at = [&](int i) {            // broadcast lam[i] from the owning lane
         const int q = i >> 5, src = i & 31;
@@ -75,25 +79,48 @@ __device__ void arrow_root(const Sys<NPL>& S, int i0, int i1, int which, int idx
         else { org = idx; lo = -half; hi = 0.0; }
     }
     const double lorg = lam_at(org);
+    // weight of the pole the offset is measured from: every entry whose eigenvalue is identical
+    // to lam[org] sits on that pole (the degenerate cluster of a quasi-Newton Hessian does)
+    double w = 0.0;
+#pragma unroll
+    for (int u = 0; u < NPL; ++u) {
+        const int i = lane + 32 * u;
+        if (i >= i0 && i < i1 && S.lam[u] == lorg) w += S.g2[u];
+    }
+    w = a2 * sb_warp_sum(w);
     double tt = (tt_guess > lo && tt_guess < hi) ? tt_guess : 0.5 * (lo + hi);
+    // F(tt) = p(tt) + r(tt): p = -w/tt is the nearest pole, r the smooth remainder.  Each step
+    // solves  r(tt_k) + r'(tt_k)(t - tt_k) - w/t = 0  (a quadratic; Newton on r with the pole kept
+    // exact), which converges in a few steps even when the root hugs the pole; bracket and
+    // bisection safeguards as before.
     for (int it = 0; it < 200; ++it) {
-        double f = 0.0, df = 0.0;
+        if (iters) ++*iters;
+        double r = 0.0, dr = 0.0, ra = 0.0;
 #pragma unroll
         for (int u = 0; u < NPL; ++u) {
             const int i = lane + 32 * u;
-            if (i >= i0 && i < i1) {
+            if (i >= i0 && i < i1 && S.lam[u] != lorg) {
                 const double den = a2 * (S.lam[u] - lorg) - tt;
-                const double r = 1.0 / den;
-                const double q = a2 * S.g2[u] * r;
-                f += q;
-                df = fma(q, r, df);
+                const double rc = 1.0 / den;
+                const double q = a2 * S.g2[u] * rc;
+                r += q;
+                ra += fabs(q);
+                dr = fma(q, rc, dr);
             }
         }
-        f = (a2 * lorg + tt) + sb_warp_sum(f);
-        df = 1.0 + sb_warp_sum(df);
-        if (f == 0.0) break;
+        r = (a2 * lorg + tt) + sb_warp_sum(r);
+        dr = 1.0 + sb_warp_sum(dr);
+        ra = sb_warp_sum(ra);
+        const double f = r - w / tt;
+        // F cannot be evaluated more accurately than eps * (sum of |terms|): stop there
+        // (LAPACK dlaed4's criterion) instead of chasing the last bit of tt through noise
+        if (fabs(f) <= 4.0 * RFO_EPS * (fabs(a2 * lorg) + fabs(tt) + ra + fabs(w / tt))) break;
         if (f < 0.0) lo = tt; else hi = tt;
-        double next = tt - f / df;
+        const double Bq = r - dr * tt;
+        const double sq = sqrt(fma(Bq, Bq, 4.0 * dr * w));
+        double next;
+        if (lo >= 0.0) next = Bq <= 0.0 ? (sq - Bq) / (2.0 * dr) : 2.0 * w / (Bq + sq);
+        else next = Bq >= 0.0 ? -(Bq + sq) / (2.0 * dr) : -2.0 * w / (sq - Bq);
         if (!(next > lo && next < hi)) {
             if (lo >= 0.0) {
                 if (lo > 0.0 && hi > 4.0 * lo) next = sqrt(lo) * sqrt(hi);
@@ -119,7 +146,7 @@ __device__ void arrow_root(const Sys<NPL>& S, int i0, int i1, int which, int idx
 // stores s into sreg.  `guess` in/out: tt / alpha^2 of this block's root (0 = none).
 template <int NPL>
 __device__ void rfo_block(const Sys<NPL>& S, int i0, int i1, int which, int idx, double alpha, double* guess,
-                          double* ss_out, double* sds_out, double* sreg) {
+                          double* ss_out, double* sds_out, double* sreg, int* iters = nullptr) {
     const int lane = threadIdx.x & 31;
     if (i1 <= i0) { *ss_out = 0.0; *sds_out = 0.0; return; }
     const double a2 = alpha * alpha;
@@ -131,7 +158,7 @@ __device__ void rfo_block(const Sys<NPL>& S, int i0, int i1, int which, int idx,
     }
     gn = sb_warp_sum(gn);
     int org; double tt;
-    arrow_root<NPL>(S, i0, i1, which, idx, a2, gn, (*guess) * a2, &org, &tt);
+    arrow_root<NPL>(S, i0, i1, which, idx, a2, gn, (*guess) * a2, &org, &tt, iters);
     if (which != 2) *guess = (a2 > 0.0) ? tt / a2 : 0.0;
     double lorg;
     {
@@ -198,15 +225,19 @@ rfo_tr_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_,
     const int mo = order < n ? order : n;
     double guess_a = 0.0, guess_b = 0.0;
     double sreg[NPL];
+    int n_eval = 0, n_iter = 0, n_root = 0;
+    const long long t_begin = clock64();
     auto eval = [&](double alpha, double* val, double* dval, bool store) {
         double ss, sds;
+        ++n_eval;
+        n_root += mode == 0 ? 1 : 2;
         if (mode == 0) {
             const int which = mo == 0 ? 0 : (mo == n ? 1 : 2);
-            rfo_block<NPL>(S, 0, n, which, mo, alpha, &guess_a, &ss, &sds, store ? sreg : nullptr);
+            rfo_block<NPL>(S, 0, n, which, mo, alpha, &guess_a, &ss, &sds, store ? sreg : nullptr, &n_iter);
         } else {
             double s1, d1, s2, d2;
-            rfo_block<NPL>(S, 0, mo, 1, mo, alpha, &guess_a, &s1, &d1, store ? sreg : nullptr);
-            rfo_block<NPL>(S, mo, n, 0, mo, alpha, &guess_b, &s2, &d2, store ? sreg : nullptr);
+            rfo_block<NPL>(S, 0, mo, 1, mo, alpha, &guess_a, &s1, &d1, store ? sreg : nullptr, &n_iter);
+            rfo_block<NPL>(S, mo, n, 0, mo, alpha, &guess_b, &s2, &d2, store ? sreg : nullptr, &n_iter);
             ss = s1 + s2; sds = d1 + d2;
         }
         *val = sqrt(ss + extra2);
@@ -242,6 +273,11 @@ rfo_tr_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_,
         smag[b] = interior ? val : delta;
         alpha_out[b] = alpha;
         if (st && status) atomicOr(&status[b], st);
+        atomicAdd(&rfo_prof[0], (unsigned long long)n_eval);
+        atomicAdd(&rfo_prof[1], (unsigned long long)n_iter);
+        atomicAdd(&rfo_prof[2], (unsigned long long)n_root);
+        atomicAdd(&rfo_prof[3], (unsigned long long)(clock64() - t_begin));
+        atomicAdd(&rfo_prof[4], 1ull);
     }
 }
 
@@ -400,6 +436,16 @@ rfo_ras_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_
 }
 
 }  // namespace
+
+extern "C" int sb_rfo_profile_impl(unsigned long long* out8, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out8, rfo_prof, sizeof(unsigned long long) * 8);
+    if (e != cudaSuccess) return (int)e;
+    if (reset) {
+        unsigned long long z[8] = {0};
+        e = cudaMemcpyToSymbol(rfo_prof, z, sizeof(z));
+    }
+    return (int)e;
+}
 
 extern "C" int sb_rfo_tr_impl(const double* Vg, const double* evals, const double* delta, int order, int n, int mode,
                               double* coef, double* smag, double* alpha, int* status, const int* active,

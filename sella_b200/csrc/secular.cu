@@ -21,6 +21,7 @@
 // Quasi-Newton Hessians are "scaled identity + low rank": almost everything deflates
 // and an update costs a few passes over Vt instead of a full eigensolve.  The result
 // is the eigendecomposition of the same matrix, to rounding.
+#include <cstdlib>
 #include "small_dense.cuh"
 
 namespace {
@@ -166,21 +167,40 @@ __device__ void secular_root(const double* __restrict__ e, const double* __restr
     double lo, hi;
     if (org == j) { lo = 0.0; hi = (j + 1 < r) ? 0.5 * gap : gap; }
     else { lo = -0.5 * gap; hi = 0.0; }
-    // f is increasing in mu on the bracket; safeguarded Newton with (geometric) bisection
+    // f = p + q with p = -w/mu the pole the offset is measured from (w = rho y_org^2) and q the
+    // smooth remainder; each step solves  q(mu_k) + q'(mu_k)(t - mu_k) - w/t = 0  (Newton on q with
+    // the pole kept exact: a few steps even when the root hugs the pole), inside the bracket
+    // with (geometric) bisection as the safeguard
+    const double w = rho * y2[org];
     double mu = (org == j) ? ((j + 1 < r) ? 0.25 * gap : 0.5 * gap) : -0.25 * gap;
     for (int it = 0; it < 200; ++it) {
-        double f = 0.0, df = 0.0;
+        double q = 0.0, dq = 0.0, qa = 0.0;
         for (int i = lane; i < r; i += 32) {
+            if (i == org) continue;
             const double den = (e[i] - eo) - mu;
-            const double q = y2[i] / den;
-            f += rho * q;
-            df += rho * q / den;
+            const double t = y2[i] / den;
+            q += rho * t;
+            qa += fabs(rho * t);
+            dq += rho * t / den;
         }
-        f = 1.0 + sb_warp_sum(f);
-        df = sb_warp_sum(df);
-        if (f == 0.0) break;
+        q = 1.0 + sb_warp_sum(q);
+        dq = sb_warp_sum(dq);
+        qa = sb_warp_sum(qa);
+        const double f = q - w / mu;
+        // f cannot be evaluated more accurately than eps * (sum of |terms|): stop there (LAPACK
+        // dlaed4's criterion); the Gu-Eisenstat z-vector keeps the eigenvectors orthogonal for
+        // whatever roots were computed
+        if (fabs(f) <= 4.0 * SEC_EPS * (1.0 + qa + fabs(w / mu))) break;
         if (f < 0.0) lo = mu; else hi = mu;
-        double next = mu - f / df;
+        const double Bq = q - dq * mu;
+        const double sq = sqrt(fma(Bq, Bq, 4.0 * dq * w));
+        double next;
+        if (dq > 0.0) {
+            if (org == j) next = Bq <= 0.0 ? (sq - Bq) / (2.0 * dq) : 2.0 * w / (Bq + sq);
+            else next = Bq >= 0.0 ? -(Bq + sq) / (2.0 * dq) : -2.0 * w / (sq - Bq);
+        } else {
+            next = (Bq != 0.0) ? w / Bq : 0.5 * (lo + hi);   // no other pole: q is constant, w/t = q
+        }
         if (!(next > lo && next < hi)) {
             if (org == j) {
                 if (lo > 0.0 && hi > 4.0 * lo) next = sqrt(lo) * sqrt(hi);
@@ -200,6 +220,207 @@ __device__ void secular_root(const double* __restrict__ e, const double* __restr
     *mu_out = mu;
 }
 
+// ------------------------------------------------------------------------------
+// Pre-phase: ONE block reflector for the big degenerate cluster.
+//
+// A quasi-Newton Hessian is lam0*I + low rank: most of its eigenvalues are the same number
+// and the matching rows of Vt are an arbitrary orthonormal basis of that eigenspace.  Every
+// rank-one term has weight on all of them, and deflating term by term reflects the whole
+// cluster once per term (2 reads + 1 write of ~n rows each).  Instead, with Z_C the m x T
+// block of all T pending z vectors on the m cluster rows, one Householder QR  Z_C = Q R  is
+// applied as  Rows_C <- Q^T Rows_C  (compact WY: I - W Tm^T W^T) in a single streaming pass
+// pair; afterwards term t only touches the first t+1 cluster rows (R is upper triangular)
+// and the per-term code below finds nothing left to reflect.
+//   cluster_qr_kernel      (1 CTA / system): finds the cluster, factors Z_C in place (Z gets R),
+//                          writes W [T][m] to `work`, Tm [16x16] and {c0, m, T} to `qwork`.
+//   cluster_reflect_kernel (column chunks x systems): the bandwidth-bound application.
+constexpr int CQ_TMAX = 16;
+constexpr int CR_THREADS = 128;
+constexpr int CR_ROWS = 64;
+
+__global__ void __launch_bounds__(SEC_THREADS)
+cluster_qr_kernel(const double* __restrict__ evals_, double* __restrict__ Z_, int zcap, const int* __restrict__ nterm,
+                  int n, double* __restrict__ work_, double* __restrict__ qwork_, const int* __restrict__ skip) {
+    const int b = blockIdx.x;
+    int* meta = reinterpret_cast<int*>(qwork_ + (size_t)b * n * n);
+    double* TmG = qwork_ + (size_t)b * n * n + 8;
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    const int T = skip[b] ? 0 : min(nterm[b], CQ_TMAX);
+    if (T == 0 || nterm[b] > CQ_TMAX) { if (tid == 0) { meta[0] = 0; meta[1] = 0; meta[2] = 0; } return; }
+    extern __shared__ double sm[];
+    double* d = sm;                          // n
+    double* scratch = d + n;                 // SB_SCRATCH_DOUBLES
+    double* G = scratch + SB_SCRATCH_DOUBLES;   // 16 x 16
+    double* Tm = G + CQ_TMAX * CQ_TMAX;      // 16 x 16
+    double* beta = Tm + CQ_TMAX * CQ_TMAX;   // 16
+    double* dots = beta + CQ_TMAX;           // 16
+    int* ibuf = reinterpret_cast<int*>(dots + CQ_TMAX);   // 16 ints
+    double dmax = 0.0;
+    for (int i = tid; i < n; i += nt) { const double v = evals_[(size_t)b * n + i]; d[i] = v; dmax = fmax(dmax, fabs(v)); }
+    dmax = sb_warp_max(dmax);
+    if (lane == 0) scratch[warp] = dmax;
+    __syncthreads();
+    dmax = 0.0;
+    for (int w = 0; w < nw; ++w) dmax = fmax(dmax, scratch[w]);
+    const double tolc = 8.0 * SEC_EPS * dmax;
+    // longest window [lo, i] of the ascending spectrum with d[i] - d[lo] <= tolc
+    int best = 0;
+    for (int i = tid; i < n; i += nt) {
+        int a = 0, e = i;                                   // smallest j in [0, i] with d[i] - d[j] <= tolc
+        const double di = d[i];
+        while (a < e) { const int mid = (a + e) >> 1; if (di - d[mid] <= tolc) e = mid; else a = mid + 1; }
+        const int key = ((i - a + 1) << 12) | i;            // n <= 4095
+        best = max(best, key);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    __syncthreads();
+    if (lane == 0) ibuf[warp] = best;
+    __syncthreads();
+    best = 0;
+    for (int w = 0; w < nw; ++w) best = max(best, ibuf[w]);
+    const int m = best >> 12, iend = best & 4095, c0 = iend - m + 1;
+    if (m < T + 2 || m < 8) { if (tid == 0) { meta[0] = 0; meta[1] = 0; meta[2] = 0; } return; }
+    double* Z = Z_ + (size_t)b * zcap * n;
+    double* W = work_ + (size_t)b * n * n;                  // [T][m]
+    auto row = [&](int j) { return c0 + m - 1 - j; };
+    __syncthreads();
+    for (int t = 0; t < T; ++t) {
+        double* zt = Z + (size_t)t * n;
+        double acc = 0.0;
+        for (int j = t + 1 + tid; j < m; j += nt) { const double v = zt[row(j)]; acc = fma(v, v, acc); }
+        const double tail2 = sb_block_sum(acc, scratch);
+        const double x0 = zt[row(t)];
+        if (!(tail2 > 0.0)) {                               // nothing below the diagonal
+            for (int j = tid; j < m; j += nt) W[(size_t)t * m + j] = 0.0;
+            if (tid == 0) beta[t] = 0.0;
+            __syncthreads();
+            continue;
+        }
+        const double nrm = sqrt(tail2 + x0 * x0);
+        const double alpha = x0 > 0.0 ? -nrm : nrm;
+        const double wt = x0 - alpha;
+        const double bt = 2.0 / (tail2 + wt * wt);
+        for (int j = tid; j < m; j += nt) W[(size_t)t * m + j] = j < t ? 0.0 : (j == t ? wt : zt[row(j)]);
+        __syncthreads();
+        for (int s2 = t + 1 + warp; s2 < T; s2 += nw) {
+            const double* zs = Z + (size_t)s2 * n;
+            double dd = 0.0;
+            for (int j = t + lane; j < m; j += 32) dd = fma(W[(size_t)t * m + j], zs[row(j)], dd);
+            dd = sb_warp_sum(dd);
+            if (lane == 0) dots[s2] = dd;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < (T - t - 1) * (m - t); idx += nt) {
+            const int s2 = t + 1 + idx / (m - t), j = t + idx % (m - t);
+            double* zs = Z + (size_t)s2 * n;
+            zs[row(j)] = fma(-bt * dots[s2], W[(size_t)t * m + j], zs[row(j)]);
+        }
+        for (int j = t + 1 + tid; j < m; j += nt) zt[row(j)] = 0.0;
+        if (tid == 0) { zt[row(t)] = alpha; beta[t] = bt; }
+        __syncthreads();
+    }
+    // compact WY: Q = H_0 ... H_{T-1} = I - W Tm W^T
+    for (int pr = warp; pr < T * T; pr += nw) {
+        const int i = pr / T, j = pr % T;
+        if (j <= i) continue;
+        double dd = 0.0;
+        for (int e = lane; e < m; e += 32) dd = fma(W[(size_t)i * m + e], W[(size_t)j * m + e], dd);
+        dd = sb_warp_sum(dd);
+        if (lane == 0) G[i * CQ_TMAX + j] = dd;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int t = 0; t < T; ++t) {
+            for (int i = 0; i < t; ++i) {
+                double acc = 0.0;
+                for (int l = i; l < t; ++l) acc += Tm[i * CQ_TMAX + l] * G[l * CQ_TMAX + t];
+                Tm[i * CQ_TMAX + t] = -beta[t] * acc;
+            }
+            Tm[t * CQ_TMAX + t] = beta[t];
+            for (int i = t + 1; i < T; ++i) Tm[i * CQ_TMAX + t] = 0.0;
+        }
+        meta[0] = c0; meta[1] = m; meta[2] = T;
+    }
+    __syncthreads();
+    for (int i = tid; i < T * T; i += nt) TmG[(i / T) * CQ_TMAX + (i % T)] = Tm[(i / T) * CQ_TMAX + (i % T)];
+}
+
+template <int TT>
+__global__ void __launch_bounds__(CR_THREADS)
+cluster_reflect_kernel(double* __restrict__ Vt_, const double* __restrict__ work_, const double* __restrict__ qwork_, int n) {
+    const int b = blockIdx.y;
+    const int* meta = reinterpret_cast<const int*>(qwork_ + (size_t)b * n * n);
+    const int c0 = meta[0], m = meta[1], T = meta[2];
+    if (m == 0 || T > TT || (TT > 2 && T <= TT / 2)) return;       // exactly one instantiation serves a system
+    __shared__ double Wb[TT][CR_ROWS];
+    __shared__ double Tm[TT * TT];
+    const double* TmG = qwork_ + (size_t)b * n * n + 8;
+    const double* W = work_ + (size_t)b * n * n;
+    const int tid = threadIdx.x;
+    const int col = blockIdx.x * CR_THREADS + tid;
+    const bool live = col < n;
+    double* X = Vt_ + (size_t)b * n * n + (live ? col : 0);
+    for (int i = tid; i < TT * TT; i += CR_THREADS) {
+        const int r = i / TT, c = i % TT;
+        Tm[i] = (r < T && c < T) ? TmG[r * CQ_TMAX + c] : 0.0;
+    }
+    double y[TT];
+#pragma unroll
+    for (int t = 0; t < TT; ++t) y[t] = 0.0;
+    for (int j0 = 0; j0 < m; j0 += CR_ROWS) {
+        const int jn = min(CR_ROWS, m - j0);
+        __syncthreads();
+        for (int i = tid; i < TT * CR_ROWS; i += CR_THREADS) {
+            const int t = i / CR_ROWS, jj = i % CR_ROWS;
+            Wb[t][jj] = (t < T && jj < jn) ? W[(size_t)t * m + j0 + jj] : 0.0;
+        }
+        __syncthreads();
+        if (live) {
+            for (int jj = 0; jj < jn; jj += 8) {
+                double x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = (jj + u < jn) ? X[(size_t)(c0 + m - 1 - (j0 + jj + u)) * n] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+#pragma unroll
+                    for (int t = 0; t < TT; ++t) y[t] = fma(Wb[t][jj + u], x[u], y[t]);
+            }
+        }
+    }
+    double yt[TT];
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < TT; ++i) acc = fma(Tm[i * TT + t], y[i], acc);      // (Tm^T y)_t, Tm upper triangular
+        yt[t] = acc;
+    }
+    for (int j0 = 0; j0 < m; j0 += CR_ROWS) {
+        const int jn = min(CR_ROWS, m - j0);
+        __syncthreads();
+        for (int i = tid; i < TT * CR_ROWS; i += CR_THREADS) {
+            const int t = i / CR_ROWS, jj = i % CR_ROWS;
+            Wb[t][jj] = (t < T && jj < jn) ? W[(size_t)t * m + j0 + jj] : 0.0;
+        }
+        __syncthreads();
+        if (live) {
+            for (int jj = 0; jj < jn; jj += 8) {
+                double x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = (jj + u < jn) ? X[(size_t)(c0 + m - 1 - (j0 + jj + u)) * n] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    double acc = x[u];
+#pragma unroll
+                    for (int t = 0; t < TT; ++t) acc = fma(-Wb[t][jj + u], yt[t], acc);
+                    if (jj + u < jn) X[(size_t)(c0 + m - 1 - (j0 + jj + u)) * n] = acc;
+                }
+            }
+        }
+    }
+}
+
 // optional in-kernel phase profile (cycles, summed over CTAs by thread 0)
 __device__ unsigned long long sec_prof[16];
 #define SEC_MARK(ph)                                                        \
@@ -211,9 +432,15 @@ __device__ unsigned long long sec_prof[16];
         }                                                                   \
     } while (0)
 
+// the per-term kernel is latency-bound (short serial phases, few rows touched): small CTAs,
+// several per SM, hide that better than one wide CTA
+constexpr int SECK_THREADS = 128;
+constexpr int SEC_QS_MAX = 54;          // r <= this: eigenvector block Qh lives in shared memory
+
 struct SecShared {
     double scratch[SB_SCRATCH_DOUBLES];
     int r, nrot, flag;
+    int wcnt[SECK_THREADS / 32];
     double rho;
 };
 
@@ -257,7 +484,7 @@ __device__ void apply_rotations(double* __restrict__ Vt, int n, const int* __res
 // Zs: [b, zcap, n] (row t = V^T p_t in the CURRENT row order of Vt), work: [b, n, n],
 // qwork: [b, n, n].  On exit evals ascending, Vt rows permuted accordingly.
 template <int CPT>
-__global__ void __launch_bounds__(SEC_THREADS)
+__global__ void __launch_bounds__(SECK_THREADS, 4)
 secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, double* __restrict__ Z_, int zcap,
                       const double* __restrict__ sig_, const int* __restrict__ nterm, int n,
                       double* __restrict__ work_, double* __restrict__ qwork_, int* __restrict__ status,
@@ -315,12 +542,25 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
         // eigenpair; runs of (numerically) equal eigenvalues among the rest are an exact
         // eigenspace, so ONE Householder reflection of those eigenvectors can move all
         // of z's weight onto a single row (instead of a chain of plane rotations).
+        // candidates (non-negligible z) in ascending-d order: ballot compaction
+        if (tid == 0) S.flag = 0;
+        __syncthreads();
+        for (int p0 = 0; p0 < n; p0 += nt) {
+            const int p = p0 + tid;
+            const int i = p < n ? ord[p] : 0;
+            const bool f = p < n && fabs(rho * z[i]) > tol;
+            const unsigned bal = __ballot_sync(0xffffffffu, f);
+            if ((tid & 31) == 0) S.wcnt[tid >> 5] = __popc(bal);
+            __syncthreads();
+            int off = S.flag;
+            for (int w = 0; w < (tid >> 5); ++w) off += S.wcnt[w];
+            if (f) nd[off + __popc(bal & ((1u << (tid & 31)) - 1u))] = i;
+            __syncthreads();
+            if (tid == 0) { int tot = 0; for (int w = 0; w < nt / 32; ++w) tot += S.wcnt[w]; S.flag += tot; }
+            __syncthreads();
+        }
         if (tid == 0) {
-            int na = 0;
-            for (int p = 0; p < n; ++p) {
-                const int i = ord[p];
-                if (fabs(rho * z[i]) > tol) nd[na++] = i;           // candidates, ascending d
-            }
+            const int na = S.flag;
             int nc = 0, ncand = 0;
             const double tolc = 8.0 * SEC_EPS * dmax;
             int a = 0;
@@ -368,7 +608,7 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
 #pragma unroll
                         for (int q = 0; q < LPC; ++q) yp[q] = 0.0;
                         {
-                            constexpr int RU = 4;                // rows in flight per warp
+                            constexpr int RU = 2;                // rows in flight per warp
                             for (int i0 = warp; i0 < m; i0 += nw * RU) {
                                 double v[RU][LPC];
                                 double wv[RU];
@@ -402,7 +642,7 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
 #pragma unroll
                         for (int q = 0; q < LPC; ++q) yp[q] = ysum_[lane + 32 * q];
                         {
-                            constexpr int RU = 4;
+                            constexpr int RU = 2;
                             for (int i0 = warp; i0 < m; i0 += nw * RU) {
                                 double v[RU][LPC];
 #pragma unroll
@@ -533,16 +773,21 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
         }
         __syncthreads();
         // eigenvector matrix (mirrored index space): Qh[i*r + j] = zh_i / (dd_i - lam_j), columns normalised
+        const bool qsmem = r <= SEC_QS_MAX && (size_t)r * r <= (size_t)tile_doubles;
+        if (qsmem) Qh = tile;
+        else Qh = qwork_ + (size_t)b * n * n;
+        for (int idx = tid; idx < r * r; idx += nt) {
+            const int i = idx / r, j = idx % r;
+            Qh[idx] = zh[i] / ((dd[i] - dd[org[j]]) - mu[j]);
+        }
+        __syncthreads();
         for (int j = tid; j < r; j += nt) {
             double nrm = 0.0;
-            for (int i = 0; i < r; ++i) {
-                const double q = zh[i] / ((dd[i] - dd[org[j]]) - mu[j]);
-                Qh[(size_t)i * r + j] = q;
-                nrm = fma(q, q, nrm);
-            }
-            nrm = 1.0 / sqrt(nrm);
-            for (int i = 0; i < r; ++i) Qh[(size_t)i * r + j] *= nrm;
+            for (int i = 0; i < r; ++i) { const double q = Qh[(size_t)i * r + j]; nrm = fma(q, q, nrm); }
+            y2[j] = 1.0 / sqrt(nrm);           // y2 is free again (weights consumed by the roots / zh)
         }
+        __syncthreads();
+        for (int idx = tid; idx < r * r; idx += nt) Qh[idx] *= y2[idx % r];
         __syncthreads();
         SEC_MARK(4);
         // ---------------- new eigenvectors: row_new(j) = sum_i Qh[i][j] row_old(i)   (mirrored index i,j)
@@ -552,7 +797,63 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
             int cw = tile_doubles / r;
             cw = (cw / 32) * 32;
             if (cw > n) cw = ((n + 31) / 32) * 32;
-            if (cw >= 32) {
+            if (qsmem) {
+                // warps own blocks of 8 new rows, lanes own 4 columns of a 128-column chunk; old rows
+                // stream from global/L1 (each is read once per row block), Qh from shared memory;
+                // a chunk is written back in place after a barrier (chunks are independent)
+                constexpr int JB = 8, CC = 4, IU = 2;
+                const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+                const int nblk = (r + JB - 1) / JB;
+                for (int c0 = 0; c0 < n; c0 += 32 * CC) {
+                    for (int blk0 = 0; blk0 < nblk; blk0 += nw) {
+                        // all row blocks of this chunk must be computed before any is stored: when
+                        // nblk > nw the extra rounds go through `work`
+                        const int blk = blk0 + warp;
+                        const int jb0 = blk * JB;
+                        if (blk < nblk) {
+                            double acc[JB][CC];
+#pragma unroll
+                            for (int jj = 0; jj < JB; ++jj)
+#pragma unroll
+                                for (int q = 0; q < CC; ++q) acc[jj][q] = 0.0;
+                            for (int i0 = 0; i0 < r; i0 += IU) {
+                                double x[IU][CC];
+#pragma unroll
+                                for (int u = 0; u < IU; ++u) {
+                                    const int i = i0 + u;
+                                    const double* src = Vt + (size_t)rowof(i < r ? i : 0) * n + c0;
+#pragma unroll
+                                    for (int q = 0; q < CC; ++q) {
+                                        const int col = lane + 32 * q;
+                                        x[u][q] = (i < r && c0 + col < n) ? src[col] : 0.0;
+                                    }
+                                }
+#pragma unroll
+                                for (int u = 0; u < IU; ++u) {
+                                    const int i = i0 + u;
+                                    if (i >= r) break;
+                                    const double* qrow = Qh + (size_t)i * r + jb0;
+#pragma unroll
+                                    for (int jj = 0; jj < JB; ++jj) {
+                                        const double qv = (jb0 + jj < r) ? qrow[jj] : 0.0;
+#pragma unroll
+                                        for (int q = 0; q < CC; ++q) acc[jj][q] = fma(qv, x[u][q], acc[jj][q]);
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int jj = 0; jj < JB; ++jj) {
+                                if (jb0 + jj >= r) break;
+#pragma unroll
+                                for (int q = 0; q < CC; ++q) {
+                                    const int col = lane + 32 * q;
+                                    if (c0 + col < n) work[(size_t)(jb0 + jj) * n + c0 + col] = acc[jj][q];
+                                }
+                            }
+                        }
+                    }
+                }
+            } else if (cw >= 32) {
                 constexpr int RB = 8;
                 for (int c0 = 0; c0 < n; c0 += cw) {
                     const int wcols = min(cw, n - c0);
@@ -736,21 +1037,37 @@ extern "C" int sb_secular_update_impl(double* evals, double* Vt, double* Z, int 
     int dev = 0, optin = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    size_t tile_bytes = 64 * 1024;
+    // 23 KB of staging: Qh of up to 54 x 54 in shared memory, and 4 CTAs per SM at n = 384
+    size_t tile_bytes = 23 * 1024;
     if (base + tile_bytes > (size_t)optin) tile_bytes = base < (size_t)optin ? ((size_t)optin - base) / 1024 * 1024 : 0;
     const int tile_doubles = (int)(tile_bytes / sizeof(double));
-    if (tile_doubles < (SEC_THREADS / 32 + 1) * 256) return -2;   // n too large for this build
+    if (tile_doubles < (SECK_THREADS / 32 + 1) * 256) return -2;   // n too large for this build
     const size_t smem = base + tile_bytes;
-    const int cpt = (n + SEC_THREADS - 1) / SEC_THREADS;
+    const int cpt = (n + SECK_THREADS - 1) / SECK_THREADS;
+    if (n >= 32 && n < 4096 && !getenv("SB_NO_CLUSTER_QR")) {
+        // pre-phase: one block reflector for the degenerate cluster (all terms at once)
+        const size_t qsm = ((size_t)n + SB_SCRATCH_DOUBLES + 2 * CQ_TMAX * CQ_TMAX + 2 * CQ_TMAX) * sizeof(double) + 64;
+        cudaFuncSetAttribute(cluster_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsm);
+        SB_COUNT(1);
+        cluster_qr_kernel<<<batch, SEC_THREADS, qsm, st>>>(evals, Z, zcap, nterm, n, work, qwork, skip);
+        dim3 grid((n + CR_THREADS - 1) / CR_THREADS, batch);
+        const int tmax = zcap < CQ_TMAX ? zcap : CQ_TMAX;
+        SB_COUNT(1);
+        cluster_reflect_kernel<2><<<grid, CR_THREADS, 0, st>>>(Vt, work, qwork, n);
+        if (tmax > 2) { SB_COUNT(1); cluster_reflect_kernel<4><<<grid, CR_THREADS, 0, st>>>(Vt, work, qwork, n); }
+        if (tmax > 4) { SB_COUNT(1); cluster_reflect_kernel<8><<<grid, CR_THREADS, 0, st>>>(Vt, work, qwork, n); }
+        if (tmax > 8) { SB_COUNT(1); cluster_reflect_kernel<16><<<grid, CR_THREADS, 0, st>>>(Vt, work, qwork, n); }
+    }
     SB_COUNT(1);
 #define SB_SEC_LAUNCH(C)                                                                                          \
     cudaFuncSetAttribute(secular_update_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-    secular_update_kernel<C><<<batch, SEC_THREADS, smem, st>>>(evals, Vt, Z, zcap, sig, nterm, n, work, qwork,  \
+    secular_update_kernel<C><<<batch, SECK_THREADS, smem, st>>>(evals, Vt, Z, zcap, sig, nterm, n, work, qwork,  \
                                                                status, skip, tile_doubles)
     if (cpt <= 1) { SB_SEC_LAUNCH(1); }
     else if (cpt <= 2) { SB_SEC_LAUNCH(2); }
     else if (cpt <= 4) { SB_SEC_LAUNCH(4); }
     else if (cpt <= 8) { SB_SEC_LAUNCH(8); }
+    else if (cpt <= 16) { SB_SEC_LAUNCH(16); }
     else return -2;
 #undef SB_SEC_LAUNCH
     return SB_LAUNCH_CHECK();

@@ -14,8 +14,8 @@ Scope (raises NotImplementedError otherwise, never falls back to the CPU): Carte
 coordinates; translation constraints (``sella_b200.Constraints.fix_translation``, incl.
 the centre-of-geometry projection the reference adds by default, peswrapper.py:233-244);
 no rotation projection (pass ``proj_rot=False`` for non-periodic systems: the reference
-would add the nonlinear ``fix_rotation`` there), ``threepoint=False``, no
-``hessian_function``, no cell optimisation.
+would add the nonlinear ``fix_rotation`` there), no ``hessian_function``, no cell
+optimisation.
 """
 import warnings
 from time import localtime, strftime
@@ -131,8 +131,8 @@ class Sella(_Base):
                  hessian_function=None, optimize_cell=False, **kwargs):
         if internal:
             raise NotImplementedError("internal coordinates are not on the CUDA path yet")
-        if optimize_cell or hessian_function is not None or threepoint or v0 is not None:
-            raise NotImplementedError("optimize_cell / hessian_function / threepoint / v0 are not on the CUDA path")
+        if optimize_cell or hessian_function is not None or v0 is not None:
+            raise NotImplementedError("optimize_cell / hessian_function / v0 are not on the CUDA path")
         pbc = np.asarray(getattr(atoms, "pbc", [False] * 3))
         proj_trans = kwargs.pop("proj_trans", None)
         proj_rot = kwargs.pop("proj_rot", None)
@@ -170,7 +170,7 @@ class Sella(_Base):
         self._eng = BatchedSella(self._surface, x0, order=order, delta0=delta0, sigma_inc=sigma_inc,
                                  sigma_dec=sigma_dec, rho_dec=rho_dec, rho_inc=rho_inc, eig=eig, eta=eta,
                                  method=method, gamma=gamma, rs=rs, nsteps_per_diag=nsteps_per_diag,
-                                 diag_every_n=diag_every_n, eigensolver=eigensolver, kcap=16,
+                                 diag_every_n=diag_every_n, eigensolver=eigensolver, kcap=16, threepoint=threepoint,
                                  constraints=None if lin is None else (lin[0], lin[1][None, :]))
         self.pes = _PESView(self)
         self.ord = order
