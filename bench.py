@@ -34,6 +34,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "optimizer steps/sec (batched 3N-DOF Davidson+TR)"
+# dram__bytes_read.sum + dram__bytes_write.sum per sb_secular_update call (three kernels), from the
+# committed ncu --set full captures, keyed by (systems per GPU, 3N)
+NCU_TRAFFIC = {(1024, 384): 3.537e9}     # profiles/ncu_full_r1_h_eigen_update.csv
 UNIT = "system-steps/s"
 
 
@@ -332,22 +335,38 @@ def run_ours(args):
     hv_bytes = b * 8 * (n * n + 2 * n)
     hv_gbs = hv_bytes / (hv_ms * 1e-3) / 1e9
     # profiled pass (not part of `value`): CUDA events around the heaviest kernels of a step
+    import ctypes
     eng.prof = {}
-    for _ in range(4):
+    lib.sb_secular_timing(None, 1)
+    t3 = (ctypes.c_float * 3)()
+    parts = []
+    for _ in range(6):
+        nd0 = eng.ndiag
         eng.step()
+        if eng.ndiag == nd0 and lib.sb_secular_timing(t3, -1) == 0:     # plain step: last call = the rank-2 update
+            parts.append(tuple(t3))
+    lib.sb_secular_timing(t3, 0)
     prof = eng.prof_summary()
     eng.prof = None
     step_ms = ms_max / args.steps
     sec_cnt, sec_ms = prof.get("secular_update_k1", (0, 0.0))
+    part_ms = [sum(p[i] for p in parts) / len(parts) for i in range(3)] if parts else [0.0, 0.0, 0.0]
     sec_bytes = b * 8 * 2 * n * n               # every eigenvector read once and written once
     sec_gbs = sec_bytes / (sec_ms * 1e-3) / 1e9 if sec_ms else 0.0
-    roofline = dict(kernel="secular_update_kernel (rank-2 eigen-update of (evals, Vt), one launch per step)",
-                    bound="hbm", achieved=sec_gbs, peak=peak, unit="GB/s", frac=sec_gbs / peak, traffic=None,
+    # DRAM bytes per launch from `ncu --set full` of the same workload (profiles/ncu_full_r1_h_*.csv)
+    traffic = NCU_TRAFFIC.get((b, n))
+    roofline = dict(kernel="eigen-update of (evals, Vt) after the rank-2 secant update: cluster_qr_kernel + "
+                           "cluster_reflect_kernel<2> + secular_update_kernel<4> (one sb_secular_update per step; "
+                           "the largest item of a step)",
+                    bound="hbm", achieved=sec_gbs, peak=peak, unit="GB/s", frac=sec_gbs / peak, traffic=traffic,
                     ms_per_launch=sec_ms, share_of_step=min(1.0, sec_ms / step_ms) if step_ms else None,
                     bytes_per_launch=sec_bytes, peak_source=peak_src,
-                    note="largest single kernel of a step; algorithmic bytes = read+write the eigenvector matrix "
-                         "once (2*n^2*8 per system); the kernel is latency-bound (serial deflation scan, "
-                         "reflections/rotations of eigenvector rows), see DESIGN.md section 5")
+                    kernels_ms=dict(cluster_qr_kernel=part_ms[0], cluster_reflect_kernel=part_ms[1],
+                                    secular_update_kernel=part_ms[2]),
+                    note="algorithmic bytes = read+write the eigenvector matrix once (2*n^2*8 per system); "
+                         "cluster_reflect streams the degenerate cluster's rows (2 reads + 1 write, the second read "
+                         "mostly from L2); secular_update_kernel is latency-bound (deflation, secular roots, "
+                         "a few dozen rows rewritten), see DESIGN.md section 5")
     roofline_hv = dict(kernel="hv_tma_kernel<1> (batched H.V / B.s / V^T g)", bound="hbm", achieved=hv_gbs,
                        peak=peak, unit="GB/s", frac=hv_gbs / peak, frac_of_8TBs_nominal=hv_gbs / 8000.0,
                        traffic=None, ms_per_launch=hv_ms, bytes_per_launch=hv_bytes, peak_source=peak_src,

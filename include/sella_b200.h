@@ -161,6 +161,10 @@ int sb_lowrank_factor(const double* U, const double* J, const double* Cmat, int 
 /* diagnostic: cycles spent per phase of sb_secular_update, summed over CTAs (host array
  * of 16 uint64; synchronises the device).                                              */
 int sb_secular_profile(unsigned long long* out16, int reset);
+/* diagnostic: enable > 0 switches on CUDA-event timing of the three kernels of the following
+ * sb_secular_update calls; enable <= 0 reads the last call's {cluster_qr, cluster_reflect,
+ * secular_update} milliseconds into out3 (synchronises; enable == 0 also switches it off).  */
+int sb_secular_timing(float* out3, int enable);
 int sb_secular_update(double* evals, double* Vt, double* Z, int zcap, const double* sig,
                       const int32_t* nterm, int n, double* work, double* qwork, int32_t* status,
                       const int32_t* skip, int batch, void* stream);

@@ -239,6 +239,8 @@ int sb_lowrank_factor(const double* U, const double* J, const double* Cmat, int 
     return sb_lowrank_factor_impl(U, J, Cmat, kcap, kvec, n, P, sig, nterm, skip, batch, ST);
 }
 extern "C" int sb_secular_profile_impl(unsigned long long*, int);
+extern "C" int sb_secular_timing_impl(float*, int);
+int sb_secular_timing(float* out3, int enable) { return sb_secular_timing_impl(out3, enable); }
 extern "C" int sb_rfo_profile_impl(unsigned long long*, int);
 int sb_rfo_profile(unsigned long long* out8, int reset) { return sb_rfo_profile_impl(out8, reset); }
 int sb_secular_profile(unsigned long long* out16, int reset) { return sb_secular_profile_impl(out16, reset); }

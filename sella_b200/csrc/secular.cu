@@ -794,13 +794,11 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
         {
             auto rowof = [&](int i) { return neg ? nd[r - 1 - i] : nd[i]; };
             // out[j][col] = sum_i Qh[i][j] old[rowof(i)][col], column chunks staged in smem
-            int cw = tile_doubles / r;
-            cw = (cw / 32) * 32;
-            if (cw > n) cw = ((n + 31) / 32) * 32;
-            if (qsmem) {
+            {
                 // warps own blocks of 8 new rows, lanes own 4 columns of a 128-column chunk; old rows
-                // stream from global/L1 (each is read once per row block), Qh from shared memory;
-                // a chunk is written back in place after a barrier (chunks are independent)
+                // stream from global/L1 (each is read once per row block), Qh from shared memory
+                // (r <= SEC_QS_MAX) or from L1/L2 (8 consecutive doubles per old row, broadcast);
+                // results go through `work` and are copied back below
                 constexpr int JB = 8, CC = 4, IU = 2;
                 const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
                 const int nblk = (r + JB - 1) / JB;
@@ -853,59 +851,6 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
                         }
                     }
                 }
-            } else if (cw >= 32) {
-                constexpr int RB = 8;
-                for (int c0 = 0; c0 < n; c0 += cw) {
-                    const int wcols = min(cw, n - c0);
-                    __syncthreads();
-                    for (int idx = tid; idx < r * wcols; idx += nt) {
-                        const int i = idx / wcols, cc = idx % wcols;
-                        tile[i * cw + cc] = Vt[(size_t)rowof(i) * n + c0 + cc];
-                    }
-                    __syncthreads();
-                    // work items: (j-block, column)
-                    const int njb = (r + RB - 1) / RB;
-                    for (int item = tid; item < njb * wcols; item += nt) {
-                        const int jb0 = (item / wcols) * RB, cc = item % wcols;
-                        const int jb = min(RB, r - jb0);
-                        double a8[RB];
-#pragma unroll
-                        for (int q = 0; q < RB; ++q) a8[q] = 0.0;
-                        for (int i = 0; i < r; ++i) {
-                            const double x = tile[i * cw + cc];
-                            const double* qrow = Qh + (size_t)i * r + jb0;
-#pragma unroll
-                            for (int q = 0; q < RB; ++q)
-                                if (q < jb) a8[q] = fma(qrow[q], x, a8[q]);
-                        }
-#pragma unroll
-                        for (int q = 0; q < RB; ++q)
-                            if (q < jb) work[(size_t)(jb0 + q) * n + c0 + cc] = a8[q];
-                    }
-                }
-            } else {
-            constexpr int JB = 8;
-            for (int j0 = 0; j0 < r; j0 += JB) {
-                const int jb = min(JB, r - j0);
-#pragma unroll
-                for (int u = 0; u < CPT; ++u) {
-                    const int col = tid + u * nt;
-                    if (col >= n) continue;
-                    double a8[JB];
-#pragma unroll
-                    for (int q = 0; q < JB; ++q) a8[q] = 0.0;
-                    for (int i = 0; i < r; ++i) {
-                        const double x = Vt[(size_t)rowof(i) * n + col];
-                        const double* qrow = Qh + (size_t)i * r + j0;
-#pragma unroll
-                        for (int q = 0; q < JB; ++q)
-                            if (q < jb) a8[q] = fma(qrow[q], x, a8[q]);
-                    }
-#pragma unroll
-                    for (int q = 0; q < JB; ++q)
-                        if (q < jb) work[(size_t)(j0 + q) * n + col] = a8[q];
-                }
-            }
             }
             __syncthreads();
             for (int idx = tid; idx < r * n; idx += nt) {
@@ -1030,6 +975,23 @@ extern "C" int sb_lowrank_factor_impl(const double* U, const double* J, const do
     return SB_LAUNCH_CHECK();
 }
 
+// optional per-kernel timing of the three kernels of one eigen-update (bench.py roofline)
+static int sec_timing_on = 0;
+static cudaEvent_t sec_ev[4];
+extern "C" int sb_secular_timing_impl(float* out3, int enable) {
+    if (enable > 0 && !sec_timing_on) {
+        for (int i = 0; i < 4; ++i) cudaEventCreate(&sec_ev[i]);
+        sec_timing_on = 1;
+        return 0;
+    }
+    if (!sec_timing_on) return -1;
+    cudaError_t e = cudaEventSynchronize(sec_ev[3]);
+    if (e != cudaSuccess) return (int)e;
+    for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&out3[i], sec_ev[i], sec_ev[i + 1]);
+    if (enable == 0) sec_timing_on = 0;
+    return 0;
+}
+
 extern "C" int sb_secular_update_impl(double* evals, double* Vt, double* Z, int zcap, const double* sig,
                                       const int* nterm, int n, double* work, double* qwork, int* status,
                                       const int* skip, int batch, cudaStream_t st) {
@@ -1044,12 +1006,14 @@ extern "C" int sb_secular_update_impl(double* evals, double* Vt, double* Z, int 
     if (tile_doubles < (SECK_THREADS / 32 + 1) * 256) return -2;   // n too large for this build
     const size_t smem = base + tile_bytes;
     const int cpt = (n + SECK_THREADS - 1) / SECK_THREADS;
+    if (sec_timing_on) cudaEventRecord(sec_ev[0], st);
     if (n >= 32 && n < 4096 && !getenv("SB_NO_CLUSTER_QR")) {
         // pre-phase: one block reflector for the degenerate cluster (all terms at once)
         const size_t qsm = ((size_t)n + SB_SCRATCH_DOUBLES + 2 * CQ_TMAX * CQ_TMAX + 2 * CQ_TMAX) * sizeof(double) + 64;
         cudaFuncSetAttribute(cluster_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsm);
         SB_COUNT(1);
         cluster_qr_kernel<<<batch, SEC_THREADS, qsm, st>>>(evals, Z, zcap, nterm, n, work, qwork, skip);
+        if (sec_timing_on) cudaEventRecord(sec_ev[1], st);
         dim3 grid((n + CR_THREADS - 1) / CR_THREADS, batch);
         const int tmax = zcap < CQ_TMAX ? zcap : CQ_TMAX;
         SB_COUNT(1);
@@ -1057,7 +1021,10 @@ extern "C" int sb_secular_update_impl(double* evals, double* Vt, double* Z, int 
         if (tmax > 2) { SB_COUNT(1); cluster_reflect_kernel<4><<<grid, CR_THREADS, 0, st>>>(Vt, work, qwork, n); }
         if (tmax > 4) { SB_COUNT(1); cluster_reflect_kernel<8><<<grid, CR_THREADS, 0, st>>>(Vt, work, qwork, n); }
         if (tmax > 8) { SB_COUNT(1); cluster_reflect_kernel<16><<<grid, CR_THREADS, 0, st>>>(Vt, work, qwork, n); }
+    } else if (sec_timing_on) {
+        cudaEventRecord(sec_ev[1], st);
     }
+    if (sec_timing_on) cudaEventRecord(sec_ev[2], st);
     SB_COUNT(1);
 #define SB_SEC_LAUNCH(C)                                                                                          \
     cudaFuncSetAttribute(secular_update_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
@@ -1070,5 +1037,6 @@ extern "C" int sb_secular_update_impl(double* evals, double* Vt, double* Z, int 
     else if (cpt <= 16) { SB_SEC_LAUNCH(16); }
     else return -2;
 #undef SB_SEC_LAUNCH
+    if (sec_timing_on) cudaEventRecord(sec_ev[3], st);
     return SB_LAUNCH_CHECK();
 }
