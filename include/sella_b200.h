@@ -56,6 +56,17 @@ int sb_quadratic_pes(const double* A, const double* xstar, const double* x,
                      double* f, double* g, double* dwork, const int32_t* active,
                      int batch, int n, void* stream);
 
+/* EMT-form copper surface (energy f[b], gradient g[b,3N]) for a batch of configurations: the
+ * on-device stand-in for the ASE calculator call of sella/peswrapper.py:413-418 in the EMT
+ * configurations (README.md:14,29).  Functional form and constants: oracle/emt.py ("EMT-form";
+ * ASE itself is not part of the reference tree).  par6 (HOST): E0, s0, V0, eta2, kappa, lambda
+ * in eV / Angstrom; cell (device, may be NULL): lattice vectors as rows, shared by the batch
+ * (cellstride 0) or per configuration (cellstride 9); nimg3 (HOST): periodic images to scan
+ * along each lattice vector (0 = not periodic).                                            */
+int sb_emt_pes(const double* x, int natoms, const double* cell, long long cellstride,
+               const int32_t* nimg3, const double* par6, double* f, double* g,
+               const int32_t* active, int batch, void* stream);
+
 /* Symmetric eigendecomposition, replaces scipy.linalg.eigh at
  * sella/linalg.py:174-195, sella/optimize/stepper.py:79-83,
  * sella/eigensolvers.py:11, sella/_gpu.py:70-97 (gpu_eigh / gpu_eigh_t).

@@ -132,6 +132,13 @@ int sb_quadratic_pes(const double* A, const double* xstar, const double* x, doub
     dot_kernel<<<batch, 256, 0, st>>>(dwork, g, f, 0.5, active, n);
     return SB_LAUNCH_CHECK();
 }
+extern "C" int sb_emt_pes_impl(const double*, int, const double*, long long, const int*, const double*, double*,
+                               double*, const int*, int, cudaStream_t);
+int sb_emt_pes(const double* x, int natoms, const double* cell, long long cellstride, const int32_t* nimg3,
+               const double* par6, double* f, double* g, const int32_t* active, int batch, void* stream) {
+    if (natoms < 1 || !par6) return -1;
+    return sb_emt_pes_impl(x, natoms, cell, cellstride, nimg3, par6, f, g, active, batch, (cudaStream_t)stream);
+}
 
 int sb_eigh(const double* A, double* evals, double* Vt, double* work, double* small_work, int32_t* status,
             const int32_t* active, int batch, int n, void* stream) {

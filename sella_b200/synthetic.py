@@ -11,6 +11,9 @@
 ``quadratic_batch_torch`` draws the same family directly on a torch device for
 the large benchmark configurations (1024 x 384^2 and up), where a per-system
 host QR would take minutes.
+
+``fcc_cluster`` / ``fcc111_slab``: copper geometries of the EMT configurations of BASELINE.json
+(C2: 64-atom clusters, C3: 128-atom slabs), built without ASE.
 """
 import numpy as np
 
@@ -72,3 +75,42 @@ def quadratic_batch_torch(batch, n, device, seed=1000, chunk=256):
             (m, n), dtype=torch.float64, device=device, generator=gen) / n ** 0.5
         del G, Q, Ab
     return A, xs, x0
+
+
+# --------------------------------------------------------------------------- copper geometries
+def fcc_cluster(natoms, a=3.61, seed=0, rattle=0.05):
+    """Ball cut from fcc copper + Gaussian rattle (config C2 of BASELINE.json)."""
+    m = 6
+    pts = []
+    basis = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]])
+    for i in range(-m, m + 1):
+        for j in range(-m, m + 1):
+            for k in range(-m, m + 1):
+                for bvec in basis:
+                    pts.append((np.array([i, j, k]) + bvec) * a)
+    pts = np.array(pts) - np.array([0.13, 0.07, 0.03]) * a          # generic centre: no ties at the surface
+    order = np.argsort((pts ** 2).sum(1), kind="stable")
+    pos = pts[order[:natoms]].copy()
+    pos -= pos.mean(0)
+    rng = np.random.RandomState(seed)
+    return pos + rattle * rng.normal(size=pos.shape)
+
+
+def fcc111_slab(nx, ny, nlayers, a=3.61, vacuum=7.5, seed=None, rattle=0.05):
+    """Orthogonal fcc(111) slab: nx x ny surface cells (2 atoms each per layer), ABC stacking,
+    periodic in x and y.  Returns (positions, cell, pbc)."""
+    d = a / np.sqrt(2.0)
+    ax, ay, dz = d, d * np.sqrt(3.0), a / np.sqrt(3.0)
+    pos = []
+    for l in range(nlayers):
+        off = np.array([0.0, (l % 3) * ay / 3.0])
+        for i in range(nx):
+            for j in range(ny):
+                for bx, by in ((0.0, 0.0), (0.5, 0.5)):
+                    p = np.array([(i + bx) * ax, (j + by) * ay]) + off
+                    pos.append([p[0] % (nx * ax), p[1] % (ny * ay), vacuum + l * dz])
+    pos = np.array(pos)
+    cell = np.diag([nx * ax, ny * ay, 2 * vacuum + (nlayers - 1) * dz])
+    if seed is not None:
+        pos = pos + rattle * np.random.RandomState(seed).normal(size=pos.shape)
+    return pos, cell, (True, True, False)
