@@ -46,33 +46,76 @@ def parse():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=1024, help="systems per GPU")
-    ap.add_argument("--n", type=int, default=384, help="3N degrees of freedom")
+    ap.add_argument("--workload", default="quadratic", choices=["quadratic", "emt-slab", "emt-cluster"],
+                    help="quadratic: synthetic indefinite-quadratic PES (SURVEY 8d; the default, C4/C5 family); "
+                         "emt-slab: C3-style 128-atom Cu(111) slabs, bottom half fixed, EMT-form surface; "
+                         "emt-cluster: C2-style 64-atom Cu clusters, centre of mass held, EMT-form surface")
+    ap.add_argument("--batch", type=int, default=None, help="systems per GPU (default 1024; 256 for emt-cluster)")
+    ap.add_argument("--n", type=int, default=None, help="3N degrees of freedom (default 384; 192 for emt-cluster)")
     ap.add_argument("--rs", default="tr")
     ap.add_argument("--method", default="prfo", help="step model: prfo (Sella's default for saddles), rfo, qn")
     ap.add_argument("--kdiag", type=int, default=5)
     ap.add_argument("--diag-every", type=int, default=3)
     ap.add_argument("--cpu-systems", type=int, default=0, help="reference sample size (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.batch is None:
+        a.batch = 256 if a.workload == "emt-cluster" else 1024
+    if a.n is None:
+        a.n = 192 if a.workload == "emt-cluster" else 384
+    if a.workload == "emt-cluster" and "--kdiag" not in sys.argv:
+        a.kdiag = 2                                  # BASELINE.json C2: Davidson k=2
+    return a
+
+
+def emt_problem(args, first, count):
+    """Geometries and linear constraints of the EMT workloads (host arrays; shared by both arms)."""
+    from sella_b200.synthetic import fcc_cluster, fcc111_slab
+    nat = args.n // 3
+    if args.workload == "emt-cluster":
+        x0 = np.stack([fcc_cluster(nat, seed=first + i).ravel() for i in range(count)])
+        C = np.zeros((3, args.n))
+        for d in range(3):
+            C[d, d::3] = 1.0 / nat                   # the reference's default translation projection
+        return x0, C, None, (False, False, False)
+    ny = 2
+    nl = 8
+    nx = nat // (2 * ny * nl)
+    if 2 * nx * ny * nl != nat:
+        raise SystemExit("emt-slab needs 3N = 96 * k (k surface cells x 2 x 8 layers)")
+    geo = [fcc111_slab(nx, ny, nl, seed=first + i) for i in range(count)]
+    ideal = fcc111_slab(nx, ny, nl)[0]
+    fixed = np.nonzero(ideal[:, 2] < ideal[:, 2].mean())[0]            # bottom half, Constraints.fix_translation
+    C = np.zeros((3 * len(fixed), args.n))
+    for r, i in enumerate(fixed):
+        for d in range(3):
+            C[3 * r + d, 3 * i + d] = 1.0
+    return np.stack([g[0].ravel() for g in geo]), C, geo[0][1], geo[0][2]
 
 
 def workload(args):
-    return dict(
-        workload="batch=%d/GPU x 3N=%d synthetic indefinite-quadratic PES (SURVEY 8d), Cartesian, order=1, "
-                 "%s + %s restricted step, TS-BFGS, jd0 Davidson gamma=0.1 maxiter=%d, diag_every_n=%d"
-                 % (args.batch, args.n, args.method, args.rs, args.kdiag, args.diag_every),
-        batch_per_gpu=args.batch, dof=args.n, rs=args.rs, method=args.method, davidson_maxiter=args.kdiag,
-        diag_every_n=args.diag_every, eta=1e-4, gamma=0.1,
-        l2_policy="working set %.1f GB per GPU >> 126 MB L2 (no flush needed)"
-                  % (args.batch * args.n * args.n * 8 * 4 / 1e9))
+    common = dict(batch_per_gpu=args.batch, dof=args.n, rs=args.rs, method=args.method, davidson_maxiter=args.kdiag,
+                  diag_every_n=args.diag_every, eta=1e-4, gamma=0.1)
+    tail = ("Cartesian, order=1, %s + %s restricted step, TS-BFGS, jd0 Davidson gamma=0.1 maxiter=%d, diag_every_n=%d"
+            % (args.method, args.rs, args.kdiag, args.diag_every))
+    if args.workload == "quadratic":
+        return dict(workload="batch=%d/GPU x 3N=%d synthetic indefinite-quadratic PES (SURVEY 8d), %s"
+                             % (args.batch, args.n, tail),
+                    l2_policy="working set %.1f GB per GPU >> 126 MB L2 (no flush needed)"
+                              % (args.batch * args.n * args.n * 8 * 4 / 1e9), **common)
+    what = ("%d-atom Cu(111) slabs (rattled 0.05 A), bottom half held by fix_translation (%d linear constraints)"
+            % (args.n // 3, args.n // 2)) if args.workload == "emt-slab" else \
+           ("%d-atom Cu clusters (fcc ball + 0.05 A rattle), centre of mass held (3 linear constraints)" % (args.n // 3))
+    return dict(workload="batch=%d/GPU x 3N=%d EMT-form surface on the device, %s, %s" % (args.batch, args.n, what, tail),
+                l2_policy="working set %.1f GB per GPU >> 126 MB L2 (no flush needed)"
+                          % (args.batch * args.n * args.n * 8 * 4 / 1e9), **common)
 
 
 # ----------------------------------------------------------------------------- CPU reference
 def _cpu_worker(job):
     """Runs `nsys` oracle searches for `steps` steps with 1 BLAS thread; returns
     (steps done, seconds in the timed part)."""
-    first, nsys, n, rs, kdiag, diag_every, warm, steps, threads, method = job
+    first, nsys, n, rs, kdiag, diag_every, warm, steps, threads, method, wl = job
     os.environ["OMP_NUM_THREADS"] = str(threads)
     os.environ["OPENBLAS_NUM_THREADS"] = str(threads)
     os.environ["MKL_NUM_THREADS"] = str(threads)
@@ -85,9 +128,16 @@ def _cpu_worker(job):
     from oracle.driver import SaddleSearch
     from sella_b200.synthetic import quadratic_system, quadratic_func
     runs = []
+    if wl != "quadratic":
+        from oracle.emt import emt_func
+        ns = argparse.Namespace(workload=wl, n=n)
+        X0, C, cell, pbc = emt_problem(ns, first, nsys)
     for i in range(nsys):
-        A, xs, x0 = quadratic_system(first + i, n)
-        p = CartesianPES(quadratic_func(A, xs), x0)
+        if wl == "quadratic":
+            A, xs, x0 = quadratic_system(first + i, n)
+            p = CartesianPES(quadratic_func(A, xs), x0)
+        else:
+            p = CartesianPES(emt_func(cell, pbc), X0[i], C, C @ X0[i])
         o = SaddleSearch(p, method=method, rs=rs, diag_maxiter=kdiag, diag_every_n=diag_every)
         runs.append(o)
     done = 0
@@ -120,7 +170,8 @@ def cpu_reference(args, warm, steps, budget_s=25.0):
     cores = os.cpu_count() or 1
     # calibrate: one system, all threads
     t0 = time.perf_counter()
-    done, dt = _cpu_worker((0, 1, args.n, args.rs, args.kdiag, args.diag_every, warm, steps, cores, args.method))
+    done, dt = _cpu_worker((0, 1, args.n, args.rs, args.kdiag, args.diag_every, warm, steps, cores, args.method,
+                            args.workload))
     wall1 = time.perf_counter() - t0
     rate_mt = done / dt
     per_sys_wall = wall1
@@ -133,7 +184,7 @@ def cpu_reference(args, warm, steps, budget_s=25.0):
     if args.cpu_systems:
         per_proc = max(1, args.cpu_systems // nproc)
     jobs = [(100 + i * per_proc, per_proc, args.n, args.rs, args.kdiag, args.diag_every, warm, steps, 1,
-             args.method) for i in range(nproc)]
+             args.method, args.workload) for i in range(nproc)]
     t0 = time.perf_counter()
     with ctx.Pool(nproc) as pool:
         res = pool.map(_cpu_worker, jobs)
@@ -234,12 +285,20 @@ def run_ours(args):
     lib.sb_launch_count.restype = __import__("ctypes").c_longlong
 
     b, n = args.batch, args.n
-    A, xs, x0 = quadratic_batch_torch(b, n, dev, seed=1000 + rank)
-    surf = QuadraticSurface(A, xs)
+    cons = None
+    if args.workload == "quadratic":
+        A, xs, x0 = quadratic_batch_torch(b, n, dev, seed=1000 + rank)
+        surf = QuadraticSurface(A, xs)
+    else:
+        from sella_b200.emt import EMTSurface
+        X0, C, cell, pbc = emt_problem(args, 1000 + rank * b, b)
+        x0 = torch.from_numpy(X0).to(dev)
+        surf = EMTSurface(b, n // 3, dev, cell=cell, pbc=pbc)
+        cons = (C, None)
 
     def make():
         return BatchedSella(surf, x0, method=args.method, rs=args.rs, diag_maxiter=args.kdiag,
-                            diag_every_n=args.diag_every, kcap=max(8, args.kdiag + 1))
+                            diag_every_n=args.diag_every, kcap=max(8, args.kdiag + 1), constraints=cons)
 
     def barrier():
         torch.cuda.synchronize()

@@ -263,13 +263,49 @@ cluster_qr_kernel(const double* __restrict__ evals_, double* __restrict__ Z_, in
     dmax = 0.0;
     for (int w = 0; w < nw; ++w) dmax = fmax(dmax, scratch[w]);
     const double tolc = 8.0 * SEC_EPS * dmax;
-    // longest window [lo, i] of the ascending spectrum with d[i] - d[lo] <= tolc
+    // Window [lo, i] of the ascending spectrum with d[i] - d[lo] <= tolc that holds the most rows
+    // on which some pending z is non-negligible (a cluster the update does not touch -- e.g. the
+    // constraint block of a projected Hessian -- needs no reflection however large it is).
+    double* Zb = Z_ + (size_t)b * zcap * n;
+    for (int t = warp; t < T; t += nw) {                    // tolz_t = 8 eps |z_t|
+        double acc = 0.0;
+        for (int e = lane; e < n; e += 32) { const double v = Zb[(size_t)t * n + e]; acc = fma(v, v, acc); }
+        acc = sb_warp_sum(acc);
+        if (lane == 0) dots[t] = 8.0 * SEC_EPS * sqrt(acc);
+    }
+    __syncthreads();
+    int* pre = reinterpret_cast<int*>(ibuf + 16);           // n + 1 ints: prefix counts of "live" rows
+    {
+        const int per = (n + nt - 1) / nt;
+        const int i0 = tid * per, i1 = min(n, i0 + per);
+        int cnt = 0;
+        for (int i = i0; i < i1; ++i) {
+            bool live = false;
+            for (int t = 0; t < T; ++t) live = live || fabs(Zb[(size_t)t * n + i]) > dots[t];
+            pre[i + 1] = live ? 1 : 0;
+            cnt += live ? 1 : 0;
+        }
+        // exclusive scan of the per-thread counts
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) ibuf[warp] = incl;
+        __syncthreads();
+        int base = 0;
+        for (int w = 0; w < warp; ++w) base += ibuf[w];
+        int run = base + incl - cnt;
+        if (tid == 0) pre[0] = 0;
+        for (int i = i0; i < i1; ++i) { run += pre[i + 1]; pre[i + 1] = run; }
+        __syncthreads();
+    }
     int best = 0;
     for (int i = tid; i < n; i += nt) {
         int a = 0, e = i;                                   // smallest j in [0, i] with d[i] - d[j] <= tolc
         const double di = d[i];
         while (a < e) { const int mid = (a + e) >> 1; if (di - d[mid] <= tolc) e = mid; else a = mid + 1; }
-        const int key = ((i - a + 1) << 12) | i;            // n <= 4095
+        const int live = pre[i + 1] - pre[a];
+        // key: live rows first, then window length; the window start is recovered below
+        const int key = (live << 12) | i;                   // n <= 4095
         best = max(best, key);
     }
 #pragma unroll
@@ -279,7 +315,16 @@ cluster_qr_kernel(const double* __restrict__ evals_, double* __restrict__ Z_, in
     __syncthreads();
     best = 0;
     for (int w = 0; w < nw; ++w) best = max(best, ibuf[w]);
-    const int m = best >> 12, iend = best & 4095, c0 = iend - m + 1;
+    const int iend = best & 4095, nlive = best >> 12;
+    int c0;
+    {
+        int a = 0, e = iend;
+        const double di = d[iend];
+        while (a < e) { const int mid = (a + e) >> 1; if (di - d[mid] <= tolc) e = mid; else a = mid + 1; }
+        c0 = a;
+    }
+    const int m = iend - c0 + 1;
+    if (nlive < T + 2) { if (tid == 0) { meta[0] = 0; meta[1] = 0; meta[2] = 0; } return; }
     if (m < T + 2 || m < 8) { if (tid == 0) { meta[0] = 0; meta[1] = 0; meta[2] = 0; } return; }
     double* Z = Z_ + (size_t)b * zcap * n;
     double* W = work_ + (size_t)b * n * n;                  // [T][m]
@@ -1009,7 +1054,8 @@ extern "C" int sb_secular_update_impl(double* evals, double* Vt, double* Z, int 
     if (sec_timing_on) cudaEventRecord(sec_ev[0], st);
     if (n >= 32 && n < 4096 && !getenv("SB_NO_CLUSTER_QR")) {
         // pre-phase: one block reflector for the degenerate cluster (all terms at once)
-        const size_t qsm = ((size_t)n + SB_SCRATCH_DOUBLES + 2 * CQ_TMAX * CQ_TMAX + 2 * CQ_TMAX) * sizeof(double) + 64;
+        const size_t qsm = ((size_t)n + SB_SCRATCH_DOUBLES + 2 * CQ_TMAX * CQ_TMAX + 2 * CQ_TMAX) * sizeof(double) + 64 +
+                           ((size_t)n + 20) * sizeof(int);
         cudaFuncSetAttribute(cluster_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsm);
         SB_COUNT(1);
         cluster_qr_kernel<<<batch, SEC_THREADS, qsm, st>>>(evals, Z, zcap, nterm, n, work, qwork, skip);
