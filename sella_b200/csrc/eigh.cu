@@ -370,12 +370,12 @@ extern "C" int sb_eigh_impl(const double* A, double* evals, double* Vt, double* 
         if (threads < 32) threads = 32;
         const size_t smem = (size_t)4 * n * sizeof(double);
         switch (cpt) {
-            case 1: SB_COUNT(1); ql_kernel<1><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
-            case 2: SB_COUNT(1); ql_kernel<2><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
-            case 3: SB_COUNT(1); ql_kernel<3><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
-            case 4: SB_COUNT(1); ql_kernel<4><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
-            case 5: case 6: SB_COUNT(1); ql_kernel<6><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
-            case 7: case 8: SB_COUNT(1); ql_kernel<8><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
+            case 1: SB_COUNT(1); cudaFuncSetAttribute(ql_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); ql_kernel<1><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
+            case 2: SB_COUNT(1); cudaFuncSetAttribute(ql_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); ql_kernel<2><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
+            case 3: SB_COUNT(1); cudaFuncSetAttribute(ql_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); ql_kernel<3><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
+            case 4: SB_COUNT(1); cudaFuncSetAttribute(ql_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); ql_kernel<4><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
+            case 5: case 6: SB_COUNT(1); cudaFuncSetAttribute(ql_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); ql_kernel<6><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
+            case 7: case 8: SB_COUNT(1); cudaFuncSetAttribute(ql_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); ql_kernel<8><<<batch, threads, smem, st>>>(d, e, Vt, status, active, n); break;
             default: return -2;  // n > 2048 not supported by this build
         }
     }

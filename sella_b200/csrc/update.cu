@@ -340,7 +340,7 @@ constexpr int ROWS_PER_CTA = 32;
 __global__ void __launch_bounds__(UP_THREADS)
 update_apply_kernel(double* __restrict__ B_, const double* __restrict__ U_, const double* __restrict__ J_,
                     const double* __restrict__ W_, int kcap, const int* __restrict__ kvec, int n,
-                    const int* __restrict__ skip) {
+                    const int* __restrict__ skip, int kcs) {
     const int b = blockIdx.y;
     if (skip[b]) return;
     extern __shared__ double sm[];
@@ -353,11 +353,11 @@ update_apply_kernel(double* __restrict__ B_, const double* __restrict__ U_, cons
     const int r0 = blockIdx.x * ROWS_PER_CTA;
     const int r1 = min(n, r0 + ROWS_PER_CTA);
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int a0 = 0; a0 < k; a0 += KC) {
-        const int kc = min(KC, k - a0);
-        double* cu = sm;                       // [kc][n]
-        double* cj = cu + (size_t)KC * n;
-        double* cw = cj + (size_t)KC * n;
+    for (int a0 = 0; a0 < k; a0 += kcs) {
+        const int kc = min(kcs, k - a0);
+        double* cu = sm;                       // [kc][n]; kcs = staged pairs per pass (1 when every system has k = 1)
+        double* cj = cu + (size_t)kcs * n;
+        double* cw = cj + (size_t)kcs * n;
         __syncthreads();
         for (int i = tid; i < kc * n; i += nt) {
             cu[i] = U[(size_t)a0 * n + i];
@@ -454,10 +454,11 @@ extern "C" int sb_update_mid_impl(const double* S, const double* Ytil, const dou
 
 extern "C" int sb_update_apply_impl(double* B, const double* U, const double* J, const double* W, int kcap,
                                     const int* kvec, int n, const int* skip, int batch, cudaStream_t st) {
-    const size_t smem = (size_t)3 * KC * n * sizeof(double);
+    const int kcs = kvec ? (kcap < KC ? kcap : KC) : 1;
+    const size_t smem = (size_t)3 * kcs * n * sizeof(double);
     cudaFuncSetAttribute(update_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((n + ROWS_PER_CTA - 1) / ROWS_PER_CTA, batch);
     SB_COUNT(1);
-    update_apply_kernel<<<grid, UP_THREADS, smem, st>>>(B, U, J, W, kcap, kvec, n, skip);
+    update_apply_kernel<<<grid, UP_THREADS, smem, st>>>(B, U, J, W, kcap, kvec, n, skip, kcs);
     return SB_LAUNCH_CHECK();
 }

@@ -137,3 +137,49 @@ def test_eigh_update_secular(n, k):
             Vi = V[i].T
             np.testing.assert_allclose(Vi.T @ Vi, np.eye(n), atol=2e-12, err_msg="orth rep %d sys %d" % (rep, i))
             np.testing.assert_allclose(B[i] @ Vi, Vi * w[i][None, :], atol=5e-12 * scale)
+
+
+@pytest.mark.parametrize("n", [768, 1536])
+def test_eigh_large_sizes(n):
+    """BASELINE configs C4/C5 (3N = 768, 1536): eigenpairs through size-independent properties."""
+    from sella_b200 import kernels as K
+    rng = np.random.RandomState(n)
+    A = rng.normal(size=(2, n, n)); A = A + A.transpose(0, 2, 1)
+    w, Vt, st = K.eigh(torch.from_numpy(A).cuda())
+    assert int(st.sum()) == 0
+    w, Vt = w.cpu().numpy(), Vt.cpu().numpy()
+    for i in range(2):
+        scale = np.abs(w[i]).max()
+        assert (np.diff(w[i]) >= 0).all()
+        np.testing.assert_allclose(Vt[i] @ Vt[i].T, np.eye(n), atol=5e-13)
+        np.testing.assert_allclose(A[i] @ Vt[i].T, Vt[i].T * w[i][None, :], atol=5e-12 * scale)
+        np.testing.assert_allclose(w[i].sum(), np.trace(A[i]), rtol=0, atol=1e-11 * scale * n ** 0.5)
+
+
+@pytest.mark.parametrize("n", [768, 1536])
+def test_engine_large_sizes_match_oracle(n):
+    """C4/C5 sizes: a few steps of two searches against the oracle, and the carried eigenpairs
+    against the stored Hessian."""
+    from oracle.pes import CartesianPES
+    from oracle.driver import SaddleSearch
+    from sella_b200.batched import BatchedSella, QuadraticSurface
+    from sella_b200.synthetic import quadratic_system, quadratic_func
+    data = [quadratic_system(b, n) for b in (0, 1)]
+    dev = torch.device("cuda:0")
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    eng = BatchedSella(QuadraticSurface(up(np.stack([d[0] for d in data])), up(np.stack([d[1] for d in data]))),
+                       up(np.stack([d[2] for d in data])), method="prfo", rs="tr", diag_maxiter=5, diag_every_n=3, kcap=8)
+    orc = []
+    for (A, xs, x0) in data:
+        p = CartesianPES(quadratic_func(A, xs), x0)
+        orc.append((p, SaddleSearch(p, method="prfo", rs="tr", diag_maxiter=5, diag_every_n=3)))
+    for t in range(4):
+        eng.step()
+        x = eng.x.cpu().numpy()
+        for i, (p, o) in enumerate(orc):
+            o.step()
+            np.testing.assert_allclose(x[i], p.get_x(), rtol=0, atol=1e-8)
+    eng.check_status()
+    B, w, Vt = eng.B.cpu().numpy(), eng.evals.cpu().numpy(), eng.Vt.cpu().numpy()
+    for i in range(2):
+        np.testing.assert_allclose(B[i] @ Vt[i].T, Vt[i].T * w[i][None, :], atol=1e-10)
