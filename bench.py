@@ -23,7 +23,6 @@ summed over all GPUs (weak scaling: per-GPU batch fixed).  Prints ONE JSON line.
 import argparse
 import json
 import os
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")   # no lazy kernel loading inside a timed region
 import subprocess
 import sys
 import time

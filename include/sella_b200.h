@@ -250,6 +250,23 @@ int sb_internals_hess(const int32_t* trans, int nt, const int32_t* bonds, int nb
                       const double* td, const double* x, int n, const double* v, double* D,
                       const double* w, double* R, const int32_t* active, int batch, void* stream);
 
+/* ---- dense algebra of the internal-coordinate path (sella/peswrapper.py:674-736, 1011-1082,
+ * 1124-1127, 1176-1183; sella/_gpu.py:100-132).  Row-major matrices with explicit leading
+ * dimensions; batch strides in doubles (0 = one matrix shared by the batch).
+ *   sb_gemm : C = alpha op(A) op(B) + beta C, op(A) M x K, op(B) K x N (transX != 0: X is stored
+ *             transposed); fp64 tensor-core (DMMA) tiles.  Serves gpu_project (U^T H U), g_int =
+ *             B+^T g_cart, Binv = R^-1 Q^T, Hc = B+^T (D_c - D_q) B+, get_df_pred.
+ *   sb_qr   : economy Householder QR of A [b, m, n] (m >= n; A is overwritten with the reflectors),
+ *             Q [b, m, n] with orthonormal columns, R [b, n, n] upper triangular (LAPACK signs):
+ *             gpu_qr (_gpu.py:100-111), _get_jacobian_qr (peswrapper.py:674-709).
+ *   sb_trtri: Rinv [b, n, n] = R^-1 (upper triangular); SB_ST_SINGULAR on a zero diagonal.      */
+int sb_gemm(int transA, int transB, int M, int N, int K, double alpha, const double* A, int lda,
+            long long strideA, const double* B, int ldb, long long strideB, double beta, double* C,
+            int ldc, long long strideC, const int32_t* active, int batch, void* stream);
+int sb_qr(double* A, int m, int n, double* Q, double* R, const int32_t* active, int batch, void* stream);
+int sb_trtri(const double* R, double* Rinv, int n, int32_t* status, const int32_t* active, int batch,
+             void* stream);
+
 /* ---- per-step bookkeeping (sella/peswrapper.py:578-602, optimize/optimize.py:362-434) ----
  * dpar = {rho_inc, rho_dec, sigma_inc, sigma_dec, delta_min} (host array of 5 doubles),
  * ipar = {order, eig, nsteps_per_diag, diag_every_n(<0: never)} (host array of 4 ints). */

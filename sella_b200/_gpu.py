@@ -1,5 +1,5 @@
 """CUDA mirror of the reference's device seam sella/_gpu.py (gpu_eigh :70-84,
-gpu_eigh_t :87-97, gpu_project :114-132, to_gpu :55-67): same names and return
+gpu_eigh_t :87-97, gpu_qr :100-111, gpu_project :114-132, to_gpu :55-67): same names and return
 conventions, backed by the hand-written kernels instead of torch.linalg.
 
 There is deliberately no CPU fallback and no size threshold: the reference's
@@ -28,16 +28,15 @@ def gpu_eigh(A, A_gpu=None):
     return w.cpu().numpy(), V.cpu().numpy()
 
 
+def gpu_qr(A):
+    """Economy QR (sella/_gpu.py:100-111): (Q, R) as numpy arrays, LAPACK sign convention."""
+    Q, R = K.qr(up(np.asarray(A, dtype=np.float64)).unsqueeze(0).contiguous())
+    return Q[0].cpu().numpy(), R[0].cpu().numpy()
+
+
 def gpu_project(H, U, H_gpu=None):
-    """U.T @ H @ U (sella/_gpu.py:114-132) through the batched H.V kernel."""
+    """U.T @ H @ U (sella/_gpu.py:114-132): two fp64 tensor-core GEMMs."""
     Hd = (H_gpu if H_gpu is not None else up(H)).unsqueeze(0).contiguous()
-    U = np.asarray(U, dtype=np.float64)
-    n, m = U.shape
-    Ut = up(U.T).unsqueeze(0).contiguous()            # [1, m, n] vector-major
-    HU = torch.empty_like(Ut)
-    done = 0
-    while done < m:                                    # sb_hv handles any nvec in chunks
-        c = min(32, m - done)
-        HU[:, done:done + c] = K.hv(Hd, Ut[:, done:done + c].contiguous())
-        done += c
-    return (Ut[0] @ HU[0].T).cpu().numpy()            # small (m x m) Gram product
+    Ud = up(np.asarray(U, dtype=np.float64)).unsqueeze(0).contiguous()      # [1, n, m]
+    HU = K.gemm(Hd, Ud)                                                       # [1, n, m]
+    return K.gemm(Ud, HU, transA=True)[0].cpu().numpy()

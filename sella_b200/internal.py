@@ -76,3 +76,66 @@ class BatchedInternals:
         call("sb_internals_hess", *self._topo(), _p(x), I(self.n), _p(None), _p(None), _p(w), _p(R), _p(active),
              I(b), _stream())
         return R
+
+
+class WilsonAlgebra:
+    """The linear algebra InternalPES builds on the Wilson matrix Bm [b, nint, ncart]
+    (sella/peswrapper.py:674-736, 1011-1082, 1124-1127, 1176-1183), batched on the device:
+
+        Q, R            economy QR, Unred = Q                       _get_jacobian_qr  :674-709
+        Binv            R^-1 Q^T  [b, ncart, nint]                  _get_Binv         :711-736
+        gradient(g)     g_cart @ Binv                               eval              :1124-1127
+        drdx(J)         J R^-1 (reduced) and J R^-1 Q^T (internal)  _compute_basis_int:1050-1082
+        Hc(Dc, Dq)      Binv^T (D_cons - D_int) Binv                _compute_Hc_int   :1011-1031
+        reduce(H)       Q^T H Q  and  df_pred                       get_df_pred       :1176-1183
+        H0(h0)          P diag(h0) P,  P = Q Q^T                    _range_space_projector :72-82
+
+    A rank-deficient Jacobian (|R_ii| < 1e-6 max|R_ii|; the reference then switches to an SVD,
+    :691-704) is reported through ``rank_deficient`` and not handled on the device."""
+
+    def __init__(self, Bm):
+        from . import kernels as K
+        check_f64(Bm)
+        self.b, self.nint, self.ncart = Bm.shape
+        if self.nint < self.ncart:
+            raise ValueError("the Wilson matrix needs nint >= ncart")
+        self.Q, self.R = K.qr(Bm)
+        rd = torch.diagonal(self.R, dim1=1, dim2=2).abs()
+        self.rank_deficient = rd.min(dim=1).values < 1e-6 * rd.max(dim=1).values
+        self.Rinv, self.status = K.trtri(self.R)
+        self.Binv = K.gemm(self.Rinv, self.Q, transB=True)
+
+    def gradient(self, g_cart):
+        from . import kernels as K
+        return K.gemm(g_cart.view(self.b, 1, self.ncart).contiguous(), self.Binv).view(self.b, self.nint)
+
+    def drdx(self, J):
+        """J: constraint Jacobian wrt Cartesians, [b, nc, ncart] or [nc, ncart] shared."""
+        from . import kernels as K
+        red = K.gemm(J, self.Rinv)                              # [b, nc, ncart]: in the basis Q
+        return red, K.gemm(red, self.Q, transB=True)            # [b, nc, nint]
+
+    def Hc(self, D_cons, D_int):
+        from . import kernels as K
+        T = K.gemm((D_cons - D_int).contiguous(), self.Binv)    # [b, ncart, nint]
+        return K.gemm(self.Binv, T, transA=True)                # [b, nint, nint]
+
+    def reduce(self, H):
+        from . import kernels as K
+        return K.gemm(self.Q, K.gemm(H, self.Q), transA=True)   # [b, ncart, ncart]
+
+    def df_pred(self, dx, g, H):
+        from . import kernels as K
+        dxr = K.gemm(dx.view(self.b, 1, self.nint).contiguous(), self.Q)          # [b, 1, ncart]
+        gr = K.gemm(g.view(self.b, 1, self.nint).contiguous(), self.Q)
+        Hr = self.reduce(H)
+        Hd = K.gemm(dxr, Hr)
+        return (gr * dxr).sum(dim=(1, 2)) + 0.5 * (Hd * dxr).sum(dim=(1, 2))
+
+    def H0(self, h0):
+        """h0 [nint] or [b, nint]: diagonal guess projected onto range(Bm)."""
+        from . import kernels as K
+        h = h0 if h0.dim() == 2 else h0.unsqueeze(0).expand(self.b, self.nint)
+        DQ = (h.unsqueeze(2) * self.Q).contiguous()                               # diag(h0) Q
+        core = K.gemm(self.Q, DQ, transA=True)                                    # Q^T diag(h0) Q
+        return K.gemm(self.Q, K.gemm(core, self.Q, transB=True))                  # Q core Q^T

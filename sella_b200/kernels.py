@@ -128,3 +128,50 @@ def eigh_update(evals, Vt, U, J, C, active=None):
     call("sb_secular_update", _p(evals), _p(Vt), _p(Z), I(2 * k), _p(sig), _p(nterm), I(n), _p(work),
          _p(qwork), _p(status), _p(skip), I(b), _stream())
     return evals, Vt, status
+
+
+# --------------------------------------------------------------------------
+# dense algebra of the internal-coordinate path (csrc/dense.cu)
+# --------------------------------------------------------------------------
+def gemm(A, B, transA=False, transB=False, alpha=1.0, beta=0.0, out=None, active=None):
+    """C[b] = alpha op(A[b]) op(B[b]) + beta C[b] on fp64 tensor-core tiles.  A, B: [b, r, c]
+    row-major (a 2-D operand is shared by the batch)."""
+    require_cuda()
+    check_f64(A, B)
+    sA = 0 if A.dim() == 2 else A.shape[-2] * A.shape[-1]
+    sB = 0 if B.dim() == 2 else B.shape[-2] * B.shape[-1]
+    batch = A.shape[0] if A.dim() == 3 else (B.shape[0] if B.dim() == 3 else 1)
+    M, K = (A.shape[-1], A.shape[-2]) if transA else (A.shape[-2], A.shape[-1])
+    K2, N = (B.shape[-1], B.shape[-2]) if transB else (B.shape[-2], B.shape[-1])
+    if K != K2:
+        raise ValueError("gemm: inner dimensions differ (%d, %d)" % (K, K2))
+    if out is None:
+        out = torch.empty((batch, M, N), dtype=torch.float64, device=A.device)
+        beta = 0.0
+    check_f64(out)
+    call("sb_gemm", I(int(transA)), I(int(transB)), I(M), I(N), I(K), D(float(alpha)), _p(A), I(A.shape[-1]), LL(sA),
+         _p(B), I(B.shape[-1]), LL(sB), D(float(beta)), _p(out), I(N), LL(M * N), _p(_mask(active)), I(batch), _stream())
+    return out
+
+
+def qr(A, active=None):
+    """Economy QR of A [b, m, n], m >= n: Q [b, m, n], R [b, n, n] (LAPACK sign convention)."""
+    require_cuda()
+    check_f64(A)
+    b, m, n = A.shape
+    work = A.clone()
+    Q = torch.empty((b, m, n), dtype=torch.float64, device=A.device)
+    R = torch.empty((b, n, n), dtype=torch.float64, device=A.device)
+    call("sb_qr", _p(work), I(m), I(n), _p(Q), _p(R), _p(_mask(active)), I(b), _stream())
+    return Q, R
+
+
+def trtri(R, active=None, status=None):
+    """Inverse of the upper-triangular R [b, n, n]."""
+    require_cuda()
+    check_f64(R)
+    b, n, _ = R.shape
+    X = torch.empty_like(R)
+    status = torch.zeros(b, dtype=torch.int32, device=R.device) if status is None else status
+    call("sb_trtri", _p(R), _p(X), I(n), _p(status), _p(_mask(active)), I(b), _stream())
+    return X, status
