@@ -129,8 +129,10 @@ int sb_hvp_finish(const double* vfull, long long vstride, const double* gplus, c
                   void* stream);
 /* vstride: distance in doubles between the direction vectors of consecutive systems. */
 /* PES.diag tail, sella/peswrapper.py:541-551: Ritz rotation of the history (in place). */
+/* HcVs (may be NULL): [b,kcap,n] = Hc @ Vs, the constraint-Hessian term of :546 (Atilde -= Vs^T Hc Vs). */
 int sb_history_ritz(double* Vs, double* AVs, int kcap, const int32_t* nhist, int n,
-                    int32_t* nvec_out, const int32_t* dav_state, int32_t* status, int batch, void* stream);
+                    int32_t* nvec_out, const int32_t* dav_state, int32_t* status, const double* HcVs,
+                    int batch, void* stream);
 
 /* ---- quasi-Newton update (sella/hessian_update.py:40-152, sella/linalg.py:274-304) ----
  * sb_update_prep: Ytil = symmetrize_Y(S, Y, symm) with symm in {0,1,2} (:27-37), the
@@ -212,6 +214,12 @@ int sb_qn_ras(const double* Vg, const double* evals, const double* Vt, const dou
  *   sb_scons_measure / sb_combine_step : size of the constraint-restoring step, the
  *     "violation alone exceeds the radius" branch (NaiveStepper), s_tot = s_free + scons
  *   sb_converged_cons : fmax over atoms of the projected gradient, cmax = |res|.        */
+/* Position-dependent constraints (peswrapper.py:395-407, 429-438, 467-481): Uc [b,nc,n] = the
+ * orthonormalised rows of the constraint Jacobian drdx (sb_mgs), G [b,nc,nc] = drdx Uc^T (sb_gemm).
+ *   Mr [b,nc,n] = G^-T Uc          (scons = -sum_j res_j Mr[j,:], as for linear constraints)
+ *   L  [b,nc]   = G^-T u, u = Uc g (Lagrange multipliers, lstsq(drdx^T, g); u/L may be NULL)    */
+int sb_cons_solve(const double* G, const double* Uc, const double* u, int nc, int n, double* Mr,
+                  double* L, int32_t* status, const int32_t* active, int batch, void* stream);
 int sb_rect_dots(const double* R, long long rstride, int nr, const double* x, long long xstride,
                  const double* c, double* out, int n, const int32_t* active, int batch, void* stream);
 int sb_rect_comb(const double* R, long long rstride, int nr, const double* coef, double scale,

@@ -360,3 +360,48 @@ class CartesianPES:
         if diag:
             self.diag(**diag_kwargs)
         return ratio
+
+
+class NonlinearPES(CartesianPES):
+    """Cartesian PES with position-dependent constraints: internal coordinates (bonds, angles,
+    dihedrals, single-atom translations; oracle/internals.py) held at target values, optionally
+    next to linear rows.  Follows the reference's generic PES: get_drdx / get_res evaluated at the
+    current geometry (peswrapper.py:388-393), basis per geometry (:395-407), multipliers
+    L = lstsq(drdx^T, g) (:467-481) and Hc = sum_i L_i d2r_i/dx2 (:343-352)."""
+
+    def __init__(self, func, x0, coords, targets=None, C=None, c=None, **kw):
+        CartesianPES.__init__(self, func, x0, C, c, **kw)
+        self.coords = {k: [tuple(int(a) for a in t) for t in coords.get(k, ())]
+                       for k in ("translations", "bonds", "angles", "dihedrals")}
+        self.ndih = len(self.coords["dihedrals"])
+        q0 = self._q(self.x)[0]
+        self.targets = q0.copy() if targets is None else np.asarray(targets, float)
+
+    def _q(self, x, hess=False):
+        from . import internals as oi
+        c = self.coords
+        q, B, H = oi.evaluate(x.reshape(-1, 3), c["translations"], c["bonds"], c["angles"], c["dihedrals"])
+        return q, B, H
+
+    def get_drdx(self):
+        return np.vstack([self.C, self._q(self.x)[1]])
+
+    def get_res(self):
+        r = self._q(self.x)[0] - self.targets
+        if self.ndih:
+            r[-self.ndih:] = (r[-self.ndih:] + np.pi) % (2 * np.pi) - np.pi
+        return np.concatenate([self.C @ self.x - self.c, r])
+
+    def _calc_basis(self):
+        drdx = self.get_drdx()
+        Ucons, Ufree = split_constraints(drdx)
+        return drdx, Ucons, np.eye(self.dim), Ufree
+
+    def get_Hc(self):
+        L = self.curr["L"]
+        H = self._q(self.x)[2]
+        nlin = self.C.shape[0]
+        out = np.zeros((self.dim, self.dim))
+        for Li, Hi in zip(L[nlin:], H):
+            out += Li * Hi
+        return out

@@ -183,6 +183,8 @@ class BatchedSella:
             return
         from scipy.linalg import qr
         b, n, dev = self.batch, self.n, self.dev
+        if len(constraints) == 4:
+            return self._setup_nonlinear_constraints(*constraints)
         C, c = constraints
         C = np.asarray(C, dtype=np.float64)
         shared = C.ndim == 2
@@ -230,6 +232,103 @@ class BatchedSella:
         self.evalsB = torch.zeros(b, n, **f64)
         self.VtB = torch.zeros(b, n, n, **f64)
 
+    def _setup_nonlinear_constraints(self, C_lin, c_lin, internals, targets):
+        """Position-dependent constraints (peswrapper.py:395-407, 429-438, 467-481): the internal
+        coordinates of `internals` (a BatchedInternals: bonds, angles, dihedrals, single-atom
+        translations) held at `targets` [b, nnl] (None: their values at x0), optionally together with
+        linear rows C_lin x = c_lin.  The constraint basis, the multipliers, the constraint Hessian
+        Hc = sum_i L_i d2q_i/dx2 and the spectrum of the projected Lagrangian Hessian are rebuilt
+        at every geometry (`_refresh_constraints`), as the reference does."""
+        b, n, dev = self.batch, self.n, self.dev
+        f64 = dict(dtype=torch.float64, device=dev)
+        nlin = 0 if C_lin is None else int(np.asarray(C_lin).shape[-2])
+        nnl = internals.nint
+        nc = nlin + nnl
+        if nc == 0:
+            return
+        if nc > 32:
+            raise NotImplementedError("at most 32 constraints when some are position dependent")
+        cons = dict(shared=False, nc=nc, rank=nc, nfree=n - nc, cstride=nc * n, ustride=nc * n,
+                    C=torch.zeros(b, nc, n, **f64), Uc=torch.zeros(b, nc, n, **f64), Mr=torch.zeros(b, nc, n, **f64),
+                    c=torch.zeros(b, nc, **f64), res=torch.zeros(b, nc, **f64), uw=torch.zeros(b, nc, **f64))
+        if nlin:
+            Cl = np.asarray(C_lin, dtype=np.float64)
+            Cl = np.array(np.broadcast_to(Cl if Cl.ndim == 3 else Cl[None], (b, nlin, n)))
+            cons["C"][:, :nlin] = torch.from_numpy(Cl).to(dev)
+            if c_lin is None:
+                cons["c"][:, :nlin] = torch.einsum("bjn,bn->bj", cons["C"][:, :nlin], self.x)
+            else:
+                cons["c"][:, :nlin] = torch.from_numpy(np.ascontiguousarray(np.asarray(c_lin, dtype=np.float64))).to(dev).reshape(b, nlin)
+        q0 = internals.calc(self.x)
+        if targets is None:
+            tgt = q0.clone()
+        else:
+            tgt = torch.from_numpy(np.ascontiguousarray(np.asarray(targets, dtype=np.float64))).to(dev).reshape(b, nnl).clone()
+        for k in ("scons", "gp", "pg", "slift"):
+            cons[k] = torch.zeros(b, n, **f64)
+        for k in ("scons2", "consval", "cmax"):
+            cons[k] = torch.zeros(b, **f64)
+        cons["naive"] = torch.zeros(b, dtype=torch.int32, device=dev)
+        cons["regular"] = torch.ones(b, dtype=torch.int32, device=dev)
+        ndih0 = nnl - internals.ndihedrals
+        cons["nl"] = dict(ints=internals, target=tgt, nlin=nlin, dih0=ndih0, Lmul=torch.zeros(b, nc, **f64),
+                          Hc=torch.zeros(b, n, n, **f64), HL=torch.zeros(b, n, n, **f64), u=torch.zeros(b, nc, **f64),
+                          evalsHL=torch.zeros(b, n, **f64), hcv=torch.zeros(b, 1, n, **f64), hcv2=torch.zeros(b, 1, n, **f64),
+                          HcVs=None, x_basis=None, x_model=None)
+        self.cons = cons
+        self.evalsB = torch.zeros(b, n, **f64)          # B keeps its own (updated) spectrum; (evals, Vt) hold the
+        self.VtB = torch.zeros(b, n, n, **f64)          # projected Lagrangian Hessian, rebuilt per geometry
+        if self.eig_mode != "update":
+            raise NotImplementedError("constraints need eig_mode='update'")
+
+    def _refresh_bases(self):
+        """Constraint Jacobian, residual, Ucons, the scons map and the multipliers at self.x / self.g."""
+        cn = self.cons
+        nl = cn["nl"]
+        b, n, nc, nlin = self.batch, self.n, cn["nc"], nl["nlin"]
+        ints = nl["ints"]
+        q, Bm = ints.calc(self.x, jacobian=True)
+        cn["C"][:, nlin:] = Bm
+        res = q - nl["target"]
+        if ints.ndihedrals:                             # dihedrals live on a circle
+            d = res[:, nl["dih0"]:]
+            res[:, nl["dih0"]:] = torch.remainder(d + np.pi, 2.0 * np.pi) - np.pi
+        # c is chosen so that C x - c is the true residual: the linear-constraint kernels then apply as they are
+        call("sb_rect_dots", _p(cn["C"]), LL(cn["cstride"]), I(nc), _p(self.x), LL(n), _p(None), _p(cn["res"]),
+             I(n), _p(None), I(b), _stream())
+        cn["c"][:, nlin:] = cn["res"][:, nlin:] - res
+        cn["Uc"].copy_(cn["C"])
+        nkept, st = K.mgs(cn["Uc"])                     # rows of drdx, orthonormalised (subspace of peswrapper.py:51-69)
+        self.status |= st
+        self.status |= ((nkept != nc).to(torch.int32) * 16)          # rank-deficient constraint Jacobian
+        G = K.gemm(cn["C"], cn["Uc"], transB=True)      # drdx = G Uc
+        call("sb_rect_dots", _p(cn["Uc"]), LL(cn["ustride"]), I(nc), _p(self.g), LL(n), _p(None), _p(nl["u"]),
+             I(n), _p(None), I(b), _stream())
+        call("sb_cons_solve", _p(G), _p(cn["Uc"]), _p(nl["u"]), I(nc), I(n), _p(cn["Mr"]), _p(nl["Lmul"]),
+             _p(self.status), _p(None), I(b), _stream())
+        nl["x_basis"] = self.x.clone()
+
+    def _refresh_constraints(self):
+        """Everything that depends on the geometry in the position-dependent case: bases, multipliers,
+        Hc (peswrapper.py:343-352) and -- once the Hessian exists -- the spectrum of
+        Bp = P_f (B - Hc) P_f + sigma P_c, which is the model of restricted_step.py:57-62."""
+        cn = self.cons
+        nl = cn["nl"]
+        b, n, nlin = self.batch, self.n, nl["nlin"]
+        self._refresh_bases()
+        nl["Hc"] = nl["ints"].ldot(self.x, nl["Lmul"][:, nlin:].contiguous())
+        if not self.H_initialized:
+            return
+        torch.sub(self.B, nl["Hc"], out=nl["HL"])
+        Pc = K.gemm(cn["Uc"], cn["Uc"], transA=True)                  # Ucons Ucons^T
+        Pf = torch.eye(n, dtype=torch.float64, device=self.dev).expand(b, n, n) - Pc
+        Pf = Pf.contiguous()
+        sigma = 1.0 + 8.0 * torch.maximum(self.evalsB[:, 0].abs(), self.evalsB[:, -1].abs())
+        Bp = K.gemm(Pf, K.gemm(nl["HL"], Pf))
+        Bp = 0.5 * (Bp + Bp.transpose(1, 2)) + sigma[:, None, None] * Pc
+        K.eigh(Bp.contiguous(), evals=self.evals, Vt=self.Vt, ws=self.eig_ws, status=self.status)
+        nl["x_model"] = True
+
     def _identity_model(self):
         b, n = self.batch, self.n
         one = torch.ones(b, dtype=torch.float64, device=self.dev)
@@ -237,6 +336,8 @@ class BatchedSella:
              I(b), _stream())
         if self.cons is not None:
             cn = self.cons
+            if "nl" in cn:
+                raise NotImplementedError("eig=False starts with position-dependent constraints are not batched yet")
             self.Vt.copy_(cn["Q"].expand(b, n, n) if cn["shared"] else cn["Q"])
             self.evals.fill_(1.0)
             self.evals[:, cn["nfree"]:] = 8.0
@@ -284,7 +385,7 @@ class BatchedSella:
         if first:
             call("sb_fill_scaled_identity", _p(self.B), _p(self.evalsB), _p(self.VtB), _p(self.lam0), I(n),
                  I(n), _p(self.skip), I(b), _stream())
-            if self.cons is not None:
+            if self.cons is not None and "nl" not in self.cons:
                 # Bp = lam0 P_f + sigma P_c: eigenvectors = [Ufree; Ucons] rows, sigma > lam0
                 cn = self.cons
                 self.Vt.copy_(cn["Q"].expand(b, n, n) if cn["shared"] else cn["Q"])
@@ -320,7 +421,7 @@ class BatchedSella:
                 "sb_secular_update", _p(self.evalsB), _p(self.VtB), _p(sec["Z"]), I(2 * kc), _p(sec["sig"]),
                 _p(self.nterm), I(n), _p(self.eig_ws.work), _p(self.qwork), _p(self.status), _p(self.skip),
                 I(b), _stream()))
-            if self.cons is not None:
+            if self.cons is not None and "nl" not in self.cons:
                 # same update seen through the projector: Bp+ = Bp + P_f Delta P_f
                 self._project_free(bufs["U"], nv, kc, active)
                 self._project_free(bufs["J"], nv, kc, active)
@@ -357,15 +458,28 @@ class BatchedSella:
             # Uproj^T (H v): the subspace image lives in the free space (linalg.py:92-93); the
             # operator history (Vs, AVs) keeps the unprojected vector, as the reference does
             kmax = int(kslot.max().item())
+            nl = self.cons.get("nl")
+            if nl is not None:
+                # operator of peswrapper.py:537: Hproj - Ufree^T Hc Ufree
+                nl["hcv"].copy_(vec.unsqueeze(1))
+                K.hv_ld(nl["Hc"], nl["hcv"], nl["hcv2"], 1, active=active)
+                if "one" not in nl:
+                    nl["one"] = torch.ones(b, 1, dtype=torch.float64, device=self.dev)
             for k in range(kmax + 1):
                 m = ((kslot == k) & (active > 0)).to(torch.int32) if active is not None else (kslot == k).to(torch.int32)
                 if int(m.sum().item()):
+                    if nl is not None:
+                        call("sb_rect_comb", _p(nl["hcv2"]), LL(n), I(1), _p(nl["one"]), D(-1.0), _p(self.AV[:, k]),
+                             LL(self.kcap * n), D(1.0), _p(self.AV[:, k]), LL(self.kcap * n), I(n), _p(m), I(b), _stream())
                     self._project_free(self.AV[:, k:k + 1], 1, self.kcap, m)
 
     def _diag(self, part=None):
         """PES.diag (peswrapper.py:508-556) for the systems with part[b] != 0."""
         b, n, kc = self.batch, self.n, self.kcap
         first = not self.H_initialized          # P = identity, v0 = g
+        nl = self.cons.get("nl") if self.cons is not None else None
+        if nl is not None:
+            self._refresh_constraints()         # bases, Hc and the preconditioner at the current geometry
         if not first and not self.eig_valid:
             self._eigh(active=part)             # spectrum of the preconditioner P = B
         v0 = self.g
@@ -413,8 +527,14 @@ class BatchedSella:
             m = (self.dav_state == DAV_EXPAND).to(torch.int32)
             self._hvp(self.vnew, n, self.dav_state, DAV_EXPAND, m)
             rounds += 1
+        hcvs = None
+        if nl is not None:
+            if nl["HcVs"] is None:
+                nl["HcVs"] = torch.zeros_like(self.Vs)
+            hcvs = nl["HcVs"]
+            K.hv_ld(nl["Hc"], self.Vs, hcvs, min(rounds, kc), active=part)
         call("sb_history_ritz", _p(self.Vs), _p(self.AVs), I(kc), _p(self.nhist), I(n), _p(self.nvec),
-             _p(self.dav_state), _p(self.status), I(b), _stream())
+             _p(self.dav_state), _p(self.status), _p(hcvs), I(b), _stream())
         self._update(self.Vs, self.AVs, self.upk, self.nvec, min(rounds, kc), part)
         self.ndiag += 1
 
@@ -433,10 +553,13 @@ class BatchedSella:
             # B is None in the reference: the step model is the identity (linalg.py:319-334,
             # stepper.py:76-80) until the first update scales it (hessian_update.py:58-67)
             self._identity_model()
-        if not self.eig_valid:
+        cn = self.cons
+        nl = cn.get("nl") if cn is not None else None
+        if nl is not None:
+            self._refresh_constraints()
+        elif not self.eig_valid:
             self._eigh(active)
             self.eig_valid = True
-        cn = self.cons
         gvec, extra2, sadd, act_rs = self.g, None, None, active
         if cn is not None:
             # scons = -Ucons lstsq(C Ucons, res);  g' = P_f (g + B scons)   (restricted_step.py:28-37)
@@ -488,7 +611,12 @@ class BatchedSella:
             call("sb_combine_step", _p(sdst), _p(cn["scons"]), _p(cn["consval"]), _p(self.delta), _p(cn["naive"]),
                  _p(self.s), _p(self.smag), I(n), _p(active), I(b), _stream())
         # ---- re-diagonalise?  (spectrum of the Hessian itself, before this step's update)
-        call("sb_ev_decide", _p(self.evalsB), I(n), I(1), _p(self.since_diag), _p(self.ev), self._dpar,
+        ev_evals = self.evalsB
+        if nl is not None and self.eig and int((self.since_diag >= int(self._ipar[2])).any().item()):
+            # optimize.py:369-371 looks at the Hessian of the Lagrangian (B - Hc), not at B
+            K.eigh(nl["HL"], evals=nl["evalsHL"], Vt=self.eig_ws.work, status=self.status)
+            ev_evals = nl["evalsHL"]
+        call("sb_ev_decide", _p(ev_evals), I(n), I(1), _p(self.since_diag), _p(self.ev), self._dpar,
              self._ipar, _p(active), I(b), _stream())
         # ---- kick
         call("sb_axpy", _p(self.x), _p(self.s), _p(self.xnew), I(n), _p(active), I(b), _stream())
@@ -509,6 +637,8 @@ class BatchedSella:
         if cn is None:
             call("sb_converged", _p(self.g), I(n), D(float(fmax)), _p(self.fmax), _p(self.conv), I(b), _stream())
             return self.conv
+        if "nl" in cn and (cn["nl"]["x_basis"] is None or not torch.equal(cn["nl"]["x_basis"], self.x)):
+            self._refresh_bases()
         cn["pg"].copy_(self.g)
         self._project_free(cn["pg"].view(b, 1, n), 1, 1)
         call("sb_rect_dots", _p(cn["C"]), LL(cn["cstride"]), I(cn["nc"]), _p(self.x), LL(n), _p(cn["c"]),

@@ -1,5 +1,5 @@
-"""`Constraints(atoms)` with the part of the reference API (sella/internal.py:2748-3030)
-that yields LINEAR constraints, which is what the CUDA path supports:
+"""`Constraints(atoms)` with the reference API (sella/internal.py:2748-3030) for the constraint
+kinds the CUDA path supports:
 
     cons = Constraints(atoms)
     cons.fix_translation(i)              # atom i held fixed (three rows of the identity)
@@ -7,9 +7,14 @@ that yields LINEAR constraints, which is what the CUDA path supports:
     cons.fix_translation()               # mean position of all atoms (Translation = pos[:, dim].mean(),
                                          #   sella/internal.py:466-470)
     cons.fix_translation((i, j, k))      # mean position of a group
+    cons.fix_bond((i, j), target=None)           # Angstrom
+    cons.fix_angle((i, j, k), target=None)       # degrees, as in the reference (:2946)
+    cons.fix_dihedral((i, j, k, l), target=None) # degrees
 
-`fix_rotation`, `fix_bond`, `fix_angle`, `fix_dihedral`, `fix_other` are nonlinear
-(geometry-dependent Jacobian, non-zero constraint Hessian) and raise NotImplementedError.
+Translations are linear (`linear_system`); bonds, angles and dihedrals are position dependent
+(`nonlinear_system`: their Jacobian rows and Hessians come from the internal-coordinate kernels at
+every geometry).  `fix_rotation`, `fix_other`, inequality comparators, `ncvecs`/`mic` periodic
+images are not on the CUDA path and raise NotImplementedError.
 """
 import numpy as np
 
@@ -28,6 +33,7 @@ class Constraints:
         self.natoms = len(atoms)
         self.internals = dict(translations=[], bonds=[], angles=[], dihedrals=[], other=[], rotations=[])
         self._targets = []
+        self._nl = dict(bonds=[], angles=[], dihedrals=[])
 
     def fix_translation(self, index=None, dim=None, target=None, replace_ok=True):
         if index is None:
@@ -53,20 +59,68 @@ class Constraints:
         self.internals['translations'].append((key, index.copy()))
         self._targets.append(target)
 
-    def _nonlinear(self, *a, **k):
-        raise NotImplementedError("only translation constraints (linear) are on the CUDA path yet")
+    def _unsupported(self, *a, **k):
+        raise NotImplementedError("fix_rotation / fix_other are not on the CUDA path yet")
 
-    fix_rotation = fix_bond = fix_angle = fix_dihedral = fix_other = _nonlinear
+    fix_rotation = fix_other = _unsupported
+
+    def _fix_internal(self, name, width, conv, indices, ncvecs=None, mic=None, target=None, comparator='eq',
+                      replace_ok=True):
+        """sella/internal.py:2906-2947."""
+        if ncvecs is not None or mic:
+            raise NotImplementedError("periodic-image constraints (ncvecs / mic) are not on the CUDA path yet")
+        if comparator != 'eq':
+            raise NotImplementedError("inequality constraints are not on the CUDA path yet")
+        key = tuple(int(i) for i in indices)
+        if len(key) != width:
+            raise ValueError("{} needs {} atom indices".format(name, width))
+        if key[0] > key[-1]:                      # a coordinate and its reverse are the same coordinate
+            key = key[::-1]
+        target = None if target is None else float(target) * conv
+        store = self._nl[name]
+        for k, (kk, _) in enumerate(store):
+            if kk == key:
+                if replace_ok:
+                    store[k] = (key, target)
+                    return
+                raise DuplicateConstraintError("Coordinate {} is already fixed".format(key))
+        store.append((key, target))
+        self.internals[name].append(key)
+
+    def fix_bond(self, indices, **kw):
+        self._fix_internal('bonds', 2, 1.0, indices, **kw)
+
+    def fix_angle(self, indices, **kw):
+        self._fix_internal('angles', 3, np.pi / 180.0, indices, **kw)
+
+    def fix_dihedral(self, indices, **kw):
+        self._fix_internal('dihedrals', 4, np.pi / 180.0, indices, **kw)
 
     # -- what the engine needs
     @property
     def ncons(self):
-        return len(self._targets)
+        return len(self._targets) + self.nnonlinear
+
+    @property
+    def nnonlinear(self):
+        return sum(len(v) for v in self._nl.values())
+
+    def nonlinear_system(self):
+        """(BatchedInternals over the fixed bonds/angles/dihedrals, targets [nnl] with NaN where the
+        value at the start geometry is to be held), or None."""
+        if not self.nnonlinear:
+            return None
+        from .internal import BatchedInternals
+        ints = BatchedInternals(self.natoms, bonds=[k for k, _ in self._nl['bonds']],
+                                angles=[k for k, _ in self._nl['angles']],
+                                dihedrals=[k for k, _ in self._nl['dihedrals']])
+        tg = [t for name in ('bonds', 'angles', 'dihedrals') for _, t in self._nl[name]]
+        return ints, np.array([np.nan if t is None else t for t in tg], dtype=np.float64)
 
     def linear_system(self):
         """(C [nc, 3N], c [nc]) with C x = c."""
         n = 3 * self.natoms
-        C = np.zeros((self.ncons, n))
+        C = np.zeros((len(self._targets), n))
         for r, ((_, dim), index) in enumerate(self.internals['translations']):
             C[r, 3 * index + dim] = 1.0 / len(index)
         return C, np.asarray(self._targets, dtype=np.float64)

@@ -25,8 +25,10 @@ extern "C" int sb_hvp_prepare_impl(const double*, long long, const double*, cons
 extern "C" int sb_hvp_finish_impl(const double*, long long, const double*, const double*, const double*, double,
                                   double*, double*, double*, int, int*, int*, int, const int*, int, int,
                                   cudaStream_t);
-extern "C" int sb_history_ritz_impl(double*, double*, int, const int*, int, int*, const int*, int*, int,
-                                    cudaStream_t);
+extern "C" int sb_history_ritz_impl(double*, double*, int, const int*, int, int*, const int*, int*, const double*,
+                                    int, cudaStream_t);
+extern "C" int sb_cons_solve_impl(const double*, const double*, const double*, int, int, double*, double*, int*,
+                                  const int*, int, cudaStream_t);
 extern "C" int sb_update_prep_impl(const double*, const double*, double*, int, const int*, int, int, int, int,
                                    double*, int*, int*, const int*, int, cudaStream_t);
 extern "C" int sb_fill_scaled_identity_impl(double*, double*, double*, const double*, int, int, const int*, int,
@@ -214,9 +216,14 @@ int sb_davidson_mjd_coeff(const double* Vhat, int kcap, const int32_t* ksz, cons
     return sb_davidson_mjd_coeff_impl(Vhat, kcap, ksz, rvhat, pl, theta, that, n, dav_state, status, batch, ST);
 }
 int sb_history_ritz(double* Vs, double* AVs, int kcap, const int32_t* nhist, int n, int32_t* nvec_out,
-                    const int32_t* dav_state, int32_t* status, int batch, void* stream) {
+                    const int32_t* dav_state, int32_t* status, const double* HcVs, int batch, void* stream) {
     if (kcap > 32) return -1;
-    return sb_history_ritz_impl(Vs, AVs, kcap, nhist, n, nvec_out, dav_state, status, batch, ST);
+    return sb_history_ritz_impl(Vs, AVs, kcap, nhist, n, nvec_out, dav_state, status, HcVs, batch, ST);
+}
+int sb_cons_solve(const double* G, const double* Uc, const double* u, int nc, int n, double* Mr, double* L,
+                  int32_t* status, const int32_t* active, int batch, void* stream) {
+    if (nc < 1 || nc > 32 || n < 1) return -1;
+    return sb_cons_solve_impl(G, Uc, u, nc, n, Mr, L, status, active, batch, ST);
 }
 int sb_update_prep(const double* S, const double* Y, double* Ytil, int kcap, const int32_t* kvec, int n, int ncart,
                    int first, int symm, double* lam0, int32_t* skip, int32_t* status, const int32_t* active,

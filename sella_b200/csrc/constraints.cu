@@ -10,7 +10,7 @@
 // reduces to products with two thin matrices stored row-wise:
 //   R[j,:] (nr x n)  ->  dots:  out[j] = R[j,:].x (- c[j]) ;  comb: out[:] (+)= sum_j coef[j] R[j,:]
 // `rstride` = nr*n for per-system matrices, 0 when the whole batch shares one.
-#include "common.cuh"
+#include "small_dense.cuh"
 
 namespace {
 
@@ -140,6 +140,55 @@ converged_cons_kernel(const double* __restrict__ pg, const double* __restrict__ 
     }
 }
 
+// Position-dependent constraints (sella/peswrapper.py:395-407, 429-438, 467-481): with the rows
+// of the constraint Jacobian orthonormalised, drdx = G Uc (G = drdx Uc^T, nc x nc),
+//   scons = -Ucons lstsq(drdx Ucons, res)  = -sum_j res_j Mr[j,:],   Mr = G^-T Uc
+//   L     = lstsq(drdx^T, g)               =  G^-T (Uc g)
+// One CTA per system inverts G in shared memory (nc <= 32) and forms Mr and, if u = Uc g is
+// given, the Lagrange multipliers.
+struct ConsSolveShared {
+    double G[SB_KMAT], Ginv[SB_KMAT];
+    int ok;
+};
+
+__global__ void __launch_bounds__(CT)
+cons_solve_kernel(const double* __restrict__ G_, const double* __restrict__ Uc_, const double* __restrict__ u_,
+                  int nc, int n, double* __restrict__ Mr_, double* __restrict__ L_, int* __restrict__ status,
+                  const int* __restrict__ active) {
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    extern __shared__ unsigned char craw[];
+    ConsSolveShared& S = *reinterpret_cast<ConsSolveShared*>(craw);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < nc * nc; i += nt) S.G[(i / nc) * SB_KLD + (i % nc)] = G_[(size_t)b * nc * nc + i];
+    __syncthreads();
+    if (tid == 0) {
+        const bool ok = sbs_invert_serial(S.G, nc, S.Ginv);
+        if (!ok && status) atomicOr(&status[b], SB_ST_SINGULAR);
+    }
+    __syncthreads();
+    if (Mr_) {
+        const double* Uc = Uc_ + (size_t)b * nc * n;
+        double* Mr = Mr_ + (size_t)b * nc * n;
+        for (int e = tid; e < n; e += nt) {
+            double ucol[SB_KMAX];
+            for (int k = 0; k < nc; ++k) ucol[k] = Uc[(size_t)k * n + e];
+            for (int j = 0; j < nc; ++j) {
+                double acc = 0.0;
+                for (int k = 0; k < nc; ++k) acc = fma(S.Ginv[k * SB_KLD + j], ucol[k], acc);     // (G^-T)[j][k]
+                Mr[(size_t)j * n + e] = acc;
+            }
+        }
+    }
+    if (L_ && u_) {
+        for (int j = tid; j < nc; j += nt) {
+            double acc = 0.0;
+            for (int k = 0; k < nc; ++k) acc = fma(S.Ginv[k * SB_KLD + j], u_[(size_t)b * nc + k], acc);
+            L_[(size_t)b * nc + j] = acc;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int sb_rect_dots_impl(const double* R, long long rstride, int nr, const double* x, long long xstride,
@@ -180,5 +229,14 @@ extern "C" int sb_converged_cons_impl(const double* pg, const double* res, int n
                                       cudaStream_t st) {
     SB_COUNT(1);
     converged_cons_kernel<<<batch, CT, 0, st>>>(pg, res, nr, n, fmax_tol, cmax_tol, fmax_out, cmax_out, conv);
+    return SB_LAUNCH_CHECK();
+}
+
+extern "C" int sb_cons_solve_impl(const double* G, const double* Uc, const double* u, int nc, int n, double* Mr,
+                                  double* L, int* status, const int* active, int batch, cudaStream_t st) {
+    const size_t smem = sizeof(ConsSolveShared);
+    cudaFuncSetAttribute(cons_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SB_COUNT(1);
+    cons_solve_kernel<<<batch, CT, smem, st>>>(G, Uc, u, nc, n, Mr, L, status, active);
     return SB_LAUNCH_CHECK();
 }

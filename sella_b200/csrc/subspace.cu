@@ -593,7 +593,7 @@ davidson_init_kernel(const double* __restrict__ v0_, const double* __restrict__ 
 __global__ void __launch_bounds__(SS_THREADS)
 history_ritz_kernel(double* __restrict__ Vs_, double* __restrict__ AVs_, int kcap, const int* __restrict__ nhist,
                     int n, int* __restrict__ nvec_out, const int* __restrict__ dav_state,
-                    int* __restrict__ status) {
+                    int* __restrict__ status, const double* __restrict__ HcVs_) {
     const int b = blockIdx.x;
     if (dav_state[b] == DAV_IDLE) {
         if (threadIdx.x == 0) nvec_out[b] = 0;
@@ -609,11 +609,14 @@ history_ritz_kernel(double* __restrict__ Vs_, double* __restrict__ AVs_, int kca
     const int tid = threadIdx.x, warp = tid >> 5;
     gram_block(Vs, Vs, k, k, n, S.STS, true);
     gram_block(AVs, Vs, k, k, n, S.YTS, false);
+    // constraint-Hessian term of peswrapper.py:546: Atilde -= Vs^T Hc Vs  (R[i][a] = (Hc Vs_i).Vs_a)
+    if (HcVs_) gram_block(HcVs_ + (size_t)b * kcap * n, Vs, k, k, n, S.R, false);
     __syncthreads();
     if (tid == 0) {
         bool ok = symmetrize_coeffs_serial(S.STS, S.YTS, k, k, S.coef, S.dYTS, S.T1, S.T2);
         for (int a = 0; a < k; ++a)
-            for (int i = 0; i < k; ++i) S.Asub[a * SB_KLD + i] = S.YTS[i * SB_KLD + a] + S.dYTS[i * SB_KLD + a];
+            for (int i = 0; i < k; ++i)
+                S.Asub[a * SB_KLD + i] = S.YTS[i * SB_KLD + a] + S.dYTS[i * SB_KLD + a] - (HcVs_ ? S.R[i * SB_KLD + a] : 0.0);
         // scipy eigh reads the lower triangle
         for (int i = 0; i < k; ++i)
             for (int j = i + 1; j < k; ++j) S.Asub[i * SB_KLD + j] = S.Asub[j * SB_KLD + i];
@@ -711,10 +714,11 @@ extern "C" int sb_hvp_finish_impl(const double* vfull, long long vstride, const 
 }
 
 extern "C" int sb_history_ritz_impl(double* Vs, double* AVs, int kcap, const int* nhist, int n, int* nvec_out,
-                                    const int* dav_state, int* status, int batch, cudaStream_t st) {
+                                    const int* dav_state, int* status, const double* HcVs, int batch,
+                                    cudaStream_t st) {
     const size_t smem = sizeof(RRShared);
     cudaFuncSetAttribute(history_ritz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     SB_COUNT(1);
-    history_ritz_kernel<<<batch, SS_THREADS, smem, st>>>(Vs, AVs, kcap, nhist, n, nvec_out, dav_state, status);
+    history_ritz_kernel<<<batch, SS_THREADS, smem, st>>>(Vs, AVs, kcap, nhist, n, nvec_out, dav_state, status, HcVs);
     return SB_LAUNCH_CHECK();
 }

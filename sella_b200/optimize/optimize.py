@@ -12,7 +12,8 @@ class with the same ``run(fmax, steps)`` loop is used.
 
 Scope (raises NotImplementedError otherwise, never falls back to the CPU): Cartesian
 coordinates; translation constraints (``sella_b200.Constraints.fix_translation``, incl.
-the centre-of-geometry projection the reference adds by default, peswrapper.py:233-244);
+the centre-of-geometry projection the reference adds by default, peswrapper.py:233-244) and
+bond / angle / dihedral constraints (``fix_bond``, ``fix_angle``, ``fix_dihedral``);
 no rotation projection (pass ``proj_rot=False`` for non-periodic systems: the reference
 would add the nonlinear ``fix_rotation`` there), no ``hessian_function``, no cell
 optimisation.
@@ -155,7 +156,8 @@ class Sella(_Base):
                 "the rotation projection (fix_rotation, nonlinear) is not on the CUDA path yet: pass "
                 "proj_rot=False or use a periodic system")
         self.constraints = constraints
-        lin = constraints.linear_system() if constraints.ncons else None
+        lin = constraints.linear_system() if len(constraints._targets) else None
+        nonlin = constraints.nonlinear_system()
         eigensolver = kwargs.pop("eigensolver", "jd0")
         if kwargs:
             raise TypeError("unsupported keyword arguments: %s" % sorted(kwargs))
@@ -171,12 +173,21 @@ class Sella(_Base):
                                  sigma_dec=sigma_dec, rho_dec=rho_dec, rho_inc=rho_inc, eig=eig, eta=eta,
                                  method=method, gamma=gamma, rs=rs, nsteps_per_diag=nsteps_per_diag,
                                  diag_every_n=diag_every_n, eigensolver=eigensolver, kcap=16, threepoint=threepoint,
-                                 constraints=None if lin is None else (lin[0], lin[1][None, :]))
+                                 constraints=self._engine_constraints(lin, nonlin, x0))
         self.pes = _PESView(self)
         self.ord = order
         self.eta = eta
         self.constraints_tol = constraints_tol
         self.fmax = None
+
+    @staticmethod
+    def _engine_constraints(lin, nonlin, x0):
+        if nonlin is None:
+            return None if lin is None else (lin[0], lin[1][None, :])
+        ints, tg = nonlin
+        q0 = ints.calc(x0)[0].cpu().numpy()
+        targets = np.where(np.isnan(tg), q0, tg)[None, :]
+        return (None if lin is None else lin[0], None if lin is None else lin[1][None, :], ints, targets)
 
     # attributes the reference exposes
     delta = property(lambda self: float(self._eng.delta[0]))

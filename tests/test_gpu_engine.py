@@ -292,3 +292,61 @@ def test_engine_constraints_golden(golden):
                 np.testing.assert_allclose(float(eng.delta[0]), G["delta%d" % i][t], rtol=1e-8)
         done += 1
     assert done >= 6
+
+
+@pytest.mark.parametrize("case", ["quadratic_bonds_angle", "quadratic_dihedral_plus_linear", "emt_cluster_bond"])
+def test_engine_with_position_dependent_constraints(case):
+    """Bond / angle / dihedral constraints (drdx, Ucons, scons, multipliers and the constraint
+    Hessian Hc rebuilt at every geometry, peswrapper.py:343-352, 395-407, 429-438, 467-481) against
+    the oracle's generic-PES restatement."""
+    from oracle.pes import NonlinearPES
+    from oracle.driver import SaddleSearch
+    from sella_b200.batched import BatchedSella, QuadraticSurface
+    from sella_b200.internal import BatchedInternals
+    from sella_b200.synthetic import quadratic_system, quadratic_func
+    C = None
+    if case.startswith("quadratic"):
+        n, systems = 30, [3, 4, 5]
+        data = [quadratic_system(b, n) for b in systems]
+        A = np.stack([d[0] for d in data]); xs = np.stack([d[1] for d in data]); x0 = np.stack([d[2] for d in data])
+        surf = QuadraticSurface(to_dev(A), to_dev(xs))
+        funcs = [quadratic_func(d[0], d[1]) for d in data]
+        if case == "quadratic_bonds_angle":
+            coords = dict(bonds=[(0, 1), (4, 7)], angles=[(2, 3, 5)])
+        else:
+            coords = dict(bonds=[(1, 2)], dihedrals=[(0, 3, 6, 8)], translations=[(9, 1)])
+            C = np.zeros((2, n)); C[0, 0::3] = 1.0 / 10; C[1, 5] = 1.0
+        kw = dict(method="prfo", rs="ras")
+    else:
+        from oracle import emt as oemt
+        from sella_b200.emt import EMTSurface
+        from sella_b200.synthetic import fcc_cluster
+        nat = 16
+        n = 3 * nat
+        x0 = np.stack([fcc_cluster(nat, seed=40 + b, rattle=0.08).ravel() for b in range(3)])
+        surf = EMTSurface(3, nat, dev())
+        funcs = [oemt.emt_func()] * 3
+        coords = dict(bonds=[(0, 1)])
+        C = np.zeros((3, n))
+        for d in range(3):
+            C[d, d::3] = 1.0 / nat
+        kw = dict(method="prfo", rs="tr")
+    ints = BatchedInternals(n // 3, translations=coords.get("translations"), bonds=coords.get("bonds"),
+                            angles=coords.get("angles"), dihedrals=coords.get("dihedrals"))
+    eng = BatchedSella(surf, to_dev(x0), constraints=(C, None, ints, None), diag_maxiter=6, **kw)
+    oracles = []
+    for b in range(len(x0)):
+        p = NonlinearPES(funcs[b], x0[b], coords, None, C, None if C is None else C @ x0[b])
+        oracles.append((p, SaddleSearch(p, diag_maxiter=6, **kw)))
+    for t in range(7):
+        eng.step()
+        x = eng.x.cpu().numpy()
+        for b, (p, o) in enumerate(oracles):
+            o.step()
+            # the oracle's constraint Hessians are central differences (1e-9 relative); the CUDA ones are exact
+            np.testing.assert_allclose(x[b], p.get_x(), rtol=0, atol=2e-7, err_msg="system %d step %d" % (b, t))
+    eng.check_status()
+    conv = eng.converged(1e-3)
+    for b, (p, o) in enumerate(oracles):
+        np.testing.assert_allclose(eng.cons["res"][b].cpu().numpy(), p.get_res(), atol=1e-7)
+        assert np.abs(p.get_res()).max() < 0.05          # the (curved) constraint surface is being tracked

@@ -234,3 +234,37 @@ def test_sella_with_translation_constraints():
     for t in range(6):
         dyn2.step(); o2.step()
         np.testing.assert_allclose(atoms2.positions.ravel(), p2.get_x(), rtol=0, atol=1e-8)
+
+
+def test_sella_with_bond_and_angle_constraints():
+    """Constraints.fix_bond / fix_angle (sella/internal.py:2946-2950) through Sella(atoms, ...): the
+    constrained coordinates are driven to their targets while the saddle search proceeds; vs the
+    oracle's generic-PES loop with the same constraints."""
+    from sella_b200 import Sella, Constraints
+    from sella_b200.synthetic import quadratic_system, quadratic_func
+    from oracle.pes import NonlinearPES
+    from oracle.driver import SaddleSearch
+    from oracle import internals as oi
+    n = 30
+    A, xs, x0 = quadratic_system(11, n)
+    func = quadratic_func(A, xs)
+    atoms = _Atoms(func, x0)
+    pos0 = x0.reshape(-1, 3)
+    d01 = np.linalg.norm(pos0[1] - pos0[0])
+    cons = Constraints(atoms)
+    cons.fix_bond((0, 1), target=d01 + 0.05)                 # pull the bond 0.05 A longer
+    cons.fix_angle((2, 3, 5))                                # hold the current angle
+    cons.fix_translation(7)
+    dyn = Sella(atoms, constraints=cons, logfile=None, proj_trans=False)
+    C, c = cons.linear_system()
+    q0 = oi.evaluate(pos0, (), [(0, 1)], [(2, 3, 5)], ())[0]
+    p = NonlinearPES(func, x0, dict(bonds=[(0, 1)], angles=[(2, 3, 5)]), np.array([d01 + 0.05, q0[1]]), C, c)
+    o = SaddleSearch(p)
+    for t in range(10):
+        dyn.step(); o.step()
+        np.testing.assert_allclose(atoms.positions.ravel(), p.get_x(), rtol=0, atol=2e-7)
+    pos = atoms.positions
+    assert abs(np.linalg.norm(pos[1] - pos[0]) - (d01 + 0.05)) < 1e-4
+    np.testing.assert_allclose(pos[7], pos0[7], atol=1e-12)
+    ok, fmax, cmax = dyn.pes.converged(10.0)
+    assert cmax < 1e-3
