@@ -56,6 +56,10 @@ def parse():
     ap.add_argument("--method", default="prfo", help="step model: prfo (Sella's default for saddles), rfo, qn")
     ap.add_argument("--kdiag", type=int, default=5)
     ap.add_argument("--diag-every", type=int, default=3)
+    ap.add_argument("--proj-rot", action="store_true",
+                    help="emt-cluster only: also hold the three rotation coordinates (the reference's default "
+                         "projection for non-periodic systems, peswrapper.py:246-253); position-dependent "
+                         "constraints take the direct-eigensolve path")
     ap.add_argument("--cpu-systems", type=int, default=0, help="reference sample size (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
@@ -105,7 +109,8 @@ def workload(args):
                               % (args.batch * args.n * args.n * 8 * 4 / 1e9), **common)
     what = ("%d-atom Cu(111) slabs (rattled 0.05 A), bottom half held by fix_translation (%d linear constraints)"
             % (args.n // 3, args.n // 2)) if args.workload == "emt-slab" else \
-           ("%d-atom Cu clusters (fcc ball + 0.05 A rattle), centre of mass held (3 linear constraints)" % (args.n // 3))
+           ("%d-atom Cu clusters (fcc ball + 0.05 A rattle), centre of mass held (3 linear constraints)%s"
+            % (args.n // 3, " + the three rotation coordinates held (position-dependent)" if args.proj_rot else ""))
     return dict(workload="batch=%d/GPU x 3N=%d EMT-form surface on the device, %s, %s" % (args.batch, args.n, what, tail),
                 l2_policy="working set %.1f GB per GPU >> 126 MB L2 (no flush needed)"
                           % (args.batch * args.n * args.n * 8 * 4 / 1e9), **common)
@@ -115,7 +120,8 @@ def workload(args):
 def _cpu_worker(job):
     """Runs `nsys` oracle searches for `steps` steps with 1 BLAS thread; returns
     (steps done, seconds in the timed part)."""
-    first, nsys, n, rs, kdiag, diag_every, warm, steps, threads, method, wl = job
+    first, nsys, n, rs, kdiag, diag_every, warm, steps, threads, method, wl = job[:11]
+    proj_rot = len(job) > 11 and job[11]
     os.environ["OMP_NUM_THREADS"] = str(threads)
     os.environ["OPENBLAS_NUM_THREADS"] = str(threads)
     os.environ["MKL_NUM_THREADS"] = str(threads)
@@ -136,6 +142,9 @@ def _cpu_worker(job):
         if wl == "quadratic":
             A, xs, x0 = quadratic_system(first + i, n)
             p = CartesianPES(quadratic_func(A, xs), x0)
+        elif proj_rot:
+            from oracle.pes import NonlinearPES
+            p = NonlinearPES(emt_func(cell, pbc), X0[i], dict(rotation_ref=X0[i].reshape(-1, 3)), np.zeros(3), C, C @ X0[i])
         else:
             p = CartesianPES(emt_func(cell, pbc), X0[i], C, C @ X0[i])
         o = SaddleSearch(p, method=method, rs=rs, diag_maxiter=kdiag, diag_every_n=diag_every)
@@ -171,7 +180,7 @@ def cpu_reference(args, warm, steps, budget_s=25.0):
     # calibrate: one system, all threads
     t0 = time.perf_counter()
     done, dt = _cpu_worker((0, 1, args.n, args.rs, args.kdiag, args.diag_every, warm, steps, cores, args.method,
-                            args.workload))
+                            args.workload, args.proj_rot))
     wall1 = time.perf_counter() - t0
     rate_mt = done / dt
     per_sys_wall = wall1
@@ -184,7 +193,7 @@ def cpu_reference(args, warm, steps, budget_s=25.0):
     if args.cpu_systems:
         per_proc = max(1, args.cpu_systems // nproc)
     jobs = [(100 + i * per_proc, per_proc, args.n, args.rs, args.kdiag, args.diag_every, warm, steps, 1,
-             args.method, args.workload) for i in range(nproc)]
+             args.method, args.workload, args.proj_rot) for i in range(nproc)]
     t0 = time.perf_counter()
     with ctx.Pool(nproc) as pool:
         res = pool.map(_cpu_worker, jobs)
@@ -317,6 +326,9 @@ def run_ours(args):
         x0 = torch.from_numpy(X0).to(dev)
         surf = EMTSurface(b, n // 3, dev, cell=cell, pbc=pbc)
         cons = (C, None)
+        if args.proj_rot and args.workload == "emt-cluster":
+            from sella_b200.internal import BatchedInternals
+            cons = (C, None, BatchedInternals(n // 3, rotation_ref=X0.reshape(b, n // 3, 3)), None)
 
     def make():
         return BatchedSella(surf, x0, method=args.method, rs=args.rs, diag_maxiter=args.kdiag,

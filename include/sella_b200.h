@@ -258,6 +258,17 @@ int sb_internals_hess(const int32_t* trans, int nt, const int32_t* bonds, int nb
                       const double* td, const double* x, int n, const double* v, double* D,
                       const double* w, double* R, const int32_t* active, int batch, void* stream);
 
+/* Rotation coordinate of a whole configuration (sella/internal.py:507-800, class Rotation
+ * :1031-1078): refpos [natoms,3] CENTRED reference geometry (refstride 0 = shared, 3*natoms = per
+ * system); qprev [b,4] (in/out, may be NULL = identity start) keeps the quaternion branch;
+ * vals (may be NULL): 3 rotation-vector components at vals + b*valstride; J (may be NULL): three
+ * Jacobian rows of length 3*natoms at J + b*jstride; if L (3 multipliers at L + b*lstride) and D
+ * are given, D[b] (3N x 3N) += sum_k L_k d2v_k/dx2.  work: batch * 14 * 3*natoms doubles.         */
+int sb_rotation(const double* x, int natoms, const double* refpos, long long refstride, double* qprev,
+                double* vals, long long valstride, double* J, long long jstride, const double* L,
+                long long lstride, double* D, double* work, const int32_t* active, int batch,
+                void* stream);
+
 /* ---- dense algebra of the internal-coordinate path (sella/peswrapper.py:674-736, 1011-1082,
  * 1124-1127, 1176-1183; sella/_gpu.py:100-132).  Row-major matrices with explicit leading
  * dimensions; batch strides in doubles (0 = one matrix shared by the batch).

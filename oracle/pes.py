@@ -374,13 +374,26 @@ class NonlinearPES(CartesianPES):
         self.coords = {k: [tuple(int(a) for a in t) for t in coords.get(k, ())]
                        for k in ("translations", "bonds", "angles", "dihedrals")}
         self.ndih = len(self.coords["dihedrals"])
+        # "rotation_ref": reference geometry of the three whole-system rotation coordinates
+        # (Constraints.fix_rotation, internal.py:2825-2859); they come last
+        self.rot_ref = coords.get("rotation_ref")
+        self.q_prev = None
         q0 = self._q(self.x)[0]
         self.targets = q0.copy() if targets is None else np.asarray(targets, float)
 
-    def _q(self, x, hess=False):
+    def _q(self, x, L=None):
         from . import internals as oi
+        from . import rotation as orot
         c = self.coords
         q, B, H = oi.evaluate(x.reshape(-1, 3), c["translations"], c["bonds"], c["angles"], c["dihedrals"])
+        if self.rot_ref is not None:
+            unit = [np.eye(3)[k] for k in range(3)]
+            out = orot.rotation(x, self.rot_ref, self.q_prev, np.zeros(3) if L is None else L)
+            vals, J, self.q_prev = out[0], out[1], out[2]
+            q = np.concatenate([q, vals])
+            B = np.vstack([B.reshape(-1, x.size), J])
+            # per-coordinate Hessians are only ever used contracted with multipliers (get_Hc)
+            H = list(H) + [("rot", k) for k in range(3)]
         return q, B, H
 
     def get_drdx(self):
@@ -389,7 +402,8 @@ class NonlinearPES(CartesianPES):
     def get_res(self):
         r = self._q(self.x)[0] - self.targets
         if self.ndih:
-            r[-self.ndih:] = (r[-self.ndih:] + np.pi) % (2 * np.pi) - np.pi
+            hi = len(r) - (3 if self.rot_ref is not None else 0)
+            r[hi - self.ndih:hi] = (r[hi - self.ndih:hi] + np.pi) % (2 * np.pi) - np.pi
         return np.concatenate([self.C @ self.x - self.c, r])
 
     def _calc_basis(self):
@@ -398,10 +412,14 @@ class NonlinearPES(CartesianPES):
         return drdx, Ucons, np.eye(self.dim), Ufree
 
     def get_Hc(self):
+        from . import rotation as orot
         L = self.curr["L"]
         H = self._q(self.x)[2]
         nlin = self.C.shape[0]
         out = np.zeros((self.dim, self.dim))
         for Li, Hi in zip(L[nlin:], H):
-            out += Li * Hi
+            if not isinstance(Hi, tuple):
+                out += Li * Hi
+        if self.rot_ref is not None:
+            out += orot.rotation(self.x, self.rot_ref, self.q_prev, L[-3:])[3]
         return out

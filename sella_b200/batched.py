@@ -270,7 +270,7 @@ class BatchedSella:
             cons[k] = torch.zeros(b, **f64)
         cons["naive"] = torch.zeros(b, dtype=torch.int32, device=dev)
         cons["regular"] = torch.ones(b, dtype=torch.int32, device=dev)
-        ndih0 = nnl - internals.ndihedrals
+        ndih0 = internals.nstd - internals.ndihedrals
         cons["nl"] = dict(ints=internals, target=tgt, nlin=nlin, dih0=ndih0, Lmul=torch.zeros(b, nc, **f64),
                           Hc=torch.zeros(b, n, n, **f64), HL=torch.zeros(b, n, n, **f64), u=torch.zeros(b, nc, **f64),
                           evalsHL=torch.zeros(b, n, **f64), hcv=torch.zeros(b, 1, n, **f64), hcv2=torch.zeros(b, 1, n, **f64),
@@ -291,8 +291,8 @@ class BatchedSella:
         cn["C"][:, nlin:] = Bm
         res = q - nl["target"]
         if ints.ndihedrals:                             # dihedrals live on a circle
-            d = res[:, nl["dih0"]:]
-            res[:, nl["dih0"]:] = torch.remainder(d + np.pi, 2.0 * np.pi) - np.pi
+            lo, hi = nl["dih0"], nl["dih0"] + ints.ndihedrals
+            res[:, lo:hi] = torch.remainder(res[:, lo:hi] + np.pi, 2.0 * np.pi) - np.pi
         # c is chosen so that C x - c is the true residual: the linear-constraint kernels then apply as they are
         call("sb_rect_dots", _p(cn["C"]), LL(cn["cstride"]), I(nc), _p(self.x), LL(n), _p(None), _p(cn["res"]),
              I(n), _p(None), I(b), _stream())

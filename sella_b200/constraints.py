@@ -13,8 +13,9 @@ kinds the CUDA path supports:
 
 Translations are linear (`linear_system`); bonds, angles and dihedrals are position dependent
 (`nonlinear_system`: their Jacobian rows and Hessians come from the internal-coordinate kernels at
-every geometry).  `fix_rotation`, `fix_other`, inequality comparators, `ncvecs`/`mic` periodic
-images are not on the CUDA path and raise NotImplementedError.
+every geometry), and so is `fix_rotation()` (the three rotation coordinates of the whole
+configuration, internal.py:507-800).  `fix_other`, rotations of atom subsets, inequality comparators
+and `ncvecs`/`mic` periodic images are not on the CUDA path and raise NotImplementedError.
 """
 import numpy as np
 
@@ -34,6 +35,7 @@ class Constraints:
         self.internals = dict(translations=[], bonds=[], angles=[], dihedrals=[], other=[], rotations=[])
         self._targets = []
         self._nl = dict(bonds=[], angles=[], dihedrals=[])
+        self._rot_ref = None
 
     def fix_translation(self, index=None, dim=None, target=None, replace_ok=True):
         if index is None:
@@ -59,10 +61,22 @@ class Constraints:
         self.internals['translations'].append((key, index.copy()))
         self._targets.append(target)
 
-    def _unsupported(self, *a, **k):
-        raise NotImplementedError("fix_rotation / fix_other are not on the CUDA path yet")
+    def fix_other(self, *a, **k):
+        raise NotImplementedError("fix_other is not on the CUDA path yet")
 
-    fix_rotation = fix_other = _unsupported
+    def fix_rotation(self, indices=None, axis=None, replace_ok=True):
+        """sella/internal.py:2825-2859: the three rotation coordinates of the whole configuration
+        relative to its current geometry are held at zero (what the reference adds by default for
+        non-periodic systems, peswrapper.py:246-253).  Subsets of atoms / single axes are not on
+        the CUDA path yet."""
+        if indices is not None and sorted(int(i) for i in np.atleast_1d(indices)) != list(range(self.natoms)):
+            raise NotImplementedError("fix_rotation of a subset of atoms is not on the CUDA path yet")
+        if axis is not None:
+            raise NotImplementedError("fix_rotation of a single axis is not on the CUDA path yet")
+        if self._rot_ref is not None and not replace_ok:
+            raise DuplicateConstraintError("This rotation has already been constrained!")
+        self._rot_ref = np.array(self.atoms.positions, dtype=np.float64)
+        self.internals['rotations'] = [('all', k) for k in range(3)]
 
     def _fix_internal(self, name, width, conv, indices, ncvecs=None, mic=None, target=None, comparator='eq',
                       replace_ok=True):
@@ -103,7 +117,7 @@ class Constraints:
 
     @property
     def nnonlinear(self):
-        return sum(len(v) for v in self._nl.values())
+        return sum(len(v) for v in self._nl.values()) + (3 if self._rot_ref is not None else 0)
 
     def nonlinear_system(self):
         """(BatchedInternals over the fixed bonds/angles/dihedrals, targets [nnl] with NaN where the
@@ -113,8 +127,10 @@ class Constraints:
         from .internal import BatchedInternals
         ints = BatchedInternals(self.natoms, bonds=[k for k, _ in self._nl['bonds']],
                                 angles=[k for k, _ in self._nl['angles']],
-                                dihedrals=[k for k, _ in self._nl['dihedrals']])
+                                dihedrals=[k for k, _ in self._nl['dihedrals']], rotation_ref=self._rot_ref)
         tg = [t for name in ('bonds', 'angles', 'dihedrals') for _, t in self._nl[name]]
+        if self._rot_ref is not None:
+            tg += [0.0, 0.0, 0.0]
         return ints, np.array([np.nan if t is None else t for t in tg], dtype=np.float64)
 
     def linear_system(self):

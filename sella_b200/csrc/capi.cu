@@ -272,6 +272,15 @@ int sb_trtri(const double* R, double* Rinv, int n, int32_t* status, const int32_
     if (n < 1 || batch < 1) return -1;
     return sb_trtri_impl(R, Rinv, n, status, active, batch, (cudaStream_t)stream);
 }
+extern "C" int sb_rotation_impl(const double*, int, const double*, long long, double*, double*, long long, double*,
+                                long long, const double*, long long, double*, double*, const int*, int, cudaStream_t);
+int sb_rotation(const double* x, int natoms, const double* refpos, long long refstride, double* qprev, double* vals,
+                long long valstride, double* J, long long jstride, const double* L, long long lstride, double* D,
+                double* work, const int32_t* active, int batch, void* stream) {
+    if (natoms < 2 || batch < 1 || !work) return -1;
+    return sb_rotation_impl(x, natoms, refpos, refstride, qprev, vals, valstride, J, jstride, L, lstride, D, work,
+                            active, batch, (cudaStream_t)stream);
+}
 extern "C" int sb_secular_timing_impl(float*, int);
 int sb_secular_timing(float* out3, int enable) { return sb_secular_timing_impl(out3, enable); }
 extern "C" int sb_rfo_profile_impl(unsigned long long*, int);

@@ -31,14 +31,28 @@ class BatchedInternals:
     [(i, j, k, l)]; tvec_*: PBC shift vectors (ncvec @ cell) per coordinate, or None."""
 
     def __init__(self, natoms, translations=None, bonds=None, angles=None, dihedrals=None,
-                 tvec_bonds=None, tvec_angles=None, tvec_dihedrals=None):
+                 tvec_bonds=None, tvec_angles=None, tvec_dihedrals=None, rotation_ref=None):
         self.natoms, self.n = int(natoms), 3 * int(natoms)
         self.trans, self.bonds = _iarr(translations, 2), _iarr(bonds, 2)
         self.angles, self.diheds = _iarr(angles, 3), _iarr(dihedrals, 4)
         self.ntrans, self.nbonds = self.trans.shape[0], self.bonds.shape[0]
         self.nangles, self.ndihedrals = self.angles.shape[0], self.diheds.shape[0]
-        self.nother = self.nrotations = 0
-        self.nint = self.ntrans + self.nbonds + self.nangles + self.ndihedrals
+        self.nother = 0
+        # the three rotation coordinates of the whole configuration relative to `rotation_ref`
+        # ([natoms, 3] shared, or [b, natoms, 3]); they come last (the reference's _names order)
+        self.nrotations = 0
+        self.rot_ref = None
+        if rotation_ref is not None:
+            r = np.asarray(rotation_ref, dtype=np.float64)
+            r = r.reshape((-1, self.natoms, 3))
+            r = r - r.mean(axis=1, keepdims=True)          # Rotation.__init__ centres it (internal.py:1041)
+            self.rot_ref = torch.from_numpy(np.ascontiguousarray(r)).to(dev())
+            self.rot_refstride = 0 if r.shape[0] == 1 else self.n
+            self.nrotations = 3
+            self.qprev = None
+            self._rot_work = None
+        self.nstd = self.ntrans + self.nbonds + self.nangles + self.ndihedrals
+        self.nint = self.nstd + self.nrotations
         self.tb = _tvec(tvec_bonds, self.nbonds, 1)
         self.ta = _tvec(tvec_angles, self.nangles, 2)
         self.td = _tvec(tvec_dihedrals, self.ndihedrals, 3)
@@ -53,8 +67,31 @@ class BatchedInternals:
         b = x.shape[0]
         q = torch.zeros((b, self.nint), dtype=torch.float64, device=x.device)
         B = torch.zeros((b, self.nint, self.n), dtype=torch.float64, device=x.device) if jacobian else None
-        call("sb_internals_qB", *self._topo(), _p(x), I(self.n), _p(q), _p(B), _p(active), I(b), _stream())
+        if self.nstd:
+            # the kernel writes coordinate c at q + b*nstd + c (and rows likewise): run it on its own block
+            qs = q if not self.nrotations else torch.zeros((b, self.nstd), dtype=torch.float64, device=x.device)
+            Bs = B if (B is None or not self.nrotations) else torch.zeros((b, self.nstd, self.n), dtype=torch.float64,
+                                                                           device=x.device)
+            call("sb_internals_qB", *self._topo(), _p(x), I(self.n), _p(qs), _p(Bs), _p(active), I(b), _stream())
+            if self.nrotations:
+                q[:, :self.nstd] = qs
+                if B is not None:
+                    B[:, :self.nstd] = Bs
+        if self.nrotations:
+            self._rotation(x, q, B, None, None, active)
         return (q, B) if jacobian else q
+
+    def _rotation(self, x, q, B, v, D, active):
+        from ._lib import LL
+        b = x.shape[0]
+        if self.qprev is None or self.qprev.shape[0] != b:
+            self.qprev = torch.zeros((b, 4), dtype=torch.float64, device=x.device)
+            self.qprev[:, 0] = 1.0
+            self._rot_work = torch.empty((b, 14 * self.n), dtype=torch.float64, device=x.device)
+        nint, n, o = self.nint, self.n, self.nstd
+        call("sb_rotation", _p(x), I(self.natoms), _p(self.rot_ref), LL(self.rot_refstride), _p(self.qprev),
+             _p(None if q is None else q[:, o:]), LL(nint), _p(None if B is None else B[:, o:]), LL(nint * n),
+             _p(None if v is None else v[:, o:]), LL(nint), _p(D), _p(self._rot_work), _p(active), I(b), _stream())
 
     def jacobian(self, x, active=None):
         return self.calc(x, jacobian=True, active=active)[1]
@@ -64,12 +101,18 @@ class BatchedInternals:
         check_f64(x, v)
         b = x.shape[0]
         D = torch.zeros((b, self.n, self.n), dtype=torch.float64, device=x.device)
-        call("sb_internals_hess", *self._topo(), _p(x), I(self.n), _p(v), _p(D), _p(None), _p(None), _p(active),
-             I(b), _stream())
+        if self.nstd:
+            vs = v if not self.nrotations else v[:, :self.nstd].contiguous()
+            call("sb_internals_hess", *self._topo(), _p(x), I(self.n), _p(vs), _p(D), _p(None), _p(None), _p(active),
+                 I(b), _stream())
+        if self.nrotations:
+            self._rotation(x, None, None, v, D, active)
         return D
 
     def rdot(self, x, w, active=None):
         """R [b, nint, n]: row c = (d2q_c/dx2) w[b]."""
+        if self.nrotations:
+            raise NotImplementedError("rdot with rotation coordinates is not on the CUDA path yet")
         check_f64(x, w)
         b = x.shape[0]
         R = torch.zeros((b, self.nint, self.n), dtype=torch.float64, device=x.device)

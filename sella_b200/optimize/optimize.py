@@ -14,9 +14,8 @@ Scope (raises NotImplementedError otherwise, never falls back to the CPU): Carte
 coordinates; translation constraints (``sella_b200.Constraints.fix_translation``, incl.
 the centre-of-geometry projection the reference adds by default, peswrapper.py:233-244) and
 bond / angle / dihedral constraints (``fix_bond``, ``fix_angle``, ``fix_dihedral``);
-no rotation projection (pass ``proj_rot=False`` for non-periodic systems: the reference
-would add the nonlinear ``fix_rotation`` there), no ``hessian_function``, no cell
-optimisation.
+the rotation projection of non-periodic systems (``fix_rotation`` of the whole configuration,
+peswrapper.py:246-253); no ``hessian_function``, no cell optimisation.
 """
 import warnings
 from time import localtime, strftime
@@ -151,14 +150,15 @@ class Sella(_Base):
                 pass
         if proj_rot is None:                        # peswrapper.py:246-253
             proj_rot = not pbc.any()
-        if proj_rot:
-            raise NotImplementedError(
-                "the rotation projection (fix_rotation, nonlinear) is not on the CUDA path yet: pass "
-                "proj_rot=False or use a periodic system")
+        if proj_rot and not constraints.internals['rotations']:
+            constraints.fix_rotation()
         self.constraints = constraints
         lin = constraints.linear_system() if len(constraints._targets) else None
         nonlin = constraints.nonlinear_system()
         eigensolver = kwargs.pop("eigensolver", "jd0")
+        # not a keyword of the reference: bounds the Davidson vectors per diagonalisation (the engine
+        # holds at most 16; the reference goes on to 2n+1)
+        diag_maxiter = kwargs.pop("diag_maxiter", None)
         if kwargs:
             raise TypeError("unsupported keyword arguments: %s" % sorted(kwargs))
         _Base.__init__(self, atoms, restart=restart, logfile=logfile, trajectory=None, master=master)
@@ -173,6 +173,7 @@ class Sella(_Base):
                                  sigma_dec=sigma_dec, rho_dec=rho_dec, rho_inc=rho_inc, eig=eig, eta=eta,
                                  method=method, gamma=gamma, rs=rs, nsteps_per_diag=nsteps_per_diag,
                                  diag_every_n=diag_every_n, eigensolver=eigensolver, kcap=16, threepoint=threepoint,
+                                 diag_maxiter=diag_maxiter,
                                  constraints=self._engine_constraints(lin, nonlin, x0))
         self.pes = _PESView(self)
         self.ord = order
@@ -196,6 +197,13 @@ class Sella(_Base):
 
     def step(self):
         self._eng.step()
+        st = int(self._eng.status[0])
+        if st & 8:
+            # the Davidson subspace filled its 16 slots before the reference's criterion was met: the
+            # Hessian is updated with the vectors found and the search goes on (the reference would
+            # keep expanding up to 2n+1 vectors)
+            warnings.warn("sella_b200: Davidson stopped at the subspace capacity (16 vectors)")
+            self._eng.status &= ~8
         self._eng.check_status()
         self.atoms.positions = self._eng.x[0].cpu().numpy().reshape((-1, 3))
 

@@ -280,7 +280,55 @@ def golden_loop(ref):
     save("loop", **out)
 
 
+def reference_rotation_functions():
+    """The rotation coordinate of sella/internal.py is pure numpy but lives in a module that imports
+    jax and ase at the top: take the function definitions (unmodified) out of the source."""
+    import ast
+    src = open("/root/reference/sella/internal.py").read()
+    want = {"_build_F_matrix_np", "_stabilize_quaternion", "_stabilize_quaternion_from_eigh", "_asinc_np",
+            "_expmap_np", "_rotation_3axis_jacobian_np", "_apply_dF", "_rotation_hessian_single"}
+    ns = {"np": np}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name in want:
+            exec(compile(ast.Module([node], []), "sella/internal.py", "exec"), ns)
+    assert want <= set(ns)
+    return ns
+
+
+def golden_rotation():
+    fn = reference_rotation_functions()
+    rng = np.random.RandomState(21)
+    out = {}
+    i = 0
+    for N in (3, 7, 20):
+        ref = rng.normal(size=(N, 3)) * 1.5
+        ref -= ref.mean(0)
+        for amp in (0.0, 1e-6, 2e-4, 1e-3, 0.05, 0.4, 1.5):
+            th = amp * np.array([0.3, -0.5, 0.8])
+            ang = np.linalg.norm(th)
+            if ang > 0:
+                k = th / ang
+                Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+                Rm = np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx
+            else:
+                Rm = np.eye(3)
+            pos = ref @ Rm.T + (0.05 * rng.normal(size=(N, 3)) if amp > 0 else 0.0) + rng.normal(size=3)
+            F = fn["_build_F_matrix_np"](pos - pos.mean(0), ref)
+            q = fn["_stabilize_quaternion"](F, None)
+            out["ref%d" % i], out["pos%d" % i], out["q%d" % i] = ref, pos, q
+            out["val%d" % i] = fn["_expmap_np"](q)
+            out["jac%d" % i] = fn["_rotation_3axis_jacobian_np"](pos, ref, q).reshape(3, -1)
+            out["hess%d" % i] = np.stack([fn["_rotation_hessian_single"](pos, k, ref, q_stable=q).reshape(3 * N, 3 * N)
+                                          for k in range(3)])
+            i += 1
+    out["ncases"] = np.array(i)
+    save("rotation", **out)
+
+
 def main():
+    golden_rotation()
+    if "--rotation-only" in sys.argv:
+        return
     ref = ref_loader.load()
     golden_mgs(ref)
     golden_symmetrize(ref)

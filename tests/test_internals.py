@@ -89,3 +89,31 @@ def test_cuda_internals_hessian_vs_fd_of_cuda_jacobian():
     D = ints.ldot(torch.from_numpy(x0[None]).to(dev), torch.from_numpy(v[None]).to(dev))[0].cpu().numpy()
     np.testing.assert_allclose(D, Dfd, rtol=1e-7, atol=1e-8)
     np.testing.assert_allclose(D, D.T, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_cuda_rotation_coordinate_matches_reference_golden(golden):
+    """sb_rotation against outputs of the reference's own rotation functions (tests/golden/rotation.npz)."""
+    torch = pytest.importorskip("torch")
+    from sella_b200.internal import BatchedInternals
+    G = golden("rotation")
+    dev = torch.device("cuda:0")
+    L = np.array([0.7, -1.1, 0.4])
+    for i in range(int(G["ncases"])):
+        ref, pos = G["ref%d" % i], G["pos%d" % i]
+        N = len(ref)
+        ints = BatchedInternals(N, bonds=[(0, 1)], rotation_ref=ref)
+        x = torch.from_numpy(np.stack([pos.ravel(), pos.ravel() + 0.3])).to(dev)       # 2nd system: translated copy
+        q, B = ints.calc(x, jacobian=True)
+        q, B = q.cpu().numpy(), B.cpu().numpy()
+        np.testing.assert_allclose(ints.qprev.cpu().numpy()[0], G["q%d" % i], atol=1e-13)
+        for s in range(2):
+            np.testing.assert_allclose(q[s, 1:], G["val%d" % i], atol=1e-13)
+            np.testing.assert_allclose(B[s, 1:], G["jac%d" % i], atol=1e-9, rtol=1e-9)
+        np.testing.assert_allclose(q[0, 0], np.linalg.norm(pos[1] - pos[0]), rtol=1e-14)
+        v = np.zeros((2, 4)); v[:, 1:] = L
+        D = ints.ldot(x, torch.from_numpy(v).to(dev)).cpu().numpy()
+        Href = np.tensordot(L, G["hess%d" % i], axes=1)
+        scale = max(1.0, np.abs(Href).max())
+        np.testing.assert_allclose(D[0], Href, atol=2e-8 * scale)
+        np.testing.assert_allclose(D[1], Href, atol=2e-8 * scale)

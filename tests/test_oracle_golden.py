@@ -166,3 +166,26 @@ def test_loop_matches_reference_sella(golden):
             np.testing.assert_allclose(dyn.delta, G["delta%d" % i][t], rtol=1e-9)
             assert p.neval == int(G["neval%d" % i][t])
         np.testing.assert_allclose(p.H.B, G["B%d" % i], rtol=1e-7, atol=1e-8)
+
+
+def test_rotation_coordinate(golden):
+    """oracle/rotation.py against the reference's own rotation functions (internal.py:507-800)."""
+    from oracle import rotation as orot
+    G = golden("rotation")
+    for i in range(int(G["ncases"])):
+        ref, pos = G["ref%d" % i], G["pos%d" % i]
+        L = np.array([0.7, -1.1, 0.4])
+        vals, J, q, H = orot.rotation(pos, ref, None, L)
+        np.testing.assert_allclose(q, G["q%d" % i], atol=1e-14)
+        np.testing.assert_allclose(vals, G["val%d" % i], atol=1e-14)
+        np.testing.assert_allclose(J, G["jac%d" % i], atol=1e-12)
+        np.testing.assert_allclose(H, np.tensordot(L, G["hess%d" % i], axes=1), atol=1e-11)
+    # and against finite differences of the value (what tests/internal/test_get_internal.py does)
+    ref, pos = G["ref8"], G["pos8"]
+    vals, J, q = orot.rotation(pos, ref)
+    h = 1e-6
+    for a in range(0, pos.size, 5):
+        pp = pos.ravel().copy(); pp[a] += h
+        pm = pos.ravel().copy(); pm[a] -= h
+        fd = (orot.rotation(pp, ref, q)[0] - orot.rotation(pm, ref, q)[0]) / (2 * h)
+        np.testing.assert_allclose(J[:, a], fd, rtol=1e-6, atol=1e-8)
