@@ -102,11 +102,12 @@ class BatchedSella:
         self.kcap = int(kcap)
         assert 2 <= self.kcap <= 32
         # "update": keep (evals, Vt) current through the secular-equation update of
-        # every low-rank Hessian update (needs kcap <= 16); "direct": full eigensolve
-        # whenever the spectrum is needed (the reference's behaviour).
+        # every low-rank Hessian update (block updates of more than 16 secant pairs -- kcap > 16 --
+        # are followed by a full eigensolve instead); "direct": full eigensolve whenever the
+        # spectrum is needed (the reference's behaviour).
         if eig_mode not in ("update", "direct"):
             raise ValueError("eig_mode must be 'update' or 'direct'")
-        self.eig_mode = eig_mode if self.kcap <= 16 else "direct"
+        self.eig_mode = eig_mode
         self.eig_refresh_every = int(eig_refresh_every)
         self._updates_since_refresh = 0
 
@@ -160,7 +161,7 @@ class BatchedSella:
         self.c2, self.s2 = z(b, 2, n), z(b, 2, n)
         if self.eig_mode == "update":
             self.sec1 = dict(P=z(b, 2, n), Z=z(b, 2, n), sig=z(b, 2))
-            self.seck = dict(P=z(b, 2 * kc, n), Z=z(b, 2 * kc, n), sig=z(b, 2 * kc))
+            self.seck = dict(P=z(b, 2 * kc, n), Z=z(b, 2 * kc, n), sig=z(b, 2 * kc)) if kc <= 16 else None
             self.Cmat = z(b, 32 * 33)
             self.nterm = zi(b)
             self.qwork = z(b, n, n)
@@ -402,7 +403,8 @@ class BatchedSella:
             call("sb_abs_scale", _p(bufs["VtS"]), _p(self.evalsB), _p(bufs["aC"]), I(kc), I(n), _p(self.skip),
                  I(b), _stream())
             K.hv_ld(self.VtB, bufs["aC"], bufs["aBS"], nv, transposed=True, active=active)
-        track = self.eig_mode == "update" and (self.eig_valid or first)
+        wide = kc > 16                      # more terms than one eigen-update takes: full eigensolve afterwards
+        track = self.eig_mode == "update" and (self.eig_valid or first) and not wide
         call("sb_update_mid", _p(S), _p(bufs["Ytil"]), _p(bufs["BS"]),
              _p(bufs["aBS"] if self.update_method == 0 else None), _p(bufs["U"]), _p(bufs["J"]), _p(bufs["W"]),
              _p(bufs["Xw"]), I(kc), _p(kvec), I(n), I(self.update_method), _p(self.skip), _p(self.status),
@@ -432,9 +434,28 @@ class BatchedSella:
                      _p(self.nterm), I(n), _p(self.eig_ws.work), _p(self.qwork), _p(self.status), _p(self.skip),
                      I(b), _stream())
             self.eig_valid = True
+        elif wide and self.eig_mode == "update":
+            self._direct_spectra()
+            self.eig_valid = True
         else:
             self.eig_valid = False
             self._updates_since_refresh = 0
+
+    def _direct_spectra(self):
+        """Full eigensolves of B (and, with linear constraints, of Bp = P_f B P_f + sigma P_c)."""
+        b, n = self.batch, self.n
+        K.eigh(self.B, evals=self.evalsB, Vt=self.VtB, ws=self.eig_ws, status=self.status)
+        cn = self.cons
+        if cn is not None and "nl" not in cn:
+            Uc = cn["Uc"][0] if cn["shared"] else cn["Uc"]
+            Pc = K.gemm(Uc, Uc, transA=True)                         # [1 or b, n, n]
+            eye = torch.eye(n, dtype=torch.float64, device=self.dev)
+            Pf = (eye - Pc[0]).contiguous() if cn["shared"] else (eye.expand(b, n, n) - Pc).contiguous()
+            sigma = 1.0 + 8.0 * torch.maximum(self.evalsB[:, 0].abs(), self.evalsB[:, -1].abs())
+            Bp = K.gemm(Pf, K.gemm(self.B, Pf))
+            Bp = 0.5 * (Bp + Bp.transpose(1, 2)) + sigma[:, None, None] * Pc
+            K.eigh(Bp.contiguous(), evals=self.evals, Vt=self.Vt, ws=self.eig_ws, status=self.status)
+        self._updates_since_refresh = 0
 
     def _hvp(self, vec, vstride, mask, maskval, active):
         """One finite-difference Hessian-vector product per participating system."""

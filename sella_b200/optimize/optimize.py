@@ -156,8 +156,8 @@ class Sella(_Base):
         lin = constraints.linear_system() if len(constraints._targets) else None
         nonlin = constraints.nonlinear_system()
         eigensolver = kwargs.pop("eigensolver", "jd0")
-        # not a keyword of the reference: bounds the Davidson vectors per diagonalisation (the engine
-        # holds at most 16; the reference goes on to 2n+1)
+        # not a keyword of the reference: bounds the Davidson vectors per diagonalisation (this shell
+        # holds at most 32; the reference goes on to 2n+1)
         diag_maxiter = kwargs.pop("diag_maxiter", None)
         if kwargs:
             raise TypeError("unsupported keyword arguments: %s" % sorted(kwargs))
@@ -172,7 +172,7 @@ class Sella(_Base):
         self._eng = BatchedSella(self._surface, x0, order=order, delta0=delta0, sigma_inc=sigma_inc,
                                  sigma_dec=sigma_dec, rho_dec=rho_dec, rho_inc=rho_inc, eig=eig, eta=eta,
                                  method=method, gamma=gamma, rs=rs, nsteps_per_diag=nsteps_per_diag,
-                                 diag_every_n=diag_every_n, eigensolver=eigensolver, kcap=16, threepoint=threepoint,
+                                 diag_every_n=diag_every_n, eigensolver=eigensolver, kcap=32, threepoint=threepoint,
                                  diag_maxiter=diag_maxiter,
                                  constraints=self._engine_constraints(lin, nonlin, x0))
         self.pes = _PESView(self)
@@ -199,10 +199,10 @@ class Sella(_Base):
         self._eng.step()
         st = int(self._eng.status[0])
         if st & 8:
-            # the Davidson subspace filled its 16 slots before the reference's criterion was met: the
+            # the Davidson subspace filled its 32 slots before the reference's criterion was met: the
             # Hessian is updated with the vectors found and the search goes on (the reference would
             # keep expanding up to 2n+1 vectors)
-            warnings.warn("sella_b200: Davidson stopped at the subspace capacity (16 vectors)")
+            warnings.warn("sella_b200: Davidson stopped at the subspace capacity (32 vectors)")
             self._eng.status &= ~8
         self._eng.check_status()
         self.atoms.positions = self._eng.x[0].cpu().numpy().reshape((-1, 3))

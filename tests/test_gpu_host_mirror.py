@@ -294,3 +294,27 @@ def test_sella_default_projection_for_molecules():
     np.testing.assert_allclose(atoms.positions.mean(0), x0.reshape(-1, 3).mean(0), atol=1e-9)
     ok, fmax, cmax = dyn.pes.converged(10.0)
     assert cmax < 1e-4
+
+
+def test_sella_long_first_davidson():
+    """No cap on the Davidson work: the reference's first diagonalisation of this rattled cluster
+    runs 17 vectors (more than one eigen-update takes, so the block update is followed by a full
+    eigensolve).  Geometries against the oracle at the north-star tolerance of 1e-6 Angstrom."""
+    from sella_b200 import Sella
+    from sella_b200.synthetic import fcc_cluster
+    from oracle import emt as oemt
+    from oracle.pes import NonlinearPES
+    from oracle.driver import SaddleSearch
+    nat = 13
+    x0 = fcc_cluster(nat, seed=77, rattle=0.03).ravel()
+    func = oemt.emt_func()
+    atoms = _Atoms(func, x0); atoms.pbc = np.array([False, False, False])
+    dyn = Sella(atoms, logfile=None)
+    C, c = dyn.constraints.linear_system()
+    p = NonlinearPES(func, x0, dict(rotation_ref=x0.reshape(-1, 3)), np.zeros(3), C, c)
+    o = SaddleSearch(p)
+    for t in range(6):
+        dyn.step(); o.step()
+        if t == 0:
+            assert p.last_rr[1].shape[1] > 16
+        np.testing.assert_allclose(atoms.positions.ravel(), p.get_x(), rtol=0, atol=1e-6, err_msg="step %d" % t)
