@@ -37,6 +37,7 @@ METRIC = "optimizer steps/sec (batched 3N-DOF Davidson+TR)"
 # dram__bytes_read.sum + dram__bytes_write.sum per sb_secular_update call (three kernels), from the
 # committed ncu --set full captures, keyed by (systems per GPU, 3N)
 NCU_TRAFFIC = {(1024, 384): 3.537e9}     # profiles/ncu_full_r1_h_eigen_update.csv
+NCU_TRAFFIC_HV = {(1024, 384): 1.211e9}  # profiles/ncu_full_r1_a_hv.csv (hv_tma_kernel<1>, one launch)
 UNIT = "system-steps/s"
 
 
@@ -464,22 +465,27 @@ def run_ours(args):
     sec_gbs = sec_bytes / (sec_ms * 1e-3) / 1e9 if sec_ms else 0.0
     # DRAM bytes per launch from `ncu --set full` of the same workload (profiles/ncu_full_r1_h_*.csv)
     traffic = NCU_TRAFFIC.get((b, n))
-    roofline = dict(kernel="eigen-update of (evals, Vt) after the rank-2 secant update: cluster_qr_kernel + "
-                           "cluster_reflect_kernel<2> + secular_update_kernel<4> (one sb_secular_update per step; "
-                           "the largest item of a step)",
-                    bound="hbm", achieved=sec_gbs, peak=peak, unit="GB/s", frac=sec_gbs / peak, traffic=traffic,
-                    ms_per_launch=sec_ms, share_of_step=min(1.0, sec_ms / step_ms) if step_ms else None,
-                    bytes_per_launch=sec_bytes, peak_source=peak_src,
-                    kernels_ms=dict(cluster_qr_kernel=part_ms[0], cluster_reflect_kernel=part_ms[1],
-                                    secular_update_kernel=part_ms[2]),
-                    note="algorithmic bytes = read+write the eigenvector matrix once (2*n^2*8 per system); "
-                         "cluster_reflect streams the degenerate cluster's rows (2 reads + 1 write, the second read "
-                         "mostly from L2); secular_update_kernel is latency-bound (deflation, secular roots, "
-                         "a few dozen rows rewritten), see DESIGN.md section 5")
-    roofline_hv = dict(kernel="hv_tma_kernel<1> (batched H.V / B.s / V^T g)", bound="hbm", achieved=hv_gbs,
-                       peak=peak, unit="GB/s", frac=hv_gbs / peak, frac_of_8TBs_nominal=hv_gbs / 8000.0,
-                       traffic=None, ms_per_launch=hv_ms, bytes_per_launch=hv_bytes, peak_source=peak_src,
-                       launches_per_step="~7 passes over n x n matrices per plain step")
+    roofline_eig = dict(kernel="eigen-update of (evals, Vt) after the rank-2 secant update: cluster_qr_kernel + "
+                               "cluster_reflect_kernel<2> + secular_update_kernel<4> (one sb_secular_update per step; "
+                               "the largest single item of a step)",
+                        bound="hbm", achieved=sec_gbs, peak=peak, unit="GB/s", frac=sec_gbs / peak, traffic=traffic,
+                        ms_per_launch=sec_ms, share_of_step=min(1.0, sec_ms / step_ms) if step_ms else None,
+                        bytes_per_launch=sec_bytes, peak_source=peak_src,
+                        kernels_ms=dict(cluster_qr_kernel=part_ms[0], cluster_reflect_kernel=part_ms[1],
+                                        secular_update_kernel=part_ms[2]),
+                        note="algorithmic bytes = read+write the eigenvector matrix once (2*n^2*8 per system); "
+                             "cluster_reflect streams the degenerate cluster's rows (2 reads + 1 write, the second "
+                             "read mostly from L2); secular_update_kernel is latency-bound (deflation, secular "
+                             "roots, a few dozen rows rewritten), see DESIGN.md section 5")
+    # the dominant kernel family of a step by GPU time (profiles/launches_r1_j.txt: hv_tma / hvt_tma
+    # variants = 41 %): the batched H.V pass, used for V^T g, V c, B s, the surface and Z = Vt P
+    roofline = dict(kernel="hv_tma_kernel<1> (batched H.V: TMA bulk-copy pipeline, one pass over a [b, n, n] matrix; "
+                           "~9 such passes per step, 41 % of GPU time with its <2>/<4>/transposed variants)",
+                    bound="hbm", achieved=hv_gbs, peak=peak, unit="GB/s", frac=hv_gbs / peak,
+                    frac_of_8TBs_nominal=hv_gbs / 8000.0, traffic=NCU_TRAFFIC_HV.get((b, n)), ms_per_launch=hv_ms,
+                    bytes_per_launch=hv_bytes, peak_source=peak_src,
+                    note="read-dominated (the measured copy peak is a read+write figure, hence fractions close to "
+                         "1); algorithmic bytes = 8 (n^2 + 2 n) per system")
     kernel_ms = {k: v[1] for k, v in prof.items()}
     if b * n * n <= 1024 * 768 * 768:             # a full batched eigensolve: seconds beyond this size
         kernel_ms["sb_eigh_full (direct mode only; not on the default path)"] = timed(lambda: eng._eigh(None), 2)
@@ -489,7 +495,7 @@ def run_ours(args):
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                    ms_per_step=step_ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                    data="synthetic", config=workload(args), clocks=clocks, e2e=e2e,
-                   gpu_launches=int(launches), roofline=roofline, roofline_hv=roofline_hv,
+                   gpu_launches=int(launches), roofline=roofline, roofline_eigen_update=roofline_eig,
                    kernel_ms=kernel_ms, systems_flagged=flagged, diagonalisations=eng.ndiag,
                    note="systems_flagged: per-system status words (the batched analogue of the reference's "
                         "exceptions); restricted_step_noconv reproduces the reference's own 'Restricted step "
