@@ -114,3 +114,28 @@ def fcc111_slab(nx, ny, nlayers, a=3.61, vacuum=7.5, seed=None, rattle=0.05):
     if seed is not None:
         pos = pos + rattle * np.random.RandomState(seed).normal(size=pos.shape)
     return pos, cell, (True, True, False)
+
+
+def fcc111_with_adatom(size=(5, 5, 6), a=3.61, vacuum=7.5, height=2.0):
+    """The README example of the reference (README.md:19-20; BASELINE.json config C1) without ASE:
+    ase.build.fcc111('Cu', size, vacuum) -- hexagonal surface cell, ABC stacking, the top layer an
+    fcc continuation of the ones below -- plus one Cu adatom `height` above a bridge site.
+    Returns (positions [nx*ny*nl + 1, 3], cell, pbc)."""
+    nx, ny, nl = size
+    d = a / np.sqrt(2.0)
+    dz = a / np.sqrt(3.0)
+    a1 = np.array([d, 0.0, 0.0])
+    a2 = np.array([0.5 * d, 0.5 * np.sqrt(3.0) * d, 0.0])
+    shift = (a1 + a2) / 3.0
+    pos = []
+    for l in range(nl):
+        off = ((nl - 1 - l) % 3) * shift                # top layer at offset 0, going down A, B, C
+        for j in range(ny):
+            for i in range(nx):
+                p = i * a1 + j * a2 + off
+                pos.append([p[0], p[1], vacuum + l * dz])
+    top = vacuum + (nl - 1) * dz
+    bridge = 0.5 * a1                                    # midway between two neighbouring top-layer atoms
+    pos.append([bridge[0], bridge[1], top + height])
+    cell = np.array([nx * a1, ny * a2, [0.0, 0.0, 2 * vacuum + (nl - 1) * dz]])
+    return np.array(pos), cell, (True, True, False)

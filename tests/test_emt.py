@@ -131,3 +131,51 @@ def test_engine_on_emt_surface_matches_oracle(case):
             np.testing.assert_allclose(x[b], p.get_x(), rtol=0, atol=1e-7, err_msg="system %d step %d" % (b, t))
     eng.check_status()
     np.testing.assert_allclose(C @ eng.x.cpu().numpy().T, (C @ x0.T), atol=1e-10)
+
+
+@pytest.mark.gpu
+def test_readme_example_cu111_adatom():
+    """BASELINE.json config C1 = the reference's README example (README.md:17-38): Cu(111) 5x5x6 slab
+    + adatom on a bridge site, atoms below the middle of the cell fixed with fix_translation,
+    `Sella(slab, constraints=cons).run(1e-3, 1000)` -- here with the EMT-form potential as the
+    calculator.  The search converges in the same number of steps to the same saddle geometry as
+    the oracle loop (north star: converged geometries within 1e-6 Angstrom)."""
+    torch = pytest.importorskip("torch")
+    from sella_b200 import Sella, Constraints
+    from sella_b200.synthetic import fcc111_with_adatom
+    from oracle.pes import CartesianPES
+    from oracle.driver import SaddleSearch
+    pos, cell, pbc = fcc111_with_adatom()
+    assert len(pos) == 151
+    func = oemt.emt_func(cell, pbc)
+
+    class Slab:                                     # the part of ase.Atoms the optimiser touches
+        def __init__(self):
+            self.positions = pos.copy()
+            self.pbc = np.array(pbc)
+            self.cell = cell
+        def __len__(self): return len(self.positions)
+        def get_potential_energy(self): return func(self.positions.ravel())[0]
+        def get_forces(self): return -func(self.positions.ravel())[1].reshape(-1, 3)
+    slab = Slab()
+    cons = Constraints(slab)
+    nfixed = 0
+    for i, p in enumerate(slab.positions):
+        if p[2] < cell[2, 2] / 2.0:
+            cons.fix_translation(i)
+            nfixed += 1
+    assert nfixed == 75 and cons.ncons == 225
+    dyn = Sella(slab, constraints=cons, logfile=None)
+    conv = dyn.run(1e-3, 1000)
+    assert conv
+    C, c = cons.linear_system()
+    ref = CartesianPES(func, pos.ravel(), C, c)
+    o = SaddleSearch(ref)
+    assert o.run(1e-3, 1000)
+    assert dyn.nsteps == o.nsteps
+    np.testing.assert_allclose(slab.positions.ravel(), ref.get_x(), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(dyn.pes.get_f(), ref.curr["f"], rtol=0, atol=1e-9)
+    # the fixed atoms have not moved; the model Hessian has exactly one negative mode in the free space
+    fixed = np.nonzero(pos[:, 2] < cell[2, 2] / 2.0)[0]
+    np.testing.assert_array_equal(slab.positions[fixed], pos[fixed])
+    assert int((dyn.pes.H.evals < 0).sum()) == 1
