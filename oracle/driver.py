@@ -66,7 +66,10 @@ class SaddleSearch:
         if not self.initialized:
             pes.get_g()
             if self.eig:
-                pes.diag(**self.diagkwargs)
+                if getattr(pes, "hessian_function", None) is not None:     # optimize.py:321-324
+                    pes.calculate_hessian()
+                else:
+                    pes.diag(**self.diagkwargs)
                 self.nsteps_since_diag = -1
             self.initialized = True
         pes._update_basis()

@@ -202,13 +202,14 @@ class CartesianPES:
     n_cell_dof = 0
 
     def __init__(self, func, x0, C=None, c=None, eta=1e-4, v0=None,
-                 eigensolver="jd0", H0=None):
+                 eigensolver="jd0", H0=None, hessian_function=None):
         self.func = func
         self.x = np.array(x0, dtype=float)
         self.dim = self.ncart = len(self.x)
         self.C = np.zeros((0, self.dim)) if C is None else np.asarray(C, float)
         self.c = np.zeros(self.C.shape[0]) if c is None else np.asarray(c, float)
         self.eta, self.v0, self.eigensolver = eta, v0, eigensolver
+        self.hessian_function = hessian_function          # x -> (n, n); peswrapper.py:228,290
         self.H = ApproxHessian(self.dim, self.ncart, H0, initialized=H0 is not None)
         self.neval = 0
         self.first_diag = True
@@ -358,8 +359,15 @@ class CartesianPES:
         if self.last["x"] is not None and self.last["g"] is not None:
             self.H.update(dx_f, dg)
         if diag:
-            self.diag(**diag_kwargs)
+            if self.hessian_function is not None:         # peswrapper.py:596-600
+                self.calculate_hessian()
+            else:
+                self.diag(**diag_kwargs)
         return ratio
+
+    def calculate_hessian(self):
+        """peswrapper.py:604-606."""
+        self.H.set_B(np.array(self.hessian_function(self.get_x()), dtype=float))
 
 
 class NonlinearPES(CartesianPES):

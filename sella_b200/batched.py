@@ -62,7 +62,7 @@ class BatchedSella:
                  rho_dec=None, rho_inc=None, eig=None, eta=1e-4, method=None, gamma=0.1,
                  rs=None, nsteps_per_diag=3, diag_every_n=None, diag_maxiter=None,
                  eigensolver="jd0", update_method="TS-BFGS", kcap=16, eig_mode="update",
-                 eig_refresh_every=0, constraints=None, threepoint=False):
+                 eig_refresh_every=0, constraints=None, threepoint=False, hessian_function=None, v0=None):
         require_cuda()
         d = _DEFAULTS["minimum" if order == 0 else "saddle"]
         self.surface = surface
@@ -94,6 +94,10 @@ class BatchedSella:
         self.eta = float(eta)
         self.gamma = float(gamma)
         self.threepoint = bool(threepoint)
+        # hessian_function(x[b,n]) -> B[b,n,n] (device tensors) replaces every Davidson diagonalisation
+        # (peswrapper.py:597-606, optimize.py:321-324); v0[b,n]: start vector of the first one (:524)
+        self.hessian_function = hessian_function
+        self.v0 = v0
         self.diag_maxiter = diag_maxiter
         if eigensolver not in _EIGENSOLVERS:
             raise NotImplementedError("eigensolver %r is not available on the batched path" % eigensolver)
@@ -441,6 +445,25 @@ class BatchedSella:
             self.eig_valid = False
             self._updates_since_refresh = 0
 
+    def _calculate_hessian(self, part=None):
+        """PES.calculate_hessian (peswrapper.py:604-606): B <- hessian_function at the current
+        geometry (for the systems with part[b] != 0), spectra by full eigensolves."""
+        Bnew = self.hessian_function(self.x)
+        check_f64(Bnew)
+        Bnew = 0.5 * (Bnew + Bnew.transpose(1, 2))
+        if part is None:
+            self.B.copy_(Bnew)
+        else:
+            m = part.to(torch.bool)
+            self.B[m] = Bnew[m]
+        self.H_initialized = True
+        if self.eig_mode == "update":
+            self._direct_spectra()
+            self.eig_valid = True
+        else:
+            self.eig_valid = False
+        self.ndiag += 1
+
     def _direct_spectra(self):
         """Full eigensolves of B (and, with linear constraints, of Bp = P_f B P_f + sigma P_c)."""
         b, n = self.batch, self.n
@@ -504,6 +527,11 @@ class BatchedSella:
         if not first and not self.eig_valid:
             self._eigh(active=part)             # spectrum of the preconditioner P = B
         v0 = self.g
+        if first and self.v0 is not None:
+            if self.cons is not None:
+                raise NotImplementedError("v0 lives in the reference's free-space basis; only without constraints")
+            check_f64(self.v0)
+            v0 = self.v0
         if self.cons is not None and first:
             v0 = self.cons["pg"]
             v0.copy_(self.g)
@@ -566,7 +594,10 @@ class BatchedSella:
         if not self.initialized:
             self.surface.evaluate(self.x, self.f, self.g)
             if self.eig:
-                self._diag(None)
+                if self.hessian_function is not None:
+                    self._calculate_hessian()
+                else:
+                    self._diag(None)
                 self.since_diag.fill_(-1)
             self.initialized = True
         # ---- _predict_step: restricted step from the spectral model
@@ -649,7 +680,10 @@ class BatchedSella:
              _p(self.nsteps), self._dpar, self._ipar, I(n), _p(active), I(b), _stream())
         self._update(S1, self.dg.view(b, 1, n), self.up1, None, 1, active, bs_ready=True, abs_ready=abs_ready)
         if self.eig and int(self.ev.sum().item()) > 0:
-            self._diag(self.ev)
+            if self.hessian_function is not None:
+                self._calculate_hessian(self.ev)
+            else:
+                self._diag(self.ev)
 
     def converged(self, fmax, cmax=1e-5):
         """PES.converged (peswrapper.py:558-568): max atomic |P_f g| < fmax and |res| < cmax."""

@@ -15,7 +15,7 @@ coordinates; translation constraints (``sella_b200.Constraints.fix_translation``
 the centre-of-geometry projection the reference adds by default, peswrapper.py:233-244) and
 bond / angle / dihedral constraints (``fix_bond``, ``fix_angle``, ``fix_dihedral``);
 the rotation projection of non-periodic systems (``fix_rotation`` of the whole configuration,
-peswrapper.py:246-253); no ``hessian_function``, no cell optimisation.
+peswrapper.py:246-253); ``hessian_function`` and (without constraints) ``v0``; no cell optimisation.
 """
 import warnings
 from time import localtime, strftime
@@ -131,8 +131,8 @@ class Sella(_Base):
                  hessian_function=None, optimize_cell=False, **kwargs):
         if internal:
             raise NotImplementedError("internal coordinates are not on the CUDA path yet")
-        if optimize_cell or hessian_function is not None or v0 is not None:
-            raise NotImplementedError("optimize_cell / hessian_function / v0 are not on the CUDA path")
+        if optimize_cell:
+            raise NotImplementedError("optimize_cell is not on the CUDA path")
         pbc = np.asarray(getattr(atoms, "pbc", [False] * 3))
         proj_trans = kwargs.pop("proj_trans", None)
         proj_rot = kwargs.pop("proj_rot", None)
@@ -173,13 +173,28 @@ class Sella(_Base):
                                  sigma_dec=sigma_dec, rho_dec=rho_dec, rho_inc=rho_inc, eig=eig, eta=eta,
                                  method=method, gamma=gamma, rs=rs, nsteps_per_diag=nsteps_per_diag,
                                  diag_every_n=diag_every_n, eigensolver=eigensolver, kcap=32, threepoint=threepoint,
-                                 diag_maxiter=diag_maxiter,
+                                 diag_maxiter=diag_maxiter, hessian_function=self._wrap_hessian(hessian_function),
+                                 v0=None if v0 is None else torch.from_numpy(
+                                     np.asarray(v0, dtype=np.float64).reshape(1, -1).copy()).to(dev()),
                                  constraints=self._engine_constraints(lin, nonlin, x0))
         self.pes = _PESView(self)
         self.ord = order
         self.eta = eta
         self.constraints_tol = constraints_tol
         self.fmax = None
+
+    def _wrap_hessian(self, fn):
+        """hessian_function(atoms) -> (3N, 3N) ndarray, as in the reference (optimize.py:76)."""
+        if fn is None:
+            return None
+
+        def device_fn(x):
+            old = self.atoms.positions.copy()
+            self.atoms.positions = x[0].cpu().numpy().reshape((-1, 3))
+            H = np.asarray(fn(self.atoms), dtype=np.float64)
+            self.atoms.positions = old
+            return torch.from_numpy(np.ascontiguousarray(H[None])).to(x.device)
+        return device_fn
 
     @staticmethod
     def _engine_constraints(lin, nonlin, x0):

@@ -350,3 +350,58 @@ def test_engine_with_position_dependent_constraints(case):
     for b, (p, o) in enumerate(oracles):
         np.testing.assert_allclose(eng.cons["res"][b].cpu().numpy(), p.get_res(), atol=1e-7)
         assert np.abs(p.get_res()).max() < 0.05          # the (curved) constraint surface is being tracked
+
+
+def test_engine_with_hessian_function_and_v0():
+    """hessian_function (exact Hessians replace every Davidson run, peswrapper.py:596-606,
+    optimize.py:321-324) and a user start vector v0 for the first diagonalisation (:524)."""
+    from oracle.pes import CartesianPES
+    from oracle.driver import SaddleSearch
+    from sella_b200.synthetic import quadratic_func
+    n, systems = 30, [0, 1, 2]
+    # 1. exact Hessian of a mildly anharmonic surface: f = quadratic + 0.05 sum (x - x*)^4
+    from sella_b200.batched import BatchedSella
+
+    class Quartic:
+        def __init__(self, A, xs):
+            self.A, self.xs, self.neval = A, xs, 0
+        def evaluate(self, x, f_out, g_out, active=None):
+            self.neval += 1
+            d = x - self.xs
+            g = torch.einsum("bij,bj->bi", self.A, d) + 0.2 * d ** 3
+            f_out.copy_(0.5 * (d * torch.einsum("bij,bj->bi", self.A, d)).sum(1) + 0.05 * (d ** 4).sum(1))
+            g_out.copy_(g)
+    from sella_b200.synthetic import quadratic_system
+    data = [quadratic_system(b, n) for b in systems]
+    A = to_dev(np.stack([d[0] for d in data])); xs = to_dev(np.stack([d[1] for d in data])); x0 = np.stack([d[2] for d in data])
+    hess_dev = lambda x: A + torch.diag_embed(0.6 * (x - xs) ** 2)
+    eng = BatchedSella(Quartic(A, xs), to_dev(x0), method="prfo", rs="tr", hessian_function=hess_dev, diag_every_n=2)
+    oracles = []
+    for (Ai, xsi, x0i) in data:
+        func = (lambda Ai, xsi: lambda x: (0.5 * (x - xsi) @ Ai @ (x - xsi) + 0.05 * ((x - xsi) ** 4).sum(),
+                                           Ai @ (x - xsi) + 0.2 * (x - xsi) ** 3))(Ai, xsi)
+        hf = (lambda Ai, xsi: lambda x: Ai + np.diag(0.6 * (x - xsi) ** 2))(Ai, xsi)
+        p = CartesianPES(func, x0i, hessian_function=hf)
+        oracles.append((p, SaddleSearch(p, method="prfo", rs="tr", diag_every_n=2)))
+    for t in range(8):
+        eng.step()
+        x = eng.x.cpu().numpy()
+        for i, (p, o) in enumerate(oracles):
+            o.step()
+            np.testing.assert_allclose(x[i], p.get_x(), rtol=0, atol=1e-8, err_msg="system %d step %d" % (i, t))
+    eng.check_status()
+    assert eng.surface.neval == oracles[0][0].neval          # no finite-difference evaluations at all
+    # 2. v0
+    rng = np.random.RandomState(9)
+    v0 = rng.normal(size=(len(systems), n))
+    eng2, data2 = make_engine(n, systems, method="qn", rs="tr", v0=to_dev(v0), diag_maxiter=6)
+    for i, (Ai, xsi, x0i) in enumerate(data2):
+        p = CartesianPES(quadratic_func(Ai, xsi), x0i, v0=v0[i])
+        o = SaddleSearch(p, method="qn", rs="tr", diag_maxiter=6)
+        for t in range(4):
+            o.step()
+        oracles[i] = (p, o)
+    for t in range(4):
+        eng2.step()
+    for i, (p, o) in enumerate(oracles):
+        np.testing.assert_allclose(eng2.x[i].cpu().numpy(), p.get_x(), rtol=0, atol=1e-8)
