@@ -1,0 +1,93 @@
+"""Host-side logic that needs no GPU: the Constraints bookkeeping (sella/internal.py:2748-3030
+semantics), the bench workload builders and the synthetic geometries."""
+import numpy as np
+import pytest
+
+
+class _Atoms:
+    def __init__(self, pos):
+        self.positions = np.array(pos, dtype=float)
+    def __len__(self):
+        return len(self.positions)
+
+
+def test_constraints_bookkeeping():
+    from sella_b200.constraints import Constraints, DuplicateConstraintError
+    rng = np.random.RandomState(0)
+    atoms = _Atoms(rng.normal(size=(6, 3)))
+    cons = Constraints(atoms)
+    cons.fix_translation(2)                               # three rows of the identity
+    cons.fix_translation((0, 1, 3), dim=1)                # mean y of a group
+    cons.fix_translation()                                # centre of geometry
+    assert cons.ncons == 3 + 1 + 3
+    C, c = cons.linear_system()
+    assert C.shape == (7, 18)
+    np.testing.assert_allclose(C @ atoms.positions.ravel(), c)            # satisfied at the start geometry
+    np.testing.assert_allclose(C[3, [1, 4, 10]], 1.0 / 3)
+    np.testing.assert_allclose(C[4:].sum(axis=1), 1.0)
+    np.testing.assert_allclose(cons.residual(), 0.0, atol=1e-15)
+    # replace_ok semantics (internal.py:2894-2904)
+    cons.fix_translation(2, dim=0, target=1.5)
+    assert cons.linear_system()[1][0] == 1.5 and cons.ncons == 7
+    with pytest.raises(DuplicateConstraintError):
+        cons.fix_translation(2, dim=0, replace_ok=False)
+    with pytest.raises(ValueError):
+        cons.fix_translation(2, target=0.0)               # "target" needs an explicit "dim"
+    # position-dependent kinds: bookkeeping only (the kernels need a GPU)
+    cons.fix_bond((4, 1), target=2.0)
+    cons.fix_bond((1, 4), target=2.2)                     # same bond, reversed: replaces the target
+    cons.fix_angle((0, 1, 2), target=90.0)                # degrees, as in the reference
+    cons.fix_dihedral((0, 1, 2, 3))
+    assert cons.nnonlinear == 3 and cons.ncons == 10
+    assert cons._nl["bonds"] == [((1, 4), 2.2)]
+    np.testing.assert_allclose(cons._nl["angles"][0][1], np.pi / 2)
+    with pytest.raises(DuplicateConstraintError):
+        cons.fix_angle((2, 1, 0), replace_ok=False)
+    with pytest.raises(NotImplementedError):
+        cons.fix_bond((0, 5), comparator="lt")
+    with pytest.raises(NotImplementedError):
+        cons.fix_rotation((0, 1, 2))                      # fragments: not on the CUDA path
+    cons.fix_rotation()
+    assert cons.ncons == 13 and len(cons.internals["rotations"]) == 3
+
+
+def test_synthetic_geometries():
+    from sella_b200.synthetic import fcc_cluster, fcc111_slab, fcc111_with_adatom, quadratic_system
+    a = 3.61
+    nn = a / np.sqrt(2)
+    pos = fcc_cluster(64, seed=0, rattle=0.0)
+    d = np.linalg.norm(pos[:, None] - pos[None], axis=-1) + 10 * np.eye(64)
+    np.testing.assert_allclose(d.min(), nn, rtol=1e-12)
+    np.testing.assert_allclose(pos.mean(0), 0, atol=1e-12)
+    p, cell, pbc = fcc111_slab(4, 2, 8)
+    assert len(p) == 128 and pbc == (True, True, False)
+    p, cell, pbc = fcc111_with_adatom()
+    assert len(p) == 151
+    # every slab atom has 6 in-plane neighbours at the nearest-neighbour distance (through the cell)
+    top = p[125:150]
+    cnt = 0
+    for i in (-1, 0, 1):
+        for j in (-1, 0, 1):
+            dd = np.linalg.norm(top[:, None] - (top[None] + i * cell[0] + j * cell[1]), axis=-1)
+            cnt += (np.abs(dd - nn) < 1e-9).sum(axis=1)
+    assert (cnt == 6).all()
+    # the adatom sits 2 A above the bridge between two top-layer atoms
+    np.testing.assert_allclose(p[-1, 2] - top[:, 2].max(), 2.0)
+    np.testing.assert_allclose(sorted(np.linalg.norm(top[:, :2] - p[-1, :2], axis=1))[:2], [nn / 2, nn / 2])
+    assert (p[:, 2] < cell[2, 2] / 2).sum() == 75
+    A, xs, x0 = quadratic_system(3, 24)
+    w = np.linalg.eigvalsh(A)
+    assert (w < 0).sum() == 1 and abs(w[0] + 0.5) < 1e-12
+
+
+def test_bench_workload_builders():
+    import argparse
+    import bench
+    ns = argparse.Namespace(workload="emt-slab", n=384)
+    X0, C, cell, pbc = bench.emt_problem(ns, 5, 2)
+    assert X0.shape == (2, 384) and C.shape == (192, 384) and pbc == (True, True, False)
+    assert (C.sum(axis=1) == 1).all() and (C.sum(axis=0) <= 1).all()
+    ns = argparse.Namespace(workload="emt-cluster", n=192)
+    X0, C, cell, pbc = bench.emt_problem(ns, 0, 3)
+    assert X0.shape == (3, 192) and C.shape == (3, 192) and cell is None
+    np.testing.assert_allclose(C @ X0[0], X0[0].reshape(-1, 3).mean(0))
