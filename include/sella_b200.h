@@ -277,14 +277,18 @@ int sb_rotation(const double* x, int natoms, const double* refpos, long long ref
  *             B+^T g_cart, Binv = R^-1 Q^T, Hc = B+^T (D_c - D_q) B+, get_df_pred.
  *   sb_qr   : economy Householder QR of A [b, m, n] (m >= n; A is overwritten with the reflectors),
  *             Q [b, m, n] with orthonormal columns, R [b, n, n] upper triangular (LAPACK signs):
- *             gpu_qr (_gpu.py:100-111), _get_jacobian_qr (peswrapper.py:674-709).
- *   sb_trtri: Rinv [b, n, n] = R^-1 (upper triangular); SB_ST_SINGULAR on a zero diagonal.      */
+ *             gpu_qr (_gpu.py:100-111), _get_jacobian_qr (peswrapper.py:674-709).  Blocked (panels of
+ *             16 columns, compact WY, trailing updates as sb_gemm); work: batch * (m*n + 32*n +
+ *             256*ceil(n/16)) doubles.
+ *   sb_trtri: Rinv [b, n, n] = R^-1 (upper triangular; diagonal blocks of <= 48 by back substitution,
+ *             assembled with sb_gemm); work: batch*n*n doubles; SB_ST_SINGULAR on a zero diagonal. */
 int sb_gemm(int transA, int transB, int M, int N, int K, double alpha, const double* A, int lda,
             long long strideA, const double* B, int ldb, long long strideB, double beta, double* C,
             int ldc, long long strideC, const int32_t* active, int batch, void* stream);
-int sb_qr(double* A, int m, int n, double* Q, double* R, const int32_t* active, int batch, void* stream);
-int sb_trtri(const double* R, double* Rinv, int n, int32_t* status, const int32_t* active, int batch,
-             void* stream);
+int sb_qr(double* A, int m, int n, double* Q, double* R, double* work, const int32_t* active, int batch,
+          void* stream);
+int sb_trtri(const double* R, double* Rinv, double* work, int n, int32_t* status, const int32_t* active,
+             int batch, void* stream);
 
 /* ---- per-step bookkeeping (sella/peswrapper.py:578-602, optimize/optimize.py:362-434) ----
  * dpar = {rho_inc, rho_dec, sigma_inc, sigma_dec, delta_min} (host array of 5 doubles),

@@ -255,8 +255,8 @@ int sb_lowrank_factor(const double* U, const double* J, const double* Cmat, int 
 extern "C" int sb_secular_profile_impl(unsigned long long*, int);
 extern "C" int sb_gemm_impl(int, int, int, int, int, double, const double*, int, long long, const double*, int, long long,
                             double, double*, int, long long, const int*, int, cudaStream_t);
-extern "C" int sb_qr_impl(double*, int, int, double*, double*, const int*, int, cudaStream_t);
-extern "C" int sb_trtri_impl(const double*, double*, int, int*, const int*, int, cudaStream_t);
+extern "C" int sb_qr_impl(double*, int, int, double*, double*, double*, const int*, int, cudaStream_t);
+extern "C" int sb_trtri_impl(const double*, double*, double*, int, int*, const int*, int, cudaStream_t);
 int sb_gemm(int transA, int transB, int M, int N, int K, double alpha, const double* A, int lda, long long strideA,
             const double* B, int ldb, long long strideB, double beta, double* C, int ldc, long long strideC,
             const int32_t* active, int batch, void* stream) {
@@ -264,13 +264,15 @@ int sb_gemm(int transA, int transB, int M, int N, int K, double alpha, const dou
     return sb_gemm_impl(transA, transB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc, strideC, active,
                         batch, (cudaStream_t)stream);
 }
-int sb_qr(double* A, int m, int n, double* Q, double* R, const int32_t* active, int batch, void* stream) {
-    if (m < n || n < 1 || batch < 1) return -1;
-    return sb_qr_impl(A, m, n, Q, R, active, batch, (cudaStream_t)stream);
+int sb_qr(double* A, int m, int n, double* Q, double* R, double* work, const int32_t* active, int batch,
+          void* stream) {
+    if (m < n || n < 1 || batch < 1 || !work) return -1;
+    return sb_qr_impl(A, m, n, Q, R, work, active, batch, (cudaStream_t)stream);
 }
-int sb_trtri(const double* R, double* Rinv, int n, int32_t* status, const int32_t* active, int batch, void* stream) {
-    if (n < 1 || batch < 1) return -1;
-    return sb_trtri_impl(R, Rinv, n, status, active, batch, (cudaStream_t)stream);
+int sb_trtri(const double* R, double* Rinv, double* work, int n, int32_t* status, const int32_t* active, int batch,
+             void* stream) {
+    if (n < 1 || batch < 1 || !work) return -1;
+    return sb_trtri_impl(R, Rinv, work, n, status, active, batch, (cudaStream_t)stream);
 }
 extern "C" int sb_rotation_impl(const double*, int, const double*, long long, double*, double*, long long, double*,
                                 long long, const double*, long long, double*, double*, const int*, int, cudaStream_t);

@@ -1,6 +1,7 @@
 // Batched dense fp64 linear algebra for the internal-coordinate path:
 //   sb_gemm   C = alpha op(A) op(B) + beta C         DMMA (mma.sync m8n8k4 f64) tensor-core tiles
-//   sb_qr     economy Householder QR  A = Q R         sella/_gpu.py:100-111 (gpu_qr),
+//   sb_qr     economy Householder QR  A = Q R  (blocked, compact WY; trailing updates are GEMMs)
+//                                                     sella/_gpu.py:100-111 (gpu_qr),
 //                                                     sella/peswrapper.py:674-709 (_get_jacobian_qr)
 //   sb_trtri  inverse of the upper-triangular R        sella/peswrapper.py:711-736 (_get_Binv:
 //                                                     Binv = R^-1 Q^T = sb_gemm(trtri(R), Q^T))
@@ -91,108 +92,172 @@ gemm_kernel(int transA, int transB, int M, int N, int K, double alpha, const dou
 }
 
 constexpr int QR_THREADS = 256;
+constexpr int QR_NB = 16;          // panel width
 
-// In-place unblocked Householder QR of A [m, n] (row-major, m >= n), LAPACK dgeqr2 conventions
-// (v_j[j] = 1 implicit, H_j = I - tau_j v_j v_j^T, R = upper triangle, beta_j = -sign(alpha)|x|),
-// followed by the explicit economy Q [m, n] (dorg2r) and R [n, n].  One CTA per system; threads
-// own columns, so every access to a matrix row is coalesced and the two passes over the trailing
-// block (w = v^T A, A -= tau v w^T) need no barrier between them.
+// Blocked Householder QR (LAPACK dgeqrf / dorgqr scheme, compact WY):
+//   for each panel of QR_NB columns: qr_panel_kernel factors it in shared memory (dgeqr2 on an
+//   m' x 16 block), writes R's rows, the explicit reflector block V (unit lower trapezoid, zeros
+//   above) and the triangular factor T (dlarft); the trailing block then gets
+//   A22 <- (I - V T^T V^T) A22 as three DMMA GEMMs (W1 = V^T A22, W2 = T^T W1, A22 -= V W2);
+//   Q = H_0 ... H_{n-1} [I; 0] is accumulated backwards, panel by panel, the same way
+//   (Q22 <- (I - V T V^T) Q22).
+// Conventions as dgeqr2: v_j[j] = 1, H_j = I - tau_j v_j v_j^T, beta_j = -sign(alpha)|x|.
+//
+// Panel kernel: one CTA per system.  Ap = A + p0*n + p0 (leading dimension n), mp = m - p0 rows,
+// nb columns.  Vp [b, m, n] receives the explicit V of this panel at rows p0.., columns p0..p0+nb.
 __global__ void __launch_bounds__(QR_THREADS)
-qr_kernel(double* __restrict__ A_, int m, int n, double* __restrict__ Q_, double* __restrict__ R_,
-          const int* __restrict__ active) {
+qr_panel_kernel(double* __restrict__ A_, int m, int n, int p0, int nb, double* __restrict__ Vp_,
+                double* __restrict__ T_, double* __restrict__ R_, const int* __restrict__ active) {
     const int b = blockIdx.x;
     if (active && !active[b]) return;
     extern __shared__ double sm[];
-    double* v = sm;                         // m
-    double* tau = v + m;                    // n
-    double* scratch = tau + n;              // SB_SCRATCH_DOUBLES
+    const int mp = m - p0;
+    double* P = sm;                              // [nb][mp] column-major panel
+    double* tau = P + (size_t)nb * mp;           // nb
+    double* Tm = tau + QR_NB;                    // QR_NB x QR_NB
+    double* dots = Tm + QR_NB * QR_NB;           // QR_NB
+    double* scratch = dots + QR_NB;              // SB_SCRATCH_DOUBLES
     double* A = A_ + (size_t)b * m * n;
-    double* Q = Q_ + (size_t)b * m * n;
+    double* Vp = Vp_ + (size_t)b * m * n;
     double* R = R_ + (size_t)b * n * n;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int j = 0; j < n; ++j) {
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    for (int idx = tid; idx < mp * nb; idx += nt) {
+        const int i = idx / nb, c = idx % nb;
+        P[(size_t)c * mp + i] = A[(size_t)(p0 + i) * n + p0 + c];
+    }
+    __syncthreads();
+    for (int j = 0; j < nb; ++j) {
+        double* col = P + (size_t)j * mp;
         double acc = 0.0;
-        for (int i = j + 1 + tid; i < m; i += nt) { const double x = A[(size_t)i * n + j]; v[i] = x; acc = fma(x, x, acc); }
+        for (int i = j + 1 + tid; i < mp; i += nt) acc = fma(col[i], col[i], acc);
         const double sigma = sb_block_sum(acc, scratch);
-        const double alpha = A[(size_t)j * n + j];
+        const double alpha = col[j];
         double tj = 0.0;
         if (sigma > 0.0) {
             const double nrm = sqrt(alpha * alpha + sigma);
             const double beta = alpha >= 0.0 ? -nrm : nrm;
             tj = (beta - alpha) / beta;
             const double scale = 1.0 / (alpha - beta);
-            for (int i = j + 1 + tid; i < m; i += nt) { const double x = v[i] * scale; v[i] = x; A[(size_t)i * n + j] = x; }
-            if (tid == 0) A[(size_t)j * n + j] = beta;
+            __syncthreads();
+            for (int i = j + 1 + tid; i < mp; i += nt) col[i] *= scale;
+            if (tid == 0) col[j] = beta;
         }
-        if (tid == 0) { tau[j] = tj; v[j] = 1.0; }
+        if (tid == 0) tau[j] = tj;
         __syncthreads();
         if (tj != 0.0) {
-            for (int c = j + 1 + tid; c < n; c += nt) {
-                double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
-                int i = j;
-                for (; i + 3 < m; i += 4) {
-                    w0 = fma(v[i], A[(size_t)i * n + c], w0);
-                    w1 = fma(v[i + 1], A[(size_t)(i + 1) * n + c], w1);
-                    w2 = fma(v[i + 2], A[(size_t)(i + 2) * n + c], w2);
-                    w3 = fma(v[i + 3], A[(size_t)(i + 3) * n + c], w3);
-                }
-                for (; i < m; ++i) w0 = fma(v[i], A[(size_t)i * n + c], w0);
-                const double w = tj * ((w0 + w1) + (w2 + w3));
-                for (i = j; i < m; ++i) A[(size_t)i * n + c] = fma(-w, v[i], A[(size_t)i * n + c]);
+            // w_c = v^T P[:, c] (v_j = 1 implicit), then P[:, c] -= tau w_c v   for the later columns
+            for (int c = j + 1 + warp; c < nb; c += nw) {
+                double* pc = P + (size_t)c * mp;
+                const double pj = pc[j];
+                double d = 0.0;
+                for (int i = j + 1 + lane; i < mp; i += 32) d = fma(col[i], pc[i], d);
+                d = sb_warp_sum(d) + pj;
+                const double w = tj * d;
+                __syncwarp();
+                if (lane == 0) pc[j] = pj - w;
+                for (int i = j + 1 + lane; i < mp; i += 32) pc[i] = fma(-w, col[i], pc[i]);
             }
         }
         __syncthreads();
     }
-    // R and Q = H_0 ... H_{n-1} [I; 0]
-    for (int idx = tid; idx < n * n; idx += nt) {
-        const int i = idx / n, c = idx % n;
-        R[idx] = c >= i ? A[(size_t)i * n + c] : 0.0;
-    }
-    for (int idx = tid; idx < m * n; idx += nt) Q[idx] = (idx / n == idx % n) ? 1.0 : 0.0;
-    __syncthreads();
-    for (int j = n - 1; j >= 0; --j) {
-        for (int i = j + 1 + tid; i < m; i += nt) v[i] = A[(size_t)i * n + j];
-        if (tid == 0) v[j] = 1.0;
-        __syncthreads();
-        const double tj = tau[j];
-        if (tj != 0.0) {
-            for (int c = j + tid; c < n; c += nt) {
-                double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
-                int i = j;
-                for (; i + 3 < m; i += 4) {
-                    w0 = fma(v[i], Q[(size_t)i * n + c], w0);
-                    w1 = fma(v[i + 1], Q[(size_t)(i + 1) * n + c], w1);
-                    w2 = fma(v[i + 2], Q[(size_t)(i + 2) * n + c], w2);
-                    w3 = fma(v[i + 3], Q[(size_t)(i + 3) * n + c], w3);
-                }
-                for (; i < m; ++i) w0 = fma(v[i], Q[(size_t)i * n + c], w0);
-                const double w = tj * ((w0 + w1) + (w2 + w3));
-                for (i = j; i < m; ++i) Q[(size_t)i * n + c] = fma(-w, v[i], Q[(size_t)i * n + c]);
-            }
+    // T (dlarft, forward, columnwise): T[j][j] = tau_j, T[0:j, j] = -tau_j T[0:j,0:j] (V[:,0:j]^T v_j)
+    for (int j = 0; j < nb; ++j) {
+        for (int i = warp; i < j; i += nw) {          // dots[i] = v_i . v_j  (unit diagonals implicit)
+            const double* vi = P + (size_t)i * mp;
+            const double* vj = P + (size_t)j * mp;
+            double d = 0.0;
+            for (int r = j + 1 + lane; r < mp; r += 32) d = fma(vi[r], vj[r], d);
+            d = sb_warp_sum(d) + vi[j];               // row j: v_j[j] = 1, v_i[j] stored
+            if (lane == 0) dots[i] = d;
         }
         __syncthreads();
+        if (tid == 0) {
+            for (int i = 0; i < j; ++i) {
+                double acc = 0.0;
+                for (int l = i; l < j; ++l) acc += Tm[i * QR_NB + l] * dots[l];
+                Tm[i * QR_NB + j] = -tau[j] * acc;
+            }
+            Tm[j * QR_NB + j] = tau[j];
+            for (int i = j + 1; i < QR_NB; ++i) Tm[i * QR_NB + j] = 0.0;
+        }
+        __syncthreads();
+    }
+    // write back: R rows of this panel (columns p0..p0+nb), explicit V, reflectors into A, T
+    for (int idx = tid; idx < mp * nb; idx += nt) {
+        const int i = idx / nb, c = idx % nb;
+        const double val = P[(size_t)c * mp + i];
+        A[(size_t)(p0 + i) * n + p0 + c] = val;
+        Vp[(size_t)(p0 + i) * n + p0 + c] = i > c ? val : (i == c ? 1.0 : 0.0);
+        if (i <= c) R[(size_t)(p0 + i) * n + p0 + c] = val;
+    }
+    for (int i = tid; i < QR_NB * QR_NB; i += nt) {
+        const int r = i / QR_NB, c = i % QR_NB;
+        T_[(size_t)b * QR_NB * QR_NB + i] = (r < nb && c < nb) ? Tm[i] : 0.0;
     }
 }
 
-// Rinv = R^-1 for upper-triangular R [n, n] (row-major).  Thread j owns column j of the
-// inverse (back substitution); status bit SB_ST_SINGULAR on a zero diagonal.
-__global__ void __launch_bounds__(256)
-trtri_kernel(const double* __restrict__ R_, double* __restrict__ X_, int n, int* __restrict__ status,
-             const int* __restrict__ active) {
+// R[p0.., p0+nb..] rows of the panel right of it (copied out after the trailing update), zero lower part
+__global__ void qr_copy_r_kernel(const double* __restrict__ A_, int m, int n, double* __restrict__ R_,
+                                 const int* __restrict__ active) {
     const int b = blockIdx.y;
     if (active && !active[b]) return;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * n) return;
+    const int i = idx / n, c = idx % n;
+    R_[(size_t)b * n * n + idx] = c >= i ? A_[(size_t)b * m * n + (size_t)i * n + c] : 0.0;
+}
+
+__global__ void qr_init_q_kernel(double* __restrict__ Q_, int m, int n, const int* __restrict__ active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= m * n) return;
+    Q_[(size_t)b * m * n + idx] = (idx / n == idx % n) ? 1.0 : 0.0;
+}
+
+// Inverse of an upper-triangular diagonal block R[r0:r0+sz, r0:r0+sz] (sz <= 48) of a row-major
+// [n, n] matrix into the same block of X; thread j owns column j of the block (back substitution).
+// Status bit SB_ST_SINGULAR on a zero diagonal.  Larger matrices are assembled from such blocks by
+// the block formula  inv([[R11, R12], [0, R22]]) = [[X11, -X11 R12 X22], [0, X22]]  with DMMA GEMMs.
+constexpr int TRI_BS = 48;          // 2 x 48 x 49 doubles of static shared memory
+__global__ void __launch_bounds__(64)
+trtri_block_kernel(const double* __restrict__ R_, double* __restrict__ X_, int n, int r0, int sz,
+                   int* __restrict__ status, const int* __restrict__ active) {
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    __shared__ double Rs[TRI_BS][TRI_BS + 1];
+    __shared__ double Xs[TRI_BS][TRI_BS + 1];
     const double* R = R_ + (size_t)b * n * n;
     double* X = X_ + (size_t)b * n * n;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    for (int i = n - 1; i > j; --i) X[(size_t)i * n + j] = 0.0;
-    for (int i = j; i >= 0; --i) {
-        double acc = (i == j) ? 1.0 : 0.0;
-        for (int k = i + 1; k <= j; ++k) acc = fma(-R[(size_t)i * n + k], X[(size_t)k * n + j], acc);
-        const double dgn = R[(size_t)i * n + i];
-        if (dgn == 0.0) { if (status) atomicOr(&status[b], SB_ST_SINGULAR); X[(size_t)i * n + j] = 0.0; }
-        else X[(size_t)i * n + j] = acc / dgn;
+    const int j = threadIdx.x;
+    for (int idx = threadIdx.x; idx < sz * sz; idx += blockDim.x) {
+        const int i = idx / sz, c = idx % sz;
+        Rs[i][c] = R[(size_t)(r0 + i) * n + r0 + c];
+        Xs[i][c] = 0.0;
     }
+    __syncthreads();
+    if (j < sz) {
+        for (int i = j; i >= 0; --i) {
+            double acc = (i == j) ? 1.0 : 0.0;
+            for (int k = i + 1; k <= j; ++k) acc = fma(-Rs[i][k], Xs[k][j], acc);
+            const double dgn = Rs[i][i];
+            if (dgn == 0.0) { if (status) atomicOr(&status[b], SB_ST_SINGULAR); Xs[i][j] = 0.0; }
+            else Xs[i][j] = acc / dgn;
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < sz * sz; idx += blockDim.x) {
+        const int i = idx / sz, c = idx % sz;
+        X[(size_t)(r0 + i) * n + r0 + c] = Xs[i][c];
+    }
+}
+
+__global__ void zero_lower_kernel(double* __restrict__ X_, int n, const int* __restrict__ active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * n) return;
+    if (idx / n > idx % n) X_[(size_t)b * n * n + idx] = 0.0;
 }
 
 }  // namespace
@@ -207,19 +272,88 @@ extern "C" int sb_gemm_impl(int transA, int transB, int M, int N, int K, double 
     return SB_LAUNCH_CHECK();
 }
 
-extern "C" int sb_qr_impl(double* A, int m, int n, double* Q, double* R, const int* active, int batch,
+extern "C" int sb_gemm_impl(int transA, int transB, int M, int N, int K, double alpha, const double* A, int lda,
+                            long long sA, const double* B, int ldb, long long sB, double beta, double* C, int ldc,
+                            long long sC, const int* active, int batch, cudaStream_t st);
+
+// work: batch * (m*n + 2*QR_NB*n + QR_NB*QR_NB) doubles (explicit reflector blocks, W1, W2, T)
+extern "C" int sb_qr_impl(double* A, int m, int n, double* Q, double* R, double* work, const int* active, int batch,
                           cudaStream_t st) {
-    const size_t smem = ((size_t)m + n + SB_SCRATCH_DOUBLES) * sizeof(double);
-    cudaFuncSetAttribute(qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    SB_COUNT(1);
-    qr_kernel<<<batch, QR_THREADS, smem, st>>>(A, m, n, Q, R, active);
+    double* Vp = work;
+    double* W1 = Vp + (size_t)batch * m * n;
+    double* W2 = W1 + (size_t)batch * QR_NB * n;
+    double* T = W2 + (size_t)batch * QR_NB * n;
+    const long long sA = (long long)m * n, sW = (long long)QR_NB * n, sT = QR_NB * QR_NB;
+    const int npan = (n + QR_NB - 1) / QR_NB;
+    // T of every panel is needed again for Q: keep them after W2 (npan blocks)
+    // (work therefore holds batch * npan * QR_NB^2 doubles of T; see the size formula in the header)
+    int rc = 0;
+    for (int p = 0; p < npan; ++p) {
+        const int p0 = p * QR_NB, nb = (n - p0 < QR_NB) ? n - p0 : QR_NB, mp = m - p0, nr = n - p0 - nb;
+        double* Tp = T + (size_t)p * batch * sT;
+        const size_t smem = ((size_t)nb * mp + 2 * QR_NB + QR_NB * QR_NB + SB_SCRATCH_DOUBLES) * sizeof(double);
+        if (smem > 200 * 1024) return -2;
+        cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        SB_COUNT(1);
+        qr_panel_kernel<<<batch, QR_THREADS, smem, st>>>(A, m, n, p0, nb, Vp, Tp, R, active);
+        if (nr > 0) {
+            const double* V = Vp + (size_t)p0 * n + p0;            // [mp, nb], ld n
+            double* A22 = A + (size_t)p0 * n + p0 + nb;            // [mp, nr], ld n
+            // W1 = V^T A22 [nb, nr];  W2 = T^T W1;  A22 -= V W2
+            if ((rc = sb_gemm_impl(1, 0, nb, nr, mp, 1.0, V, n, sA, A22, n, sA, 0.0, W1, nr, sW, active, batch, st))) return rc;
+            if ((rc = sb_gemm_impl(1, 0, nb, nr, nb, 1.0, Tp, QR_NB, sT, W1, nr, sW, 0.0, W2, nr, sW, active, batch, st))) return rc;
+            if ((rc = sb_gemm_impl(0, 0, mp, nr, nb, -1.0, V, n, sA, W2, nr, sW, 1.0, A22, n, sA, active, batch, st))) return rc;
+        }
+    }
+    {
+        dim3 g1((n * n + 255) / 256, batch), g2((m * n + 255) / 256, batch);
+        SB_COUNT(2);
+        qr_copy_r_kernel<<<g1, 256, 0, st>>>(A, m, n, R, active);
+        qr_init_q_kernel<<<g2, 256, 0, st>>>(Q, m, n, active);
+    }
+    for (int p = npan - 1; p >= 0; --p) {
+        const int p0 = p * QR_NB, nb = (n - p0 < QR_NB) ? n - p0 : QR_NB, mp = m - p0, nq = n - p0;
+        const double* Tp = T + (size_t)p * batch * sT;
+        const double* V = Vp + (size_t)p0 * n + p0;
+        double* Q22 = Q + (size_t)p0 * n + p0;                     // [mp, nq], ld n
+        // Q22 <- (I - V T V^T) Q22
+        if ((rc = sb_gemm_impl(1, 0, nb, nq, mp, 1.0, V, n, sA, Q22, n, sA, 0.0, W1, nq, sW, active, batch, st))) return rc;
+        if ((rc = sb_gemm_impl(0, 0, nb, nq, nb, 1.0, Tp, QR_NB, sT, W1, nq, sW, 0.0, W2, nq, sW, active, batch, st))) return rc;
+        if ((rc = sb_gemm_impl(0, 0, mp, nq, nb, -1.0, V, n, sA, W2, nq, sW, 1.0, Q22, n, sA, active, batch, st))) return rc;
+    }
     return SB_LAUNCH_CHECK();
 }
 
-extern "C" int sb_trtri_impl(const double* R, double* X, int n, int* status, const int* active, int batch,
-                             cudaStream_t st) {
-    dim3 grid((n + 255) / 256, batch);
+static int trtri_rec(const double* R, double* X, double* work, int n, int r0, int sz, int* status,
+                     const int* active, int batch, cudaStream_t st) {
+    if (sz <= TRI_BS) {
+        SB_COUNT(1);
+        trtri_block_kernel<<<batch, 64, 0, st>>>(R, X, n, r0, sz, status, active);
+        return 0;
+    }
+    int h = ((sz / 2 + 15) / 16) * 16;
+    if (h >= sz) h = sz / 2;
+    int rc;
+    if ((rc = trtri_rec(R, X, work, n, r0, h, status, active, batch, st))) return rc;
+    if ((rc = trtri_rec(R, X, work, n, r0 + h, sz - h, status, active, batch, st))) return rc;
+    const long long sN = (long long)n * n;
+    const double* R12 = R + (size_t)r0 * n + r0 + h;          // [h, sz-h]
+    const double* X11 = X + (size_t)r0 * n + r0;
+    const double* X22 = X + (size_t)(r0 + h) * n + r0 + h;
+    double* X12 = X + (size_t)r0 * n + r0 + h;
+    // work <- R12 X22 ;  X12 <- -X11 work
+    if ((rc = sb_gemm_impl(0, 0, h, sz - h, sz - h, 1.0, R12, n, sN, X22, n, sN, 0.0, work, sz - h, sN, active, batch, st))) return rc;
+    return sb_gemm_impl(0, 0, h, sz - h, h, -1.0, X11, n, sN, work, sz - h, sN, 0.0, X12, n, sN, active, batch, st);
+}
+
+// work: batch * n * n doubles
+extern "C" int sb_trtri_impl(const double* R, double* X, double* work, int n, int* status, const int* active,
+                             int batch, cudaStream_t st) {
+    // the strictly lower part must be zero BEFORE the merges: X22 of a level is read as a full block
+    dim3 grid((n * n + 255) / 256, batch);
     SB_COUNT(1);
-    trtri_kernel<<<grid, 256, 0, st>>>(R, X, n, status, active);
+    zero_lower_kernel<<<grid, 256, 0, st>>>(X, n, active);
+    const int rc = trtri_rec(R, X, work, n, 0, n, status, active, batch, st);
+    if (rc) return rc;
     return SB_LAUNCH_CHECK();
 }

@@ -159,10 +159,11 @@ def qr(A, active=None):
     require_cuda()
     check_f64(A)
     b, m, n = A.shape
-    work = A.clone()
+    fac = A.clone()
     Q = torch.empty((b, m, n), dtype=torch.float64, device=A.device)
     R = torch.empty((b, n, n), dtype=torch.float64, device=A.device)
-    call("sb_qr", _p(work), I(m), I(n), _p(Q), _p(R), _p(_mask(active)), I(b), _stream())
+    work = torch.empty(b * (m * n + 32 * n + 256 * ((n + 15) // 16)), dtype=torch.float64, device=A.device)
+    call("sb_qr", _p(fac), I(m), I(n), _p(Q), _p(R), _p(work), _p(_mask(active)), I(b), _stream())
     return Q, R
 
 
@@ -172,6 +173,7 @@ def trtri(R, active=None, status=None):
     check_f64(R)
     b, n, _ = R.shape
     X = torch.empty_like(R)
+    work = torch.empty_like(R)
     status = torch.zeros(b, dtype=torch.int32, device=R.device) if status is None else status
-    call("sb_trtri", _p(R), _p(X), I(n), _p(status), _p(_mask(active)), I(b), _stream())
+    call("sb_trtri", _p(R), _p(X), _p(work), I(n), _p(status), _p(_mask(active)), I(b), _stream())
     return X, status
