@@ -30,6 +30,12 @@ namespace {
 constexpr int EIG_THREADS = 256;
 
 // ---------------------------------------------------------------- 1. tridiag
+// Only the upper triangle of the work copy is read or written (the matrix is symmetric): in the
+// pass over the trailing block a warp owns row i and sweeps the columns j >= i; element (i, j)
+// contributes to p_i (row part, warp reduction) and, for j > i, to p_j (column part, kept in
+// registers per lane -- lane l owns the columns j = l mod 32 -- and summed over the warps through
+// shared memory at the end of the pass).  Half the traffic of a full-square sweep.
+template <int NPL>
 __global__ void __launch_bounds__(EIG_THREADS)
 tridiag_kernel(double* __restrict__ Wk, double* __restrict__ dout, double* __restrict__ eout,
                double* __restrict__ tauout, const int* __restrict__ active, int n) {
@@ -42,6 +48,7 @@ tridiag_kernel(double* __restrict__ Wk, double* __restrict__ dout, double* __res
     double* p = vn + n;        // tau * T v
     double* rowbuf = p + n;    // updated row k
     double* scratch = rowbuf + n;
+    double* colpart = scratch + SB_SCRATCH_DOUBLES;     // [nw][n] column parts of p
     double* W = Wk + (size_t)b * n * n;
     double* d = dout + (size_t)b * n;
     double* e = eout + (size_t)b * n;
@@ -97,22 +104,42 @@ tridiag_kernel(double* __restrict__ Wk, double* __restrict__ dout, double* __res
         }
         if (tid == 0) { e[k] = beta; tau[k] = tk; }
         __syncthreads();
-        // (c) one pass over the trailing block: apply the pending rank-2 update,
-        //     write it back, and form p = tau * T vn on the fly
+        // (c) one pass over the upper triangle of the trailing block: apply the pending rank-2
+        //     update, write it back, and form p = tau * T vn on the fly
+        double cacc[NPL];
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) cacc[q] = 0.0;
         for (int i = k + 1 + warp; i < n; i += nw) {
             double* row = W + (size_t)i * n;
             const double vi = pending ? v[i] : 0.0, wi = pending ? w[i] : 0.0;
+            const double vni = vn[i];
             double acc = 0.0;
-            for (int j = k + 1 + lane; j < n; j += 32) {
-                double val = row[j];
-                if (pending) {
-                    val -= vi * w[j] + wi * v[j];
-                    row[j] = val;
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) {
+                const int j = lane + 32 * q;
+                if (j >= i && j < n) {
+                    double val = row[j];
+                    if (pending) {
+                        val -= vi * w[j] + wi * v[j];
+                        row[j] = val;
+                    }
+                    acc = fma(val, vn[j], acc);
+                    if (j > i) cacc[q] = fma(val, vni, cacc[q]);
                 }
-                acc = fma(val, vn[j], acc);
             }
             acc = sb_warp_sum(acc);
-            if (lane == 0) p[i] = tk * acc;
+            if (lane == 0) p[i] = acc;
+        }
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) {
+            const int j = lane + 32 * q;
+            if (j < n) colpart[(size_t)warp * n + j] = cacc[q];
+        }
+        __syncthreads();
+        for (int j = k + 1 + tid; j < n; j += nt) {
+            double acc = p[j];
+            for (int w2 = 0; w2 < nw; ++w2) acc += colpart[(size_t)w2 * n + j];
+            p[j] = tk * acc;
         }
         __syncthreads();
         // (d) w = p - (tau/2)(p.v) v
@@ -350,10 +377,24 @@ extern "C" int sb_eigh_impl(const double* A, double* evals, double* Vt, double* 
     double* e = small + (size_t)batch * n;
     double* tau = small + (size_t)2 * batch * n;
     {
-        const size_t smem = (size_t)(5 * n + SB_SCRATCH_DOUBLES) * sizeof(double);
-        cudaFuncSetAttribute(tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const size_t smem = (size_t)(5 * n + SB_SCRATCH_DOUBLES + (EIG_THREADS / 32) * n) * sizeof(double);
+        const int npl = (n + 31) / 32;
         SB_COUNT(1);
-        tridiag_kernel<<<batch, EIG_THREADS, smem, st>>>(work, d, e, tau, active, n);
+#define SB_TRIDIAG(N)                                                                                         \
+    cudaFuncSetAttribute(tridiag_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+    tridiag_kernel<N><<<batch, EIG_THREADS, smem, st>>>(work, d, e, tau, active, n)
+        if (npl <= 2) { SB_TRIDIAG(2); }
+        else if (npl <= 4) { SB_TRIDIAG(4); }
+        else if (npl <= 6) { SB_TRIDIAG(6); }
+        else if (npl <= 8) { SB_TRIDIAG(8); }
+        else if (npl <= 12) { SB_TRIDIAG(12); }
+        else if (npl <= 16) { SB_TRIDIAG(16); }
+        else if (npl <= 24) { SB_TRIDIAG(24); }
+        else if (npl <= 32) { SB_TRIDIAG(32); }
+        else if (npl <= 48) { SB_TRIDIAG(48); }
+        else if (npl <= 64) { SB_TRIDIAG(64); }
+        else return -2;
+#undef SB_TRIDIAG
     }
     {
         int threads = EIG_THREADS;
