@@ -74,6 +74,10 @@ int sb_emt_pes(const double* x, int natoms, const double* cell, long long cellst
  * work: batch*n*n doubles, small: 3*batch*n doubles.                              */
 int sb_eigh(const double* A, double* evals, double* Vt, double* work, double* small_work,
             int32_t* status, const int32_t* active, int batch, int n, void* stream);
+/* same, with Q^T accumulated by blocked compact-WY GEMMs (faster for batches of large matrices);
+ * work2: batch * (n*n + 32*n + 256*ceil(n/16)) doubles.                                        */
+int sb_eigh_blocked(const double* A, double* evals, double* Vt, double* work, double* small_work,
+                    double* work2, int32_t* status, const int32_t* active, int batch, int n, void* stream);
 
 /* ---- orthogonalisation ------------------------------------------------------
  * modified_gram_schmidt(Xin, Yin, eps1, eps2, maxiter): sella/utilities/math.pyx:143-159

@@ -4,7 +4,7 @@
 
 extern "C" int sb_hv_impl(const double*, const double*, double*, const int*, int, int, int, int,
                           cudaStream_t);
-extern "C" int sb_eigh_impl(const double*, double*, double*, double*, double*, int*, const int*, int, int,
+extern "C" int sb_eigh_impl(const double*, double*, double*, double*, double*, double*, int*, const int*, int, int,
                             cudaStream_t);
 extern "C" int sb_hv_ld_impl(const double*, const double*, double*, const int*, int, int, int, int, int,
                              cudaStream_t);
@@ -145,7 +145,12 @@ int sb_emt_pes(const double* x, int natoms, const double* cell, long long cellst
 int sb_eigh(const double* A, double* evals, double* Vt, double* work, double* small_work, int32_t* status,
             const int32_t* active, int batch, int n, void* stream) {
     if (batch <= 0 || n <= 0) return -1;
-    return sb_eigh_impl(A, evals, Vt, work, small_work, status, active, batch, n, (cudaStream_t)stream);
+    return sb_eigh_impl(A, evals, Vt, work, small_work, nullptr, status, active, batch, n, (cudaStream_t)stream);
+}
+int sb_eigh_blocked(const double* A, double* evals, double* Vt, double* work, double* small_work, double* work2,
+                    int32_t* status, const int32_t* active, int batch, int n, void* stream) {
+    if (batch <= 0 || n <= 0 || !work2) return -1;
+    return sb_eigh_impl(A, evals, Vt, work, small_work, work2, status, active, batch, n, (cudaStream_t)stream);
 }
 
 extern "C" int sb_internals_qB_impl(const int*, int, const int*, int, const int*, int, const int*, int, const double*,

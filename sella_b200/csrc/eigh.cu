@@ -189,6 +189,68 @@ formqt_kernel(const double* __restrict__ Wk, const double* __restrict__ tauin, d
     }
 }
 
+// ---------------------------------------------------------------- 2b. form Q^T with GEMMs
+// Blocked accumulation (LAPACK dorgtr/dorgqr scheme, compact WY): the reflectors of a panel of
+// FQ_NB columns, B_p = H_k0 ... H_k1 = I - V T V^T, are applied to the trailing block only,
+//   Mt22 <- Mt22 (I - V T^T V^T) = Mt22 - (Mt22 V22^T) T^T V22,     Mt22 = Mt[k0+1:, k0+1:],
+// going from the last panel to the first, as three fp64 tensor-core GEMMs per panel.  This kernel
+// prepares a panel: the explicit reflector rows V22 (zeros left of the unit entry) and T (dlarft).
+constexpr int FQ_NB = 16;
+
+__global__ void __launch_bounds__(EIG_THREADS)
+formqt_panel_kernel(const double* __restrict__ Wk, const double* __restrict__ tauin, double* __restrict__ Vp_,
+                    double* __restrict__ T_, const int* __restrict__ active, int n, int batch) {
+    const int b = blockIdx.y, pnl = blockIdx.x;
+    if (active && !active[b]) return;
+    __shared__ double Tm[FQ_NB * FQ_NB];
+    __shared__ double G[FQ_NB * FQ_NB];
+    const int k0 = pnl * FQ_NB;
+    const int nref = n - 2;                                   // reflectors 0 .. n-3
+    const int nb = min(FQ_NB, nref - k0);
+    if (nb <= 0) return;
+    const double* W = Wk + (size_t)b * n * n;
+    const double* tau = tauin + (size_t)b * n;
+    double* Vp = Vp_ + (size_t)b * n * n;
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    for (int idx = tid; idx < nb * n; idx += nt) {
+        const int r = idx / n, j = idx % n, k = k0 + r;
+        Vp[(size_t)k * n + j] = j >= k + 1 ? W[(size_t)k * n + j] : 0.0;
+    }
+    __syncthreads();
+    for (int pr = warp; pr < nb * nb; pr += nw) {
+        const int i = pr / nb, j = pr % nb;
+        if (i >= j) continue;
+        const double* vi = Vp + (size_t)(k0 + i) * n;
+        const double* vj = Vp + (size_t)(k0 + j) * n;
+        double d = 0.0;
+        for (int e = k0 + j + 1 + lane; e < n; e += 32) d = fma(vi[e], vj[e], d);
+        d = sb_warp_sum(d);
+        if (lane == 0) G[i * FQ_NB + j] = d;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 0; i < FQ_NB * FQ_NB; ++i) Tm[i] = 0.0;
+        for (int j = 0; j < nb; ++j) {
+            const double tj = tau[k0 + j];
+            for (int i = 0; i < j; ++i) {
+                double acc = 0.0;
+                for (int l = i; l < j; ++l) acc += Tm[i * FQ_NB + l] * G[l * FQ_NB + j];
+                Tm[i * FQ_NB + j] = -tj * acc;
+            }
+            Tm[j * FQ_NB + j] = tj;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < FQ_NB * FQ_NB; i += nt) T_[((size_t)pnl * batch + b) * FQ_NB * FQ_NB + i] = Tm[i];
+}
+
+__global__ void identity_kernel(double* __restrict__ M_, int n, const int* __restrict__ active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n * n) M_[(size_t)b * n * n + idx] = (idx / n == idx % n) ? 1.0 : 0.0;
+}
+
 // ---------------------------------------------------------------- 3. implicit QL
 template <int CPT>
 __device__ __forceinline__ void apply_sweep(double* __restrict__ Mt, const double* __restrict__ cs, int n,
@@ -367,8 +429,14 @@ sort_kernel(const double* __restrict__ din, double* __restrict__ evals, double* 
 
 // A (read only) -> evals ascending, Vt rows = eigenvectors.  work: n*n doubles per
 // system (reflectors), small: 3*n doubles per system (d, e, tau).
+extern "C" int sb_gemm_impl(int transA, int transB, int M, int N, int K, double alpha, const double* A, int lda,
+                            long long sA, const double* B, int ldb, long long sB, double beta, double* C, int ldc,
+                            long long sC, const int* active, int batch, cudaStream_t st);
+
+// work2 (may be NULL): batch * (n*n + 32*n + 256*ceil(n/16)) doubles; when given, Q^T is formed by the
+// blocked GEMM scheme instead of the warp-per-column kernel.
 extern "C" int sb_eigh_impl(const double* A, double* evals, double* Vt, double* work, double* small,
-                            int* status, const int* active, int batch, int n, cudaStream_t st) {
+                            double* work2, int* status, const int* active, int batch, int n, cudaStream_t st) {
     if (n < 1) return -1;
     cudaError_t err = cudaMemcpyAsync(work, A, (size_t)batch * n * n * sizeof(double),
                                       cudaMemcpyDeviceToDevice, st);
@@ -396,7 +464,29 @@ extern "C" int sb_eigh_impl(const double* A, double* evals, double* Vt, double* 
         else return -2;
 #undef SB_TRIDIAG
     }
-    {
+    if (work2 && n >= 4 * FQ_NB) {
+        double* Vp = work2;
+        double* W1 = Vp + (size_t)batch * n * n;
+        double* W2 = W1 + (size_t)batch * FQ_NB * n;
+        double* T = W2 + (size_t)batch * FQ_NB * n;
+        const int nref = n - 2, npan = (nref + FQ_NB - 1) / FQ_NB;
+        const long long sN = (long long)n * n, sW = (long long)FQ_NB * n, sT = FQ_NB * FQ_NB;
+        dim3 gp(npan, batch), gi((n * n + 255) / 256, batch);
+        SB_COUNT(2);
+        formqt_panel_kernel<<<gp, EIG_THREADS, 0, st>>>(work, tau, Vp, T, active, n, batch);
+        identity_kernel<<<gi, 256, 0, st>>>(Vt, n, active);
+        int rc;
+        for (int p = npan - 1; p >= 0; --p) {
+            const int k0 = p * FQ_NB, nb = (nref - k0 < FQ_NB) ? nref - k0 : FQ_NB, np = n - k0 - 1;
+            const double* V22 = Vp + (size_t)k0 * n + k0 + 1;             // [nb, np], ld n
+            double* M22 = Vt + (size_t)(k0 + 1) * n + k0 + 1;             // [np, np], ld n
+            const double* Tp = T + (size_t)p * batch * sT;
+            // W1 = M22 V22^T [np, nb];  W2 = W1 T^T;  M22 -= W2 V22
+            if ((rc = sb_gemm_impl(0, 1, np, nb, np, 1.0, M22, n, sN, V22, n, sN, 0.0, W1, nb, sW, active, batch, st))) return rc;
+            if ((rc = sb_gemm_impl(0, 1, np, nb, nb, 1.0, W1, nb, sW, Tp, FQ_NB, sT, 0.0, W2, nb, sW, active, batch, st))) return rc;
+            if ((rc = sb_gemm_impl(0, 0, np, np, nb, -1.0, W2, nb, sW, V22, n, sN, 1.0, M22, n, sN, active, batch, st))) return rc;
+        }
+    } else {
         int threads = EIG_THREADS;
         size_t smem = (size_t)(threads / 32) * n * sizeof(double);
         cudaFuncSetAttribute(formqt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -54,6 +54,14 @@ class EighWorkspace:
     def __init__(self, batch, n, device):
         self.work = torch.empty((batch, n, n), dtype=torch.float64, device=device)
         self.small = torch.empty((3, batch, n), dtype=torch.float64, device=device)
+        self.work2 = None           # allocated on first use by eigh(): GEMM-based accumulation of Q^T
+
+    def blocked(self):
+        if self.work2 is None:
+            b, n, _ = self.work.shape
+            self.work2 = torch.empty(b * (n * n + 32 * n + 256 * ((n + 15) // 16)), dtype=torch.float64,
+                                     device=self.work.device)
+        return self.work2
 
 
 def eigh(A, active=None, evals=None, Vt=None, ws=None, status=None):
@@ -67,8 +75,12 @@ def eigh(A, active=None, evals=None, Vt=None, ws=None, status=None):
     ws = EighWorkspace(b, n, dev) if ws is None else ws
     status = torch.zeros(b, dtype=torch.int32, device=dev) if status is None else status
     active = _mask(active)
-    call("sb_eigh", _p(A), _p(evals), _p(Vt), _p(ws.work), _p(ws.small), _p(status), _p(active), I(b),
-         I(n), _stream())
+    if n >= 64 and b * n * n >= (1 << 22):
+        call("sb_eigh_blocked", _p(A), _p(evals), _p(Vt), _p(ws.work), _p(ws.small), _p(ws.blocked()), _p(status),
+             _p(active), I(b), I(n), _stream())
+    else:
+        call("sb_eigh", _p(A), _p(evals), _p(Vt), _p(ws.work), _p(ws.small), _p(status), _p(active), I(b),
+             I(n), _stream())
     return evals, Vt, status
 
 
