@@ -377,8 +377,7 @@ class BatchedSella:
 
     # ------------------------------------------------------------------ helpers
     def _eigh(self, active=None):
-        call("sb_eigh", _p(self.B), _p(self.evals), _p(self.Vt), _p(self.eig_ws.work),
-             _p(self.eig_ws.small), _p(self.status), _p(active), I(self.batch), I(self.n), _stream())
+        K.eigh(self.B, active=active, evals=self.evals, Vt=self.Vt, ws=self.eig_ws, status=self.status)
 
     def _update(self, S, Y, bufs, kvec, nv, active, bs_ready=False, abs_ready=False):
         """ApproximateHessian.update (linalg.py:274-304) for S, Y of shape [b,kc,n]."""
