@@ -325,6 +325,8 @@ class BatchedSella:
         if not self.H_initialized:
             return
         torch.sub(self.B, nl["Hc"], out=nl["HL"])
+        if self._projected_spectrum_by_update():
+            return
         Pc = K.gemm(cn["Uc"], cn["Uc"], transA=True)                  # Ucons Ucons^T
         Pf = torch.eye(n, dtype=torch.float64, device=self.dev).expand(b, n, n) - Pc
         Pf = Pf.contiguous()
@@ -333,6 +335,63 @@ class BatchedSella:
         Bp = 0.5 * (Bp + Bp.transpose(1, 2)) + sigma[:, None, None] * Pc
         K.eigh(Bp.contiguous(), evals=self.evals, Vt=self.Vt, ws=self.eig_ws, status=self.status)
         nl["x_model"] = True
+
+    def _projected_spectrum_by_update(self):
+        """Spectrum of Bp = P_f (B - Hc) P_f + sigma P_c WITHOUT a full eigensolve, for the reference's
+        default projection of molecules (linear rows + the three rotation coordinates).  With
+        A = (B - Hc) Ucons and G = Ucons^T A,
+            Bp - B = -Hc - Ucons A^T - A Ucons^T + Ucons (G + sigma I) Ucons^T,
+        and the rotation block of Hc is a sum of outer products of the per-coordinate 4-vectors that
+        sb_rotation leaves in its work buffer: Hc = 1/2 sum_c (x_c y_c^T + y_c x_c^T) with
+        (x, y) = (p_k - dFw_k, dq_k), k = 1..4, and (2 dE, dq.w).  That is nc + 5 secant-like pairs
+        (U_i, J_i) with C = -(G + sigma I): numerical rank 2 nc, one eigen-update of the CARRIED
+        spectrum of B.  Returns False when the situation is not this one (the caller then builds Bp
+        densely and calls the eigensolver)."""
+        import os
+        cn = self.cons
+        nl = cn["nl"]
+        ints = nl["ints"]
+        nc = cn["nc"]
+        if not os.environ.get("SB_NL_SECULAR") or ints.nstd != 0 or ints.nrotations != 3 or nc + 5 > 16 \
+                or self.eig_mode != "update" or not self.eig_valid:
+            return False
+        b, n = self.batch, self.n
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        if "U16" not in nl:
+            nl["U16"], nl["J16"] = torch.zeros(b, 16, n, **f64), torch.zeros(b, 16, n, **f64)
+            nl["A"], nl["A2"] = torch.zeros(b, nc, n, **f64), torch.zeros(b, nc, n, **f64)
+            nl["sec"] = dict(P=torch.zeros(b, 32, n, **f64), Z=torch.zeros(b, 32, n, **f64), sig=torch.zeros(b, 32, **f64))
+            nl["C16"] = torch.zeros(b, 32, 33, **f64)
+            nl["k16"] = torch.full((b,), nc + 5, dtype=torch.int32, device=self.dev)
+            nl["skip0"] = torch.zeros(b, dtype=torch.int32, device=self.dev)
+            nl["nterm"] = torch.zeros(b, dtype=torch.int32, device=self.dev)
+        U, J, A, A2, sec = nl["U16"], nl["J16"], nl["A"], nl["A2"], nl["sec"]
+        K.hv_ld(self.B, cn["Uc"], A, nc)
+        K.hv_ld(nl["Hc"], cn["Uc"], A2, nc)
+        A.sub_(A2)                                                     # rows a_i = (B - Hc) u_i
+        G = K.gemm(cn["Uc"], A, transB=True)                           # G_ij = u_i . a_j
+        sigma = 1.0 + 8.0 * torch.maximum(self.evalsB[:, 0].abs(), self.evalsB[:, -1].abs())
+        U[:, :nc] = cn["Uc"]
+        J[:, :nc] = -A
+        w = ints._rot_work.view(b, 14 * n)
+        dc = w[:, :4 * n].view(b, n, 4)
+        pv = w[:, 4 * n:8 * n].view(b, n, 4)
+        dfw = w[:, 8 * n:12 * n].view(b, n, 4)
+        U[:, nc:nc + 4] = (pv - dfw).transpose(1, 2)
+        J[:, nc:nc + 4] = -0.5 * dc.transpose(1, 2)
+        U[:, nc + 4] = 2.0 * w[:, 12 * n:13 * n]
+        J[:, nc + 4] = -0.5 * w[:, 13 * n:14 * n]
+        C = nl["C16"]
+        C.zero_()
+        C[:, :nc, :nc] = -(0.5 * (G + G.transpose(1, 2)) + sigma[:, None, None] * torch.eye(nc, **f64))
+        call("sb_lowrank_factor", _p(U), _p(J), _p(C), I(16), _p(nl["k16"]), I(n), _p(sec["P"]), _p(sec["sig"]),
+             _p(nl["nterm"]), _p(nl["skip0"]), I(b), _stream())
+        self.evals.copy_(self.evalsB)
+        self.Vt.copy_(self.VtB)
+        K.hv_ld(self.Vt, sec["P"], sec["Z"], 2 * (nc + 5))
+        call("sb_secular_update", _p(self.evals), _p(self.Vt), _p(sec["Z"]), I(32), _p(sec["sig"]), _p(nl["nterm"]),
+             I(n), _p(self.eig_ws.work), _p(self.qwork), _p(self.status), _p(nl["skip0"]), I(b), _stream())
+        return True
 
     def _identity_model(self):
         b, n = self.batch, self.n
