@@ -352,7 +352,7 @@ class BatchedSella:
         nl = cn["nl"]
         ints = nl["ints"]
         nc = cn["nc"]
-        if not os.environ.get("SB_NL_SECULAR") or ints.nstd != 0 or ints.nrotations != 3 or nc + 5 > 16 \
+        if os.environ.get("SB_NL_SECULAR", "1") == "0" or ints.nstd != 0 or ints.nrotations != 3 or nc + 5 > 16 \
                 or self.eig_mode != "update" or not self.eig_valid:
             return False
         b, n = self.batch, self.n
