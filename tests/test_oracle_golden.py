@@ -189,3 +189,51 @@ def test_rotation_coordinate(golden):
         pm = pos.ravel().copy(); pm[a] -= h
         fd = (orot.rotation(pp, ref, q)[0] - orot.rotation(pm, ref, q)[0]) / (2 * h)
         np.testing.assert_allclose(J[:, a], fd, rtol=1e-6, atol=1e-8)
+
+
+def test_rotation_coordinate_meaning():
+    """A rigid rotation by the vector theta gives the coordinate values theta (or -theta, by the
+    reference's convention); translations give zero; the Jacobian rows are orthogonal to translations."""
+    from oracle import rotation as orot
+    rng = np.random.RandomState(3)
+    ref = rng.normal(size=(9, 3))
+    th = np.array([0.02, -0.05, 0.03])
+    ang = np.linalg.norm(th); k = th / ang
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    Rm = np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx
+    vals, J, q = orot.rotation((ref - ref.mean(0)) @ Rm.T + 0.7, ref)
+    assert min(np.abs(vals - th).max(), np.abs(vals + th).max()) < 1e-12
+    vals0, J0, _ = orot.rotation(ref + np.array([0.3, -1.0, 2.0]), ref)
+    np.testing.assert_allclose(vals0, 0.0, atol=1e-14)
+    for d in range(3):
+        np.testing.assert_allclose(J0[:, d::3].sum(axis=1), 0.0, atol=1e-12)
+
+
+def test_nonlinear_pes_constraint_hessian_is_the_derivative_of_the_jacobian():
+    """Hc = sum_i L_i d2r_i/dx2 (peswrapper.py:343-352): finite differences of drdx^T L at fixed L,
+    for a bond + angle + rotation constraint set; and the oracle loop holds such constraints."""
+    from oracle.pes import NonlinearPES
+    from oracle.driver import SaddleSearch
+    from sella_b200.synthetic import quadratic_system, quadratic_func
+    n = 24
+    A, xs, x0 = quadratic_system(2, n)
+    coords = dict(bonds=[(0, 1)], angles=[(2, 3, 5)], rotation_ref=x0.reshape(-1, 3))
+    p = NonlinearPES(quadratic_func(A, xs), x0, coords)
+    p.get_g()
+    L = p.curr["L"]
+    assert L.shape == (5,)
+    Hc = p.get_Hc()
+    np.testing.assert_allclose(Hc, Hc.T, atol=1e-9)
+    h = 1e-6
+    rng = np.random.RandomState(0)
+    for _ in range(3):
+        v = rng.normal(size=n); v /= np.linalg.norm(v)
+        xp, xm = x0 + h * v, x0 - h * v
+        qp = NonlinearPES(quadratic_func(A, xs), xp, coords, targets=np.zeros(5)); qp.q_prev = p.q_prev
+        qm = NonlinearPES(quadratic_func(A, xs), xm, coords, targets=np.zeros(5)); qm.q_prev = p.q_prev
+        fd = (qp.get_drdx().T @ L - qm.get_drdx().T @ L) / (2 * h)
+        np.testing.assert_allclose(Hc @ v, fd, rtol=1e-5, atol=1e-7)
+    o = SaddleSearch(p, method="prfo", rs="ras", diag_maxiter=6)
+    for _ in range(6):
+        o.step()
+    assert np.abs(p.get_res()).max() < 1e-3
