@@ -237,3 +237,46 @@ def test_nonlinear_pes_constraint_hessian_is_the_derivative_of_the_jacobian():
     for _ in range(6):
         o.step()
     assert np.abs(p.get_res()).max() < 1e-3
+
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_morse_cluster_like_the_reference_integration_test(order):
+    """tests/integration/test_morse_cluster.py:11-46 of the reference (Cartesian variants) on the
+    oracle: 4-atom Morse cluster, fix_translation() + fix_rotation(), gamma=1e-3, run to fmax 1e-3;
+    the projected gradient vanishes and the projected Hessian of the Lagrangian has exactly `order`
+    negative eigenvalues.  Same inputs (RandomState(4), r0 = 4.73, rho0 = 4.73 * 1.099; the `alpha`
+    keyword of the reference's call is not a MorsePotential parameter, so epsilon stays 1)."""
+    from oracle.pes import NonlinearPES
+    from oracle.driver import SaddleSearch
+    r0, rho0 = 4.73, 4.73 * 1.099
+
+    def morse(x):
+        pos = x.reshape(-1, 3)
+        e, g = 0.0, np.zeros_like(pos)
+        for i in range(len(pos)):
+            for j in range(i + 1, len(pos)):
+                d = pos[i] - pos[j]
+                r = np.linalg.norm(d)
+                ex = np.exp(-rho0 * (r / r0 - 1.0))
+                e += ex * ex - 2.0 * ex
+                de = (-2.0 * rho0 / r0) * (ex * ex - ex)
+                g[i] += de * d / r
+                g[j] -= de * d / r
+        return e, g.ravel()
+    rng = np.random.RandomState(4)
+    nat = 4
+    x0 = rng.normal(size=(nat, 3), scale=3.0).ravel()
+    C = np.zeros((3, 3 * nat))
+    for d in range(3):
+        C[d, d::3] = 1.0 / nat
+    p = NonlinearPES(morse, x0, dict(rotation_ref=x0.reshape(-1, 3)), np.zeros(3), C, C @ x0)
+    o = SaddleSearch(p, order=order, gamma=1e-3)
+    assert o.run(fmax=1e-3, steps=500)
+    Ufree = p.get_Ufree()
+    assert Ufree.shape == (12, 6)
+    np.testing.assert_allclose(p.get_g() @ Ufree, 0, atol=5e-3)
+    p.diag(gamma=1e-16)
+    H = p.get_HL_projected(Ufree)
+    assert int(np.sum(H.evals < 0)) == order, H.evals
+    # the held coordinates are where they were put
+    assert np.abs(p.get_res()).max() < 1e-5
