@@ -80,7 +80,7 @@ def apply_dF(y, v):
     return out
 
 
-def rotation(pos, refpos, q_prev=None, L=None):
+def rotation(pos, refpos, q_prev=None, L=None, factors=False):
     """values (3,), Jacobian (3, 3N), q, and sum_k L_k Hessian_k (3N x 3N) if L is given."""
     pos = np.asarray(pos, float).reshape(-1, 3)
     y = np.asarray(refpos, float).reshape(-1, 3)
@@ -125,4 +125,9 @@ def rotation(pos, refpos, q_prev=None, L=None):
     cross = dFw @ dc.T
     H += (dE[:, None] * wdc[None, :] + dE[None, :] * wdc[:, None] + 2 * (dFq @ dc.T) * (w @ q)
           - cross - cross.T - (df @ q) * (dc @ dc.T))
+    if factors:
+        # the per-coordinate 4-vectors the CUDA kernel keeps (sella_b200/csrc/rotation.cu):
+        #   H = Pv dc^T - dc dFw^T + dE wdc^T + wdc dE^T,  Pv = dc d2f + 2 (w.q) dFq - dFw - (df.q) dc
+        Pv = dc @ d2f + 2 * (w @ q) * dFq - dFw - (df @ q) * dc
+        return vals, J, q, H, dict(dc=dc, Pv=Pv, dFw=dFw, dE=dE, wdc=wdc)
     return vals, J, q, H

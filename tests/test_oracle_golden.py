@@ -280,3 +280,36 @@ def test_morse_cluster_like_the_reference_integration_test(order):
     assert int(np.sum(H.evals < 0)) == order, H.evals
     # the held coordinates are where they were put
     assert np.abs(p.get_res()).max() < 1e-5
+
+
+def test_projected_spectrum_identity_used_by_the_engine():
+    """The algebra behind BatchedSella._projected_spectrum_by_update: with Ucons orthonormal,
+    A = (B - Hc) Ucons, G = Ucons^T A,
+        Bp - B = P_f (B - Hc) P_f + sigma P_c - B = -Hc - Ucons A^T - A Ucons^T + Ucons (G + sigma I) Ucons^T,
+    the rotation block of Hc is 1/2 sum_c (x_c y_c^T + y_c x_c^T) over the five pairs built from the
+    kernel's 4-vectors, and the whole correction has rank 2 nc for translation + rotation constraints."""
+    from oracle import rotation as orot
+    from sella_b200.synthetic import fcc_cluster
+    rng = np.random.RandomState(0)
+    N = 16; n = 3 * N
+    ref = fcc_cluster(N, seed=1)
+    pos = ref + 0.05 * rng.normal(size=ref.shape)
+    L = rng.normal(size=3)
+    vals, J, q, Hc, f = orot.rotation(pos, ref, None, L, factors=True)
+    X = np.hstack([f["Pv"] - f["dFw"], 2 * f["dE"][:, None]])           # n x 5
+    Y = np.hstack([f["dc"], f["wdc"][:, None]])
+    np.testing.assert_allclose(0.5 * (X @ Y.T + Y @ X.T), Hc, atol=1e-12 * max(1.0, np.abs(Hc).max()))
+    B = rng.normal(size=(n, n)); B = B + B.T
+    C = np.vstack([np.kron(np.ones(N) / N, np.eye(3)[d]) for d in range(3)] + [J[k] for k in range(3)])
+    Uc = np.linalg.qr(C.T)[0].T                                          # nc x n, orthonormal rows
+    nc, sigma = 6, 7.0
+    Pc = Uc.T @ Uc; Pf = np.eye(n) - Pc
+    Bp = Pf @ (B - Hc) @ Pf + sigma * Pc
+    A = (B - Hc) @ Uc.T
+    G = Uc @ A
+    U = np.hstack([Uc.T, X]); Jp = np.hstack([-A, -0.5 * Y])             # the engine's (U, J) pairs
+    Cm = np.zeros((nc + 5, nc + 5)); Cm[:nc, :nc] = -(G + sigma * np.eye(nc))
+    delta = U @ Jp.T + Jp @ U.T - U @ Cm @ U.T
+    np.testing.assert_allclose(delta, Bp - B, atol=1e-10)
+    sv = np.linalg.svd(Bp - B, compute_uv=False)
+    assert int((sv > 1e-10 * sv[0]).sum()) == 2 * nc
