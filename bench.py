@@ -50,17 +50,18 @@ def parse():
     ap.add_argument("--workload", default="quadratic", choices=["quadratic", "emt-slab", "emt-cluster"],
                     help="quadratic: synthetic indefinite-quadratic PES (SURVEY 8d; the default, C4/C5 family); "
                          "emt-slab: C3-style 128-atom Cu(111) slabs, bottom half fixed, EMT-form surface; "
-                         "emt-cluster: C2-style 64-atom Cu clusters, centre of mass held, EMT-form surface")
+                         "emt-cluster: C2-style 64-atom Cu clusters, translation + rotation projection, EMT-form surface")
     ap.add_argument("--batch", type=int, default=None, help="systems per GPU (default 1024; 256 for emt-cluster)")
     ap.add_argument("--n", type=int, default=None, help="3N degrees of freedom (default 384; 192 for emt-cluster)")
     ap.add_argument("--rs", default="tr")
     ap.add_argument("--method", default="prfo", help="step model: prfo (Sella's default for saddles), rfo, qn")
     ap.add_argument("--kdiag", type=int, default=5)
     ap.add_argument("--diag-every", type=int, default=3)
-    ap.add_argument("--proj-rot", action="store_true",
-                    help="emt-cluster only: also hold the three rotation coordinates (the reference's default "
-                         "projection for non-periodic systems, peswrapper.py:246-253); position-dependent "
-                         "constraints take the direct-eigensolve path")
+    ap.add_argument("--proj-rot", dest="proj_rot", action="store_true", default=True,
+                    help="emt-cluster only (default on): also hold the three rotation coordinates, the reference's "
+                         "default projection for non-periodic systems (peswrapper.py:246-253)")
+    ap.add_argument("--no-proj-rot", dest="proj_rot", action="store_false",
+                    help="emt-cluster only: centre of mass held, rotations left free (linear constraints only)")
     ap.add_argument("--cpu-systems", type=int, default=0, help="reference sample size (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
@@ -111,7 +112,8 @@ def workload(args):
     what = ("%d-atom Cu(111) slabs (rattled 0.05 A), bottom half held by fix_translation (%d linear constraints)"
             % (args.n // 3, args.n // 2)) if args.workload == "emt-slab" else \
            ("%d-atom Cu clusters (fcc ball + 0.05 A rattle), centre of mass held (3 linear constraints)%s"
-            % (args.n // 3, " + the three rotation coordinates held (position-dependent)" if args.proj_rot else ""))
+            % (args.n // 3, " + the three rotation coordinates held (position-dependent; the reference's default "
+                            "projection)" if args.proj_rot else ", rotations free (--no-proj-rot)"))
     return dict(workload="batch=%d/GPU x 3N=%d EMT-form surface on the device, %s, %s" % (args.batch, args.n, what, tail),
                 l2_policy="working set %.1f GB per GPU >> 126 MB L2 (no flush needed)"
                           % (args.batch * args.n * args.n * 8 * 4 / 1e9), **common)
@@ -143,7 +145,7 @@ def _cpu_worker(job):
         if wl == "quadratic":
             A, xs, x0 = quadratic_system(first + i, n)
             p = CartesianPES(quadratic_func(A, xs), x0)
-        elif proj_rot:
+        elif proj_rot and wl == "emt-cluster":
             from oracle.pes import NonlinearPES
             p = NonlinearPES(emt_func(cell, pbc), X0[i], dict(rotation_ref=X0[i].reshape(-1, 3)), np.zeros(3), C, C @ X0[i])
         else:
@@ -327,7 +329,7 @@ def run_ours(args):
         x0 = torch.from_numpy(X0).to(dev)
         surf = EMTSurface(b, n // 3, dev, cell=cell, pbc=pbc)
         cons = (C, None)
-        if args.proj_rot and args.workload == "emt-cluster":
+        if args.proj_rot and args.workload == "emt-cluster":     # the reference's default for molecules
             from sella_b200.internal import BatchedInternals
             cons = (C, None, BatchedInternals(n // 3, rotation_ref=X0.reshape(b, n // 3, 3)), None)
 
