@@ -91,3 +91,31 @@ def test_bench_workload_builders():
     X0, C, cell, pbc = bench.emt_problem(ns, 0, 3)
     assert X0.shape == (3, 192) and C.shape == (3, 192) and cell is None
     np.testing.assert_allclose(C @ X0[0], X0[0].reshape(-1, 3).mean(0))
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference: rank 0 prints ONE JSON line with the contract's keys; other ranks
+    exit 0 without output (the driver launches it under torchrun for N > 1)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    base = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--n", "24", "--batch", "8",
+            "--steps", "2", "--warmup", "1", "--cpu-systems", "2"]
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run(base + ["--gpus", "2"], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0")
+    out = subprocess.run(base, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert "workload" in d["config"]
