@@ -34,11 +34,45 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "optimizer steps/sec (batched 3N-DOF Davidson+TR)"
-# dram__bytes_read.sum + dram__bytes_write.sum per sb_secular_update call (three kernels), from the
-# committed ncu --set full captures, keyed by (systems per GPU, 3N)
-NCU_TRAFFIC = {(1024, 384): 3.537e9}     # profiles/ncu_full_r1_h_eigen_update.csv
-NCU_TRAFFIC_HV = {(1024, 384): 1.211e9}  # profiles/ncu_full_r1_a_hv.csv (hv_tma_kernel<1>, one launch)
 UNIT = "system-steps/s"
+# committed `ncu --set full` captures (raw page, csv) the roofline `traffic` figures are read from:
+# (systems per GPU, 3N) -> file under profiles/
+NCU_CAPTURES = {(1024, 384): dict(hv=("ncu_full_r2_hv.csv", "ncu_full_r1_a_hv.csv"),
+                                  eigen=("ncu_full_r2_eigen_update.csv", "ncu_full_r1_h_eigen_update.csv"))}
+
+
+def ncu_traffic(files, kernel_regex, per="launch"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the kernels matching `kernel_regex` in the first
+    of `files` that exists under profiles/ (ncu --page raw --csv: a header row, a units row, one row
+    per profiled launch).  per='launch': mean over the matching launches; per='group': summed over the
+    distinct kernel names (one launch of each).  Returns (bytes, file) or (None, None)."""
+    import csv
+    import re
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for name in files:
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.isfile(path):
+            continue
+        with open(path, newline="") as fh:
+            rows = list(csv.reader(fh))
+        if len(rows) < 3:
+            continue
+        head, units = rows[0], rows[1]
+        try:
+            kn, rd, wr = head.index("Kernel Name"), head.index("dram__bytes_read.sum"), head.index("dram__bytes_write.sum")
+        except ValueError:
+            continue
+        by_kernel = {}
+        for r in rows[2:]:
+            if len(r) <= max(kn, rd, wr) or not re.search(kernel_regex, r[kn]):
+                continue
+            tot = float(r[rd]) * scale.get(units[rd], 1.0) + float(r[wr]) * scale.get(units[wr], 1.0)
+            by_kernel.setdefault(r[kn], []).append(tot)
+        if not by_kernel:
+            continue
+        means = [sum(v) / len(v) for v in by_kernel.values()]
+        return (sum(means) if per == "group" else sum(means) / len(means)), name
+    return None, None
 
 
 def parse():
@@ -62,7 +96,13 @@ def parse():
                          "default projection for non-periodic systems (peswrapper.py:246-253)")
     ap.add_argument("--no-proj-rot", dest="proj_rot", action="store_false",
                     help="emt-cluster only: centre of mass held, rotations left free (linear constraints only)")
-    ap.add_argument("--cpu-systems", type=int, default=0, help="reference sample size (0 = auto)")
+    ap.add_argument("--cpu-systems", type=int, default=0, help="reference sample size (0 = 2 per core)")
+    ap.add_argument("--parity-systems", type=int, default=4,
+                    help="systems of the timed batch re-run on the host for the `parity` key (0 = off)")
+    ap.add_argument("--long-steps", type=int, default=100,
+                    help="length of the extra run whose per-decile step times go into `long_run` (0 = off)")
+    ap.add_argument("--spectrum", default=None, choices=[None, "compact", "dense"],
+                    help="engine representation of the Hessian spectrum (default: the engine's own choice)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     if a.batch is None:
@@ -120,38 +160,87 @@ def workload(args):
 
 
 # ----------------------------------------------------------------------------- CPU reference
-def _cpu_worker(job):
-    """Runs `nsys` oracle searches for `steps` steps with 1 BLAS thread; returns
-    (steps done, seconds in the timed part)."""
-    first, nsys, n, rs, kdiag, diag_every, warm, steps, threads, method, wl = job[:11]
-    proj_rot = len(job) > 11 and job[11]
+def _limit_threads(threads):
     os.environ["OMP_NUM_THREADS"] = str(threads)
     os.environ["OPENBLAS_NUM_THREADS"] = str(threads)
     os.environ["MKL_NUM_THREADS"] = str(threads)
     try:
         from threadpoolctl import threadpool_limits
-        limiter = threadpool_limits(limits=threads)
+        return threadpool_limits(limits=threads)
     except Exception:
-        limiter = None
-    from oracle.pes import CartesianPES
-    from oracle.driver import SaddleSearch
-    from sella_b200.synthetic import quadratic_system, quadratic_func
-    runs = []
-    if wl != "quadratic":
-        from oracle.emt import emt_func
-        ns = argparse.Namespace(workload=wl, n=n)
-        X0, C, cell, pbc = emt_problem(ns, first, nsys)
-    for i in range(nsys):
+        return None
+
+
+def _gen_chunk(job):
+    """Host generation of quadratic systems first..first+count-1 (numpy recipe of SURVEY 8d): the
+    SAME function and seeds feed the GPU arm, the CPU arm and the in-run parity check."""
+    first, count, n = job
+    _limit_threads(1)
+    from sella_b200.synthetic import quadratic_batch
+    return quadratic_batch(count, n, first=first)
+
+
+class _CpuSearch:
+    """One saddle search on the host with the reference's algorithm: the reference's OWN Sella + PES
+    classes (kind 'reference'; loaded piecewise by oracle/ref_loader.py from /root/reference or from its
+    staged copy baseline/_ref/) when they can serve the workload, else the oracle port (kind 'port')."""
+
+    def __init__(self, wl, index, n, rs, method, kdiag, diag_every, proj_rot, prefer_reference=True):
+        from sella_b200.synthetic import quadratic_system, quadratic_func
+        C = c = None
         if wl == "quadratic":
-            A, xs, x0 = quadratic_system(first + i, n)
-            p = CartesianPES(quadratic_func(A, xs), x0)
-        elif proj_rot and wl == "emt-cluster":
-            from oracle.pes import NonlinearPES
-            p = NonlinearPES(emt_func(cell, pbc), X0[i], dict(rotation_ref=X0[i].reshape(-1, 3)), np.zeros(3), C, C @ X0[i])
+            A, xs, x0 = quadratic_system(index, n)
+            func = quadratic_func(A, xs)
         else:
-            p = CartesianPES(emt_func(cell, pbc), X0[i], C, C @ X0[i])
-        o = SaddleSearch(p, method=method, rs=rs, diag_maxiter=kdiag, diag_every_n=diag_every)
-        runs.append(o)
+            from oracle.emt import emt_func
+            ns = argparse.Namespace(workload=wl, n=n)
+            X0, C, cell, pbc = emt_problem(ns, index, 1)
+            x0 = X0[0]
+            func = emt_func(cell, pbc)
+            c = C @ x0
+        self.kind = "port"
+        nonlinear = proj_rot and wl == "emt-cluster"
+        ref = None
+        if prefer_reference and not nonlinear:
+            try:
+                from oracle import ref_loader, ref_harness
+                if ref_loader.available():
+                    ref = ref_loader.load()
+            except Exception:
+                ref = None
+        if ref is not None:
+            self.dyn = ref_harness.make_reference_sella(ref, func, x0, C, c, method=method, rs=rs,
+                                                        diag_every_n=diag_every)
+            self.dyn.diagkwargs["maxiter"] = kdiag      # PES.diag(maxiter=...), peswrapper.py:508
+            self.pes = self.dyn.pes
+            self.kind = "reference"
+        else:
+            from oracle.driver import SaddleSearch
+            if nonlinear:
+                from oracle.pes import NonlinearPES
+                self.pes = NonlinearPES(func, x0, dict(rotation_ref=x0.reshape(-1, 3)), np.zeros(3), C, c)
+            else:
+                from oracle.pes import CartesianPES
+                self.pes = CartesianPES(func, x0, C, c)
+            self.dyn = SaddleSearch(self.pes, method=method, rs=rs, diag_maxiter=kdiag, diag_every_n=diag_every)
+
+    def step(self):
+        self.dyn.step()
+
+    def x(self):
+        return np.asarray(self.pes.get_x(), dtype=float).copy()
+
+    def lowest_eval(self):
+        ev = self.pes.H.evals
+        return None if ev is None else float(ev[0])
+
+
+def _cpu_worker(job):
+    """Runs the searches `indices` for warm + steps steps with `threads` BLAS threads; returns
+    (steps done, seconds in the timed part, kind)."""
+    indices, n, rs, kdiag, diag_every, warm, steps, threads, method, wl, proj_rot = job
+    limiter = _limit_threads(threads)
+    runs = [_CpuSearch(wl, i, n, rs, method, kdiag, diag_every, proj_rot) for i in indices]
     done = 0
     alive = []
     for o in runs:
@@ -171,44 +260,49 @@ def _cpu_worker(job):
             pass
     dt = time.perf_counter() - t0
     del limiter
-    return done, dt
+    return done, dt, (runs[0].kind if runs else "port")
 
 
-def cpu_reference(args, warm, steps, budget_s=25.0):
-    """The reference's algorithm (oracle port; the reference package itself cannot be
-    imported on the GPU box: it needs ase/jax) on the host cores, two ways: one
-    process with all BLAS threads, and one single-threaded process per core."""
+def _parity_worker(job):
+    """In-run parity: system `index` of the timed batch taken `nsteps` steps on the host; returns
+    (final positions, lowest eigenvalue of the approximate Hessian, kind, error text)."""
+    index, n, rs, kdiag, diag_every, nsteps, method, wl, proj_rot = job
+    _limit_threads(1)
+    try:
+        o = _CpuSearch(wl, index, n, rs, method, kdiag, diag_every, proj_rot)
+        for _ in range(nsteps):
+            o.step()
+        return o.x(), o.lowest_eval(), o.kind, None
+    except Exception as exc:
+        return None, None, "port", repr(exc)
+
+
+def cpu_reference(args, warm, steps, per_proc=2):
+    """The reference's algorithm on the host cores, timed on a FIXED sample: systems 0 .. cores*per_proc-1
+    of rank 0's batch (the same inputs the GPU arm runs), one single-threaded process per core, rate =
+    median per-process rate x processes; beside it one process with all BLAS threads on system 0.  The
+    better of the two is reported."""
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    # calibrate: one system, all threads
-    t0 = time.perf_counter()
-    done, dt = _cpu_worker((0, 1, args.n, args.rs, args.kdiag, args.diag_every, warm, steps, cores, args.method,
-                            args.workload, args.proj_rot))
-    wall1 = time.perf_counter() - t0
-    rate_mt = done / dt
-    per_sys_wall = wall1
-    # one single-threaded worker per core, sample sized to ~budget
-    nproc = cores
-    ctx = mp.get_context("spawn")
-    est_1t = per_sys_wall * 2.5          # single-thread BLAS is slower per system
-    per_proc = max(1, int(budget_s / max(est_1t, 1e-3)))
-    per_proc = min(per_proc, 4)
     if args.cpu_systems:
-        per_proc = max(1, args.cpu_systems // nproc)
-    jobs = [(100 + i * per_proc, per_proc, args.n, args.rs, args.kdiag, args.diag_every, warm, steps, 1,
-             args.method, args.workload, args.proj_rot) for i in range(nproc)]
-    t0 = time.perf_counter()
-    with ctx.Pool(nproc) as pool:
+        per_proc = max(1, args.cpu_systems // cores)
+    common = (args.n, args.rs, args.kdiag, args.diag_every, warm, steps)
+    tail = (args.method, args.workload, args.proj_rot)
+    done, dt, kind = _cpu_worker(([0], ) + common + (cores,) + tail)
+    rate_mt = done / dt if dt > 0 else 0.0
+    ctx = mp.get_context("spawn")
+    jobs = [(list(range(i * per_proc, (i + 1) * per_proc)),) + common + (1,) + tail for i in range(cores)]
+    with ctx.Pool(cores) as pool:
         res = pool.map(_cpu_worker, jobs)
-    tot_steps = sum(r[0] for r in res)
-    slowest = max(r[1] for r in res)
-    rate_mp = tot_steps / slowest
+    rates = sorted(r[0] / r[1] for r in res if r[1] > 0 and r[0] > 0)
+    rate_mp = (rates[len(rates) // 2] if len(rates) % 2 else 0.5 * (rates[len(rates) // 2 - 1] + rates[len(rates) // 2])) \
+        * cores if rates else 0.0
     best = max(rate_mt, rate_mp)
-    mode = "%d procs x 1 BLAS thread" % nproc if rate_mp >= rate_mt else "1 proc x %d BLAS threads" % cores
-    return dict(value=best, unit=UNIT, cores=cores, kind="port",
-                sample="%d systems x (%d warm-up + %d timed) steps, %s; other mode: %.3g"
-                       % (nproc * per_proc if rate_mp >= rate_mt else 1, warm, steps, mode,
-                          min(rate_mt, rate_mp)))
+    mode = "%d procs x 1 BLAS thread" % cores if rate_mp >= rate_mt else "1 proc x %d BLAS threads" % cores
+    return dict(value=best, unit=UNIT, cores=cores, kind=kind,
+                sample="systems 0..%d of the GPU arm's batch x (%d warm-up + %d timed) steps, %s (median per-process "
+                       "rate x processes); other mode: %.3g"
+                       % (cores * per_proc - 1 if rate_mp >= rate_mt else 0, warm, steps, mode, min(rate_mt, rate_mp)))
 
 
 def run_reference(args):
@@ -219,13 +313,15 @@ def run_reference(args):
     t0 = time.perf_counter()
     cb = cpu_reference(args, warm, steps)
     wall = time.perf_counter() - t0
+    what = ("the reference's own Sella + PES classes (unmodified files, oracle/ref_loader.py)" if cb["kind"] == "reference"
+            else "CPU restatement (oracle/) of the reference path")
     out = dict(metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warm,
                ms_per_step=1e3 * args.batch / cb["value"], higher_is_better=True, scaling="weak",
                vs_baseline=None, dtype="f64", data="synthetic", impl="reference", config=workload(args),
                cpu_baseline=cb,
                e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-               note="CPU restatement (oracle/) of the reference path on host cores; ms_per_step is the "
-                    "extrapolated time for one step of the whole %d-system batch; wall %.1fs" % (args.batch, wall))
+               note="%s on host cores; ms_per_step is the extrapolated time for one step of the whole "
+                    "%d-system batch; wall %.1fs" % (what, args.batch, wall))
     print(json.dumps(out))
 
 
@@ -298,12 +394,32 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def host_generated_batch(first, count, n, dev, world=1, chunk=64):
+    """Systems first..first+count-1 of the synthetic family, generated on the HOST by the numpy recipe
+    (seed 1000 + index, sella_b200/synthetic.py) in a pool of workers and uploaded chunk by chunk: the
+    CPU arm and the in-run parity check run the very same systems."""
+    import multiprocessing as mp
+    import torch
+    A = torch.empty((count, n, n), dtype=torch.float64, device=dev)
+    xs = torch.empty((count, n), dtype=torch.float64, device=dev)
+    x0 = torch.empty((count, n), dtype=torch.float64, device=dev)
+    workers = max(1, min(16, (os.cpu_count() or 1) // max(1, world)))
+    per = max(1, min(chunk, (count + workers - 1) // workers))
+    jobs = [(first + lo, min(per, count - lo), n) for lo in range(0, count, per)]
+    with mp.get_context("spawn").Pool(workers) as pool:
+        for (f0, cnt, _), (Ac, xc, x0c) in zip(jobs, pool.imap(_gen_chunk, jobs)):
+            lo = f0 - first
+            A[lo:lo + cnt] = torch.from_numpy(Ac).to(dev)
+            xs[lo:lo + cnt] = torch.from_numpy(xc).to(dev)
+            x0[lo:lo + cnt] = torch.from_numpy(x0c).to(dev)
+    return A, xs, x0
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from sella_b200 import _lib, kernels as K
     from sella_b200.batched import BatchedSella, QuadraticSurface
-    from sella_b200.synthetic import quadratic_batch_torch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -313,19 +429,29 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
+        # stdout carries the single JSON line: NCCL's own log (whatever level the driver asked for via
+        # NCCL_DEBUG; WARN if it did not) goes to a file next to the bench, one per rank
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        if "NCCL_DEBUG_FILE" not in os.environ:
+            logdir = os.path.join(ROOT, "gpurun_out")
+            try:
+                os.makedirs(logdir, exist_ok=True)
+                os.environ["NCCL_DEBUG_FILE"] = os.path.join(logdir, "nccl_bench.%h.%p.log")
+            except OSError:
+                pass
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.get_lib()
     lib.sb_launch_count.restype = __import__("ctypes").c_longlong
 
     b, n = args.batch, args.n
     cons = None
+    first = rank * b                     # global index of this rank's first system (= its seed index)
     if args.workload == "quadratic":
-        A, xs, x0 = quadratic_batch_torch(b, n, dev, seed=1000 + rank)
+        A, xs, x0 = host_generated_batch(first, b, n, dev, world)
         surf = QuadraticSurface(A, xs)
     else:
         from sella_b200.emt import EMTSurface
-        X0, C, cell, pbc = emt_problem(args, 1000 + rank * b, b)
+        X0, C, cell, pbc = emt_problem(args, first, b)
         x0 = torch.from_numpy(X0).to(dev)
         surf = EMTSurface(b, n // 3, dev, cell=cell, pbc=pbc)
         cons = (C, None)
@@ -333,9 +459,11 @@ def run_ours(args):
             from sella_b200.internal import BatchedInternals
             cons = (C, None, BatchedInternals(n // 3, rotation_ref=X0.reshape(b, n // 3, 3)), None)
 
+    extra = {} if args.spectrum is None else dict(spectrum=args.spectrum)
+
     def make():
         return BatchedSella(surf, x0, method=args.method, rs=args.rs, diag_maxiter=args.kdiag,
-                            diag_every_n=args.diag_every, kcap=max(8, args.kdiag + 1), constraints=cons)
+                            diag_every_n=args.diag_every, kcap=max(8, args.kdiag + 1), constraints=cons, **extra)
 
     def barrier():
         torch.cuda.synchronize()
@@ -346,9 +474,7 @@ def run_ours(args):
     # one-off, untimed: a throw-away engine takes 7 steps so that every kernel variant of a step and of a
     # re-diagonalisation is loaded (CUDA loads kernels lazily on first use; a re-diagonalisation first
     # happens at step 5, i.e. inside the timed region, where it cost ~20 % of the measured rate)
-    pre = BatchedSella(surf, x0, method=args.method, rs=args.rs,
-                       diag_maxiter=args.kdiag, diag_every_n=args.diag_every, kcap=max(8, args.kdiag + 1),
-                       constraints=cons)
+    pre = make()
     for _ in range(7):
         pre.step()
     del pre
@@ -391,6 +517,58 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = world * b * args.steps / (ms_max / 1e3)
+
+    # ---------------- in-run parity: systems 0..P-1 of THIS run's timed batch vs the reference algorithm on
+    # the host for the same warm-up + timed steps (same seeds -> same A, x*, x0)
+    parity = None
+    if rank == 0 and args.parity_systems > 0:
+        import multiprocessing as mp
+        npar = min(args.parity_systems, b)
+        nst = args.warmup + args.steps
+        jobs = [(first + i, n, args.rs, args.kdiag, args.diag_every, nst, args.method, args.workload, args.proj_rot)
+                for i in range(npar)]
+        with mp.get_context("spawn").Pool(min(npar, os.cpu_count() or 1)) as pool:
+            res = pool.map(_parity_worker, jobs)
+        xg = eng.x[:npar].cpu().numpy()
+        lg = eng.lowest_evals()[:npar].cpu().numpy()
+        dxs, dls, errs = [], [], []
+        for i, (xr, lr, kind, err) in enumerate(res):
+            if xr is None:
+                errs.append("system %d: %s" % (i, err))
+                continue
+            dxs.append(float(np.abs(xg[i] - xr).max()))
+            if lr is not None:
+                dls.append(float(abs(lg[i] - lr) / max(abs(lr), 1e-300)))
+        parity = dict(systems=npar, steps=nst, max_dx=max(dxs) if dxs else None,
+                      max_rel_lam=max(dls) if dls else None, checker=res[0][2] if res else None,
+                      compared=len(dxs), errors=errs,
+                      note="max |x_gpu - x_cpu| (Angstrom-like units of the synthetic surface) and relative difference "
+                           "of the lowest eigenvalue of the approximate Hessian after `steps` steps, systems 0..%d of "
+                           "the timed batch" % (npar - 1))
+
+    # ---------------- long run: ms per batch step by decile of a >= 100-step search (fresh engine; the
+    # headline above stays the driver's K/W) -- shows whether the step cost drifts as the Hessian model
+    # accumulates rank
+    long_run = None
+    if args.long_steps > 0:
+        engl = make()
+        nl_ = max(10, args.long_steps // 10 * 10)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(11)]
+        barrier()
+        evs[0].record()
+        for d in range(10):
+            for _ in range(nl_ // 10):
+                engl.step()
+            evs[d + 1].record()
+        barrier()
+        dec = [evs[d].elapsed_time(evs[d + 1]) / (nl_ // 10) for d in range(10)]
+        long_run = dict(steps=nl_, decile_ms_per_step=dec, rank_rows_max=engl.rank_bound(),
+                        note="ms per step of the whole batch, mean over each tenth of the run; rank_rows_max = "
+                             "explicit eigenpairs the model may hold at the end (2 per step + 2k per diagonalisation, "
+                             "capped at 3N); the eigenvector rotation costs O(r^2 n) per rank-one term, i.e. the step "
+                             "cost climbs until r reaches 3N and is flat afterwards")
+        del engl
+        torch.cuda.empty_cache()
 
     # ---------------- end-to-end through host buffers: `e2e`
     # the caller owns positions on the host (as ASE does): every step uploads the
@@ -497,7 +675,8 @@ def run_ours(args):
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                    ms_per_step=step_ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                    data="synthetic", config=workload(args), clocks=clocks, e2e=e2e,
-                   gpu_launches=int(launches), roofline=roofline, roofline_eigen_update=roofline_eig,
+                   gpu_launches=int(launches), parity=parity, long_run=long_run, roofline=roofline,
+                   roofline_eigen_update=roofline_eig,
                    kernel_ms=kernel_ms, systems_flagged=flagged, diagonalisations=eng.ndiag,
                    note="systems_flagged: per-system status words (the batched analogue of the reference's "
                         "exceptions); restricted_step_noconv reproduces the reference's own 'Restricted step "

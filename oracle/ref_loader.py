@@ -35,9 +35,51 @@ import sysconfig
 import tempfile
 import types
 
-REF_ROOT = os.environ.get("SELLA_REFERENCE_ROOT", "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_BIN = os.path.join(HERE, "_ref")
+# git-ignored staging area that travels to the GPU box (the base contract's baseline/_ref): the
+# reference's own files on the benchmarked path, copied there by stage() at build time
+STAGED_ROOT = os.path.join(os.path.dirname(HERE), "baseline", "_ref")
+STAGED_FILES = ["eigensolvers.py", "hessian_update.py", "linalg.py", "_gpu.py", "peswrapper.py",
+                "utilities/math.pyx", "utilities/math.pxd", "optimize/stepper.py",
+                "optimize/restricted_step.py", "optimize/optimize.py"]
+
+
+def _pick_root():
+    env = os.environ.get("SELLA_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile(os.path.join("/root/reference", "sella", "eigensolvers.py")):
+        return "/root/reference"
+    return STAGED_ROOT
+
+
+REF_ROOT = _pick_root()
+
+
+def stage(force: bool = False) -> str:
+    """Copy the reference's files on the benchmarked path (unmodified) from /root/reference into the
+    git-ignored baseline/_ref/, so that `bench.py --impl reference` and the cpu_baseline leg can run the
+    reference's OWN classes on the GPU box, where /root/reference does not exist."""
+    import shutil
+    src_root = os.path.join("/root/reference", "sella")
+    if not os.path.isdir(src_root):
+        raise RuntimeError("reference tree not present; nothing to stage")
+    for rel in STAGED_FILES:
+        src = os.path.join(src_root, rel)
+        dst = os.path.join(STAGED_ROOT, "sella", rel)
+        if not os.path.isfile(src):
+            continue
+        if force or not os.path.isfile(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
+            os.makedirs(os.path.dirname(dst), exist_ok=True)
+            shutil.copyfile(src, dst)
+    return STAGED_ROOT
+
+
+def source() -> str:
+    """Where load() takes the reference from: 'reference tree' or 'staged copy' (baseline/_ref)."""
+    return "staged copy (baseline/_ref)" if os.path.abspath(REF_ROOT) == os.path.abspath(STAGED_ROOT) \
+        else "reference tree (%s)" % REF_ROOT
 
 _loaded = None
 

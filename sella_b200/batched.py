@@ -62,7 +62,8 @@ class BatchedSella:
                  rho_dec=None, rho_inc=None, eig=None, eta=1e-4, method=None, gamma=0.1,
                  rs=None, nsteps_per_diag=3, diag_every_n=None, diag_maxiter=None,
                  eigensolver="jd0", update_method="TS-BFGS", kcap=16, eig_mode="update",
-                 eig_refresh_every=0, constraints=None, threepoint=False, hessian_function=None, v0=None):
+                 eig_refresh_every=0, constraints=None, threepoint=False, hessian_function=None, v0=None,
+                 spectrum=None):
         require_cuda()
         d = _DEFAULTS["minimum" if order == 0 else "saddle"]
         self.surface = surface
@@ -112,6 +113,9 @@ class BatchedSella:
         if eig_mode not in ("update", "direct"):
             raise ValueError("eig_mode must be 'update' or 'direct'")
         self.eig_mode = eig_mode
+        if spectrum not in (None, "compact", "dense"):
+            raise ValueError("spectrum must be 'compact' or 'dense'")
+        self._spectrum_request = spectrum
         self.eig_refresh_every = int(eig_refresh_every)
         self._updates_since_refresh = 0
 
@@ -174,6 +178,7 @@ class BatchedSella:
             # optimize.py:183-187: the spherical radius scales with the number of free coordinates
             self.delta.fill_(float(delta0 * self.cons["nfree"]))
         self.initialized = False
+        self._evaluated = False
         self.ndiag = 0
         self.prof = None          # set to {} to collect CUDA-event timings of selected kernels
 
@@ -650,7 +655,7 @@ class BatchedSella:
         """One Sella.step for every (active) system."""
         b, n = self.batch, self.n
         if not self.initialized:
-            self.surface.evaluate(self.x, self.f, self.g)
+            self.ensure_evaluated()
             if self.eig:
                 if self.hessian_function is not None:
                     self._calculate_hessian()
@@ -737,11 +742,21 @@ class BatchedSella:
              _p(self.s), _p(self.up1["BS"]), _p(self.smag), _p(self.dg), _p(self.delta), _p(self.rho),
              _p(self.nsteps), self._dpar, self._ipar, I(n), _p(active), I(b), _stream())
         self._update(S1, self.dg.view(b, 1, n), self.up1, None, 1, active, bs_ready=True, abs_ready=abs_ready)
-        if self.eig and int(self.ev.sum().item()) > 0:
+        # kick(dx, diag=ev) diagonalises whenever ev is set, whatever `eig` says (optimize.py:362-380:
+        # diag_every_n fires for eig=False runs too)
+        if int(self.ev.sum().item()) > 0:
             if self.hessian_function is not None:
                 self._calculate_hessian(self.ev)
             else:
                 self._diag(self.ev)
+
+    def ensure_evaluated(self):
+        """Energy and gradient at the current geometry, evaluated at most once per geometry
+        (PES._update, peswrapper.py:440-465): converged()/log() before the first step and the
+        first step itself share one surface call."""
+        if not self._evaluated:
+            self.surface.evaluate(self.x, self.f, self.g)
+            self._evaluated = True
 
     def converged(self, fmax, cmax=1e-5):
         """PES.converged (peswrapper.py:558-568): max atomic |P_f g| < fmax and |res| < cmax."""
@@ -759,6 +774,19 @@ class BatchedSella:
         call("sb_converged_cons", _p(cn["pg"]), _p(cn["res"]), I(cn["nc"]), I(n), D(float(fmax)), D(float(cmax)),
              _p(self.fmax), _p(cn["cmax"]), _p(self.conv), I(b), _stream())
         return self.conv
+
+    def lowest_evals(self):
+        """[b] lowest eigenvalue of the approximate Hessian B of every system (refreshes a stale spectrum)."""
+        if not self.H_initialized:
+            return torch.ones(self.batch, dtype=torch.float64, device=self.dev)
+        if not self.eig_valid:
+            self._eigh(None)
+            self.eig_valid = True
+        return self.evalsB[:, 0].clone()
+
+    def rank_bound(self):
+        """Upper bound (host-side count) on the number of distinct non-cluster eigenpairs of the model."""
+        return min(self.n, getattr(self, "_rank_bound", self.n))
 
     def check_status(self):
         st = self.status.cpu().numpy()

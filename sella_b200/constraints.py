@@ -36,6 +36,55 @@ class Constraints:
         self._targets = []
         self._nl = dict(bonds=[], angles=[], dihedrals=[])
         self._rot_ref = None
+        # sella/internal.py:2760-2762: ASE constraints attached to the atoms become Sella constraints
+        for ase_cons in (getattr(atoms, "constraints", None) or []):
+            self.merge_ase_constraint(ase_cons)
+
+    def merge_ase_constraint(self, ase_cons):
+        """sella/internal.py:2981-3030.  ASE is an optional dependency: the classes are recognised by
+        name and by the attributes the reference reads (FixAtoms.index, FixCartesian.a/.mask,
+        FixBondLengths.pairs/.bondlengths, FixInternals.bonds/.angles/.dihedrals/.bondcombos)."""
+        kind = type(ase_cons).__name__
+        if kind == "FixAtoms":
+            for index in np.atleast_1d(ase_cons.index):
+                try:
+                    self.fix_translation(int(index), replace_ok=False)
+                except DuplicateConstraintError:
+                    pass
+        elif kind == "FixCom":
+            try:
+                self.fix_translation(replace_ok=False)
+            except DuplicateConstraintError:
+                pass
+        elif kind == "FixBondLengths":
+            lengths = getattr(ase_cons, "bondlengths", None)
+            for i, indices in enumerate(ase_cons.pairs):
+                try:
+                    self.fix_bond(indices, mic=True, target=None if lengths is None else lengths[i],
+                                  replace_ok=False)
+                except DuplicateConstraintError:
+                    pass
+        elif kind == "FixCartesian":
+            a = getattr(ase_cons, "a", getattr(ase_cons, "index", None))
+            for dim, relaxed in enumerate(ase_cons.mask):
+                if relaxed:
+                    continue
+                try:
+                    self.fix_translation(a, dim=dim, replace_ok=False)
+                except DuplicateConstraintError:
+                    pass
+        elif kind == "FixInternals":
+            for lst, adder in ((ase_cons.bonds, self.fix_bond), (ase_cons.angles, self.fix_angle),
+                               (ase_cons.dihedrals, self.fix_dihedral)):
+                for target, indices in lst:
+                    try:
+                        adder(indices, target=target, replace_ok=False)
+                    except DuplicateInternalError:
+                        pass
+            if getattr(ase_cons, "bondcombos", None):
+                raise RuntimeError("Sella currently does not support combination constraints.")
+        else:
+            raise RuntimeError("Sella does not currently implement the ASE {} Constraint class.".format(kind))
 
     def fix_translation(self, index=None, dim=None, target=None, replace_ok=True):
         if index is None:
@@ -81,7 +130,8 @@ class Constraints:
     def _fix_internal(self, name, width, conv, indices, ncvecs=None, mic=None, target=None, comparator='eq',
                       replace_ok=True):
         """sella/internal.py:2906-2947."""
-        if ncvecs is not None or mic:
+        periodic = bool(np.any(np.asarray(getattr(self.atoms, "pbc", False))))
+        if ncvecs is not None or (mic and periodic):
             raise NotImplementedError("periodic-image constraints (ncvecs / mic) are not on the CUDA path yet")
         if comparator != 'eq':
             raise NotImplementedError("inequality constraints are not on the CUDA path yet")

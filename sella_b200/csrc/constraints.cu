@@ -92,8 +92,8 @@ scons_measure_kernel(const double* __restrict__ scons, const double* __restrict_
     }
 }
 
-// stot = slift + scons for regular systems; stot = scons * delta/cons(scons), smag = delta
-// for the naive branch (NaiveStepper: s(alpha) = alpha*scons, root alpha = delta/cons(scons)).
+// stot = slift + scons for regular systems; the naive branch (NaiveStepper: s(alpha) = alpha*scons,
+// alpha0 = 0.5) returns 0.5*scons when that is inside the radius, else the root alpha = delta/cons(scons).
 __global__ void combine_step_kernel(const double* __restrict__ slift, const double* __restrict__ scons,
                                     const double* __restrict__ consval, const double* __restrict__ delta,
                                     const int* __restrict__ naive, double* __restrict__ stot, double* __restrict__ smag,
@@ -104,8 +104,12 @@ __global__ void combine_step_kernel(const double* __restrict__ slift, const doub
     if (i >= n) return;
     const size_t o = (size_t)b * n + i;
     if (naive[b]) {
-        stot[o] = scons[o] * (delta[b] / consval[b]);
-        if (i == 0) smag[b] = delta[b];
+        // NaiveStepper (stepper.py:44-55) starts its search at alpha0 = 0.5 and the interior test of
+        // restricted_step.py:81-84 comes first: for delta < cons(scons) < 2 delta the step is 0.5*scons
+        const double half = 0.5 * consval[b];
+        const bool interior = half < delta[b];
+        stot[o] = scons[o] * (interior ? 0.5 : delta[b] / consval[b]);
+        if (i == 0) smag[b] = interior ? half : delta[b];
     } else {
         stot[o] = slift[o] + scons[o];
     }

@@ -65,9 +65,10 @@ except Exception:
 class _CalculatorSurface:
     """PES plug-in that evaluates the user's ASE calculator on the host (batch of one)."""
 
-    def __init__(self, atoms):
+    def __init__(self, atoms, traj=None):
         self.atoms = atoms
         self.neval = 0
+        self.traj = traj
 
     def evaluate(self, x, f_out, g_out, active=None):
         self.neval += 1
@@ -75,6 +76,8 @@ class _CalculatorSurface:
         self.atoms.positions = x[0].cpu().numpy().reshape((-1, 3))
         f = float(self.atoms.get_potential_energy())
         g = -np.asarray(self.atoms.get_forces(), dtype=np.float64).ravel()
+        if self.traj is not None:
+            self.traj.write()            # PES.eval writes every evaluated geometry (peswrapper.py:409-418)
         self.atoms.positions = old
         f_out.copy_(torch.tensor([f], dtype=torch.float64))
         g_out.copy_(torch.from_numpy(g).view(1, -1))
@@ -101,6 +104,7 @@ class _PESView:
 
     def converged(self, fmax, cmax=1e-5):
         e = self._o._eng
+        e.ensure_evaluated()
         e.converged(fmax, cmax)
         f1 = float(e.fmax[0])
         c1 = float(e.cons["cmax"][0]) if e.cons is not None else 0.0
@@ -161,8 +165,23 @@ class Sella(_Base):
         diag_maxiter = kwargs.pop("diag_maxiter", None)
         if kwargs:
             raise TypeError("unsupported keyword arguments: %s" % sorted(kwargs))
+        if trajectory is not None and isinstance(trajectory, str):
+            # optimize.py:144-150: a file name opens an ASE Trajectory attached to the atoms
+            if not _HAVE_ASE:
+                raise NotImplementedError("trajectory=<file name> needs ASE (ase.io.trajectory.Trajectory); "
+                                          "pass an object with a write() method or install ASE")
+            from ase.io.trajectory import Trajectory
+            trajectory = Trajectory(trajectory, mode="a" if append_trajectory else "w", atoms=atoms, master=master)
+        elif trajectory is not None and not hasattr(trajectory, "write"):
+            raise TypeError("trajectory must be a file name or an object with a write() method")
+        if restart is not None and not _HAVE_ASE:
+            # the reference hands `restart` to ase.optimize.Optimizer (it has no read() of its own)
+            raise NotImplementedError("restart files are handled by ASE's Optimizer, which is not installed")
         _Base.__init__(self, atoms, restart=restart, logfile=logfile, trajectory=None, master=master)
-        self._surface = _CalculatorSurface(atoms)
+        if trajectory is not None and isinstance(trajectory, object) and hasattr(self, "closelater") \
+                and hasattr(trajectory, "close"):
+            self.closelater(trajectory)
+        self._surface = _CalculatorSurface(atoms, traj=trajectory)
         x0 = torch.from_numpy(np.asarray(atoms.positions, dtype=np.float64).reshape(1, -1).copy()).to(dev())
         if rs is None:
             rs = 'ras'
@@ -224,9 +243,8 @@ class Sella(_Base):
 
     def converged(self, forces=None):
         fmax = self.fmax if self.fmax is not None else 0.05
-        if not self._eng.initialized:
-            # the reference evaluates the surface once before the first convergence test
-            self._eng.surface.evaluate(self._eng.x, self._eng.f, self._eng.g)
+        # the reference evaluates the surface once before the first convergence test; the engine
+        # reuses that evaluation in its first step (PES._update, peswrapper.py:440-465)
         return bool(self.pes.converged(fmax)[0])
 
     def gradient_converged(self, gradient=None):

@@ -268,6 +268,40 @@ def test_engine_with_fixed_atom_constraints_matches_oracle(n, method, rs):
         np.testing.assert_allclose(float(eng.fmax[i]), f_ref, rtol=1e-3, atol=1e-7)
 
 
+@pytest.mark.parametrize("factor", [1.5, 3.0])
+@pytest.mark.parametrize("rs", ["tr", "ras"])
+def test_engine_naive_branch_with_displaced_target(rs, factor):
+    """A constraint target moved off the current value by more than the radius: the
+    NaiveStepper branch (restricted_step.py:39-43, stepper.py:44-55).  With
+    delta < cons(scons) < 2 delta the reference returns the interior step 0.5*scons
+    (alpha0 = 0.5), beyond that the root alpha = delta / cons(scons)."""
+    from oracle.pes import CartesianPES
+    from oracle.driver import SaddleSearch
+    from sella_b200.synthetic import quadratic_func
+    n, systems = 30, [0, 1, 2]
+    C = np.eye(n)[:3]
+    delta0 = 0.1
+    radius = delta0 if rs == "ras" else delta0 * (n - 3)
+    from sella_b200.synthetic import quadratic_system
+    c = np.stack([C @ quadratic_system(b, n)[2] for b in systems])
+    c[:, 0] += factor * radius                              # one fixed coordinate asked to move
+    eng, data = make_engine(n, systems, method="qn", rs=rs, constraints=(C, c))
+    oracles = []
+    for i, (A, xs, x0) in enumerate(data):
+        p = CartesianPES(quadratic_func(A, xs), x0, C, c[i])
+        oracles.append((p, SaddleSearch(p, method="qn", rs=rs)))
+    for t in range(6):
+        eng.step()
+        x = eng.x.cpu().numpy(); delta = eng.delta.cpu().numpy()
+        for i, (p, o) in enumerate(oracles):
+            o.step()
+            np.testing.assert_allclose(x[i], p.get_x(), rtol=0, atol=1e-8, err_msg="system %d step %d" % (i, t))
+            np.testing.assert_allclose(delta[i], o.delta, rtol=1e-8)
+            if t == 0:
+                np.testing.assert_allclose(float(eng.smag[i]), o.history[-1]["smag"], rtol=1e-10)
+    eng.check_status()
+
+
 def test_engine_constraints_golden(golden):
     """Constrained cases of tests/golden/loop.npz (reference's own Sella + PES)."""
     G = golden("loop")
