@@ -621,60 +621,80 @@ def run_ours(args):
 
     xv = eng.g.view(b, 1, n)
     yv = torch.empty_like(xv)
-    hv_ms = timed(lambda: K.hv_ld(eng.B, xv, yv, 1), 20)
+    Mhv = surf.A if args.workload == "quadratic" else eng.B.contiguous()      # any resident [b, n, n] matrix
+    hv_ms = timed(lambda: K.hv_ld(Mhv, xv, yv, 1), 20)
     hv_bytes = b * 8 * (n * n + 2 * n)
     hv_gbs = hv_bytes / (hv_ms * 1e-3) / 1e9
-    # profiled pass (not part of `value`): CUDA events around the heaviest kernels of a step
+    # profiled pass (not part of `value`): CUDA events around the eigen-update of the plain steps
     import ctypes
     eng.prof = {}
-    lib.sb_secular_timing(None, 1)
-    t3 = (ctypes.c_float * 3)()
+    compact = bool(getattr(eng, "compact", False))
     parts = []
+    if not compact:
+        lib.sb_secular_timing(None, 1)
+    t3 = (ctypes.c_float * 3)()
+    rows_before = float(eng.mrows.double().mean().item()) if compact else float(n)
     for _ in range(6):
         nd0 = eng.ndiag
         eng.step()
-        if eng.ndiag == nd0 and lib.sb_secular_timing(t3, -1) == 0:     # plain step: last call = the rank-2 update
+        if not compact and eng.ndiag == nd0 and lib.sb_secular_timing(t3, -1) == 0:   # plain step: the rank-2 update
             parts.append(tuple(t3))
-    lib.sb_secular_timing(t3, 0)
+    if not compact:
+        lib.sb_secular_timing(t3, 0)
+    rows_after = float(eng.mrows.double().mean().item()) if compact else float(n)
     prof = eng.prof_summary()
     eng.prof = None
     step_ms = ms_max / args.steps
-    sec_cnt, sec_ms = prof.get("secular_update_k1", (0, 0.0))
+    sec_cnt, sec_ms = prof.get("eigen_update_k1" if compact else "secular_update_k1", (0, 0.0))
     part_ms = [sum(p[i] for p in parts) / len(parts) for i in range(3)] if parts else [0.0, 0.0, 0.0]
-    sec_bytes = b * 8 * 2 * n * n               # every eigenvector read once and written once
+    caps = NCU_CAPTURES.get((b, n), {})
+    traffic, traffic_src = ncu_traffic(caps.get("eigen", ()), r"cluster_reflect|secular_update|cluster_qr|append_", per="group")
+    hv_traffic, hv_traffic_src = ncu_traffic(caps.get("hv", ()), r"hv_tma_kernel<1>")
+    if compact:
+        # one rank-2 eigen-update on r explicit rows: Z = VR P, W1 = VR^T Z, VR Qc, VR^T D2 (4 reads of the
+        # r x n block) + the secular rotation (read + write of the rows it changes, <= r)
+        r_mean = 0.5 * (rows_before + rows_after)
+        sec_bytes = b * 8 * n * 6.0 * r_mean
+        what = ("eigen-update of the compact spectrum after the rank-2 secant update (r = %.0f explicit rows of %d): "
+                "lowrank_factor + 4 rectangular H.V passes + append_a/b + secular_update_kernel" % (r_mean, n))
+        note = ("algorithmic bytes = 8 n (4 r + 2 r): four reads of the r x n block of explicit eigenvectors and one "
+                "read + write by the rotation; the rotation itself costs 2 r^2 n flops per rank-one term (fp64 FMA "
+                "bound once r is a few hundred), see DESIGN.md section 5")
+    else:
+        sec_bytes = b * 8 * 2 * n * n               # every eigenvector read once and written once
+        what = ("eigen-update of (evals, Vt) after the rank-2 secant update: cluster_qr_kernel + "
+                "cluster_reflect_kernel<2> + secular_update_kernel<4> (dense representation)")
+        note = ("algorithmic bytes = read+write the eigenvector matrix once (2*n^2*8 per system); cluster_reflect "
+                "streams the degenerate cluster's rows; secular_update_kernel is latency-bound, see DESIGN.md section 5")
     sec_gbs = sec_bytes / (sec_ms * 1e-3) / 1e9 if sec_ms else 0.0
-    # DRAM bytes per launch from `ncu --set full` of the same workload (profiles/ncu_full_r1_h_*.csv)
-    traffic = NCU_TRAFFIC.get((b, n))
-    roofline_eig = dict(kernel="eigen-update of (evals, Vt) after the rank-2 secant update: cluster_qr_kernel + "
-                               "cluster_reflect_kernel<2> + secular_update_kernel<4> (one sb_secular_update per step; "
-                               "the largest single item of a step)",
-                        bound="hbm", achieved=sec_gbs, peak=peak, unit="GB/s", frac=sec_gbs / peak, traffic=traffic,
+    roofline_eig = dict(kernel=what, bound="hbm", achieved=sec_gbs, peak=peak, unit="GB/s", frac=sec_gbs / peak,
+                        traffic=traffic, traffic_source=("profiles/" + traffic_src) if traffic_src else None,
                         ms_per_launch=sec_ms, share_of_step=min(1.0, sec_ms / step_ms) if step_ms else None,
                         bytes_per_launch=sec_bytes, peak_source=peak_src,
+                        explicit_rows=dict(before=rows_before, after=rows_after, of=n),
                         kernels_ms=dict(cluster_qr_kernel=part_ms[0], cluster_reflect_kernel=part_ms[1],
-                                        secular_update_kernel=part_ms[2]),
-                        note="algorithmic bytes = read+write the eigenvector matrix once (2*n^2*8 per system); "
-                             "cluster_reflect streams the degenerate cluster's rows (2 reads + 1 write, the second "
-                             "read mostly from L2); secular_update_kernel is latency-bound (deflation, secular "
-                             "roots, a few dozen rows rewritten), see DESIGN.md section 5")
+                                        secular_update_kernel=part_ms[2]) if not compact else None,
+                        note=note)
     # the dominant kernel family of a step by GPU time (profiles/launches_r1_j.txt: hv_tma / hvt_tma
     # variants = 41 %): the batched H.V pass, used for V^T g, V c, B s, the surface and Z = Vt P
     roofline = dict(kernel="hv_tma_kernel<1> (batched H.V: TMA bulk-copy pipeline, one pass over a [b, n, n] matrix; "
                            "~9 such passes per step, 41 % of GPU time with its <2>/<4>/transposed variants)",
                     bound="hbm", achieved=hv_gbs, peak=peak, unit="GB/s", frac=hv_gbs / peak,
-                    frac_of_8TBs_nominal=hv_gbs / 8000.0, traffic=NCU_TRAFFIC_HV.get((b, n)), ms_per_launch=hv_ms,
+                    frac_of_8TBs_nominal=hv_gbs / 8000.0, traffic=hv_traffic,
+                    traffic_source=("profiles/" + hv_traffic_src) if hv_traffic_src else None, ms_per_launch=hv_ms,
                     bytes_per_launch=hv_bytes, peak_source=peak_src,
                     note="read-dominated (the measured copy peak is a read+write figure, hence fractions close to "
                          "1); algorithmic bytes = 8 (n^2 + 2 n) per system")
     kernel_ms = {k: v[1] for k, v in prof.items()}
     if b * n * n <= 1024 * 768 * 768:             # a full batched eigensolve: seconds beyond this size
-        kernel_ms["sb_eigh_full (direct mode only; not on the default path)"] = timed(lambda: eng._eigh(None), 2)
+        kernel_ms["sb_eigh_full (direct mode only; not on the default path)"] = timed(lambda: K.eigh(Mhv), 2)
 
     out = None
     if rank == 0:
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                    ms_per_step=step_ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-                   data="synthetic", config=workload(args), clocks=clocks, e2e=e2e,
+                   data="synthetic", config=dict(workload(args), spectrum="compact" if compact else "dense"),
+                   clocks=clocks, e2e=e2e,
                    gpu_launches=int(launches), parity=parity, long_run=long_run, roofline=roofline,
                    roofline_eigen_update=roofline_eig,
                    kernel_ms=kernel_ms, systems_flagged=flagged, diagonalisations=eng.ndiag,

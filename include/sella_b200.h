@@ -294,6 +294,81 @@ int sb_qr(double* A, int m, int n, double* Q, double* R, double* work, const int
 int sb_trtri(const double* R, double* Rinv, double* work, int n, int32_t* status, const int32_t* active,
              int batch, void* stream);
 
+/* ---- compact representation of the approximate Hessian and of its spectrum --------------------
+ * B = lam0 I + VR^T diag(theta - lam0) VR: mrows[b] explicit eigenpairs (theta ascending in
+ * evals[b*estride + i], eigenvector i = row i of VR at VR + b*vstride + i*n) and the eigenvalue lam0[b]
+ * on the whole orthogonal complement, whose eigenvectors are never stored (a quasi-Newton Hessian
+ * is a scaled identity plus low rank, sella/hessian_update.py:58-111).  Replaces the dense
+ * eigh(B) of sella/linalg.py:174-195 / 293 at O(n m) per pass; for mrows = n it is the dense
+ * eigendecomposition.  numpy blueprint: tests/compact_proto.py.
+ *   sb_hv_rect          : sb_hv_ld on the first mrows (HOST bound) rows of A, systems astride doubles apart
+ *                         (transposed = 0: Y[b,v,:mrows] = A X; 1: Y[b,v,:] = sum_{i<mrows} X[b,v,i] A[i,:])
+ *   sb_compact_append_a : candidates Qc (unit, mutually orthogonal) for the part of the update vectors
+ *                         P [b,zcap,n] outside span(VR); W1 = VR^T (VR P) (two sb_hv_rect passes)
+ *   sb_compact_append_b : candidates projected once more (W2 = VR^T (VR Qc)), re-orthonormalised,
+ *                         appended as rows mrows.. with eigenvalue lam0; Z[b,t,mrows+j] = q_j.p_t;
+ *                         mrows[b] += number appended
+ *   sb_secular_update_c : sb_secular_update on the first mrows[b] rows (mcap: HOST bound on mrows)
+ *   sb_compact_prepare  : merged ascending pole list (width entries, stride width) for sb_qn_tr /
+ *                         sb_rfo_tr / the *_ras_c kernels: explicit eigenvalues with coefficients Vg = VR g,
+ *                         the complement as ONE pole lam0 with coefficient |g_perp| (g_perp = g - Wg,
+ *                         Wg = VR^T Vg), zero-weight copies of lam0 as padding; rowmap: explicit row, -1
+ *                         complement, -2 padding
+ *   sb_compact_finish   : pole coefficients -> C4[b,0..2,:] = c, |theta| c, theta c on the explicit rows,
+ *                         kappa[b] = c_complement / |g_perp|
+ *   sb_compact_finish2  : (T4 = VR^T C4)  s = T4[0] + kappa g_perp, |B| s, B s likewise, xnew = x + s
+ *   sb_compact_scale / sb_compact_axpy : f(B) S = f(lam0) S + VR^T[(f(theta) - f(lam0)) (VR S)],
+ *                         mode 0: f = |.| (the |B| S of TS-BFGS, hessian_update.py:118-125), 1: f = id
+ *   sb_compact_jd_coeff / sb_compact_jd_finish : Jacobi-Davidson correction (eigensolvers.py:115-139)
+ *                         in the eigenbasis of the preconditioner, method 0 jd0, 1 gd
+ *   sb_compact_lowest   : lowest eigenvalue of B per system
+ *   sb_qn_ras_c / sb_rfo_ras_c / sb_davidson_init_c : the dense kernels of the same name on a pole
+ *                         list / the compact rows                                                      */
+int sb_hv_rect(const double* A, long long astride, int mrows, const double* X, double* Y, const int32_t* active,
+               int batch, int n, int nvec, int ldv, int transposed, void* stream);
+int sb_compact_append_a(const double* P, const double* W1, int zcap, const int32_t* nterm, const int32_t* mrows,
+                        int n, double* Qc, int32_t* ncand, const int32_t* skip, int batch, void* stream);
+int sb_compact_append_b(const double* P, const double* Qc, const double* W2, int zcap, const int32_t* nterm,
+                        const int32_t* ncand, int n, double* evals, long long estride, double* VR, long long vstride,
+                        int32_t* mrows, const double* lam0, double* Z, const int32_t* skip, int batch, void* stream);
+int sb_secular_update_c(double* evals, double* Vt, double* Z, int zcap, const double* sig, const int32_t* nterm,
+                        int n, double* work, double* qwork, int32_t* status, const int32_t* skip,
+                        const int32_t* mrows, int mcap, long long estride, long long vstride, int batch,
+                        void* stream);
+int sb_compact_prepare(const double* g, const double* Vg, const double* Wg, const double* evals, long long estride,
+                       const int32_t* mrows, const double* lam0, int n, int width, double* gperp, double* gam,
+                       double* cev, double* cvg, int32_t* rowmap, const int32_t* active, int batch, void* stream);
+int sb_compact_finish(const double* ccoef, const int32_t* rowmap, int width, const double* evals, long long estride,
+                      const double* gam, int n, int mbound, double* C4, double* kappa, const int32_t* active,
+                      int batch, void* stream);
+int sb_compact_finish2(const double* T4, const double* gperp, const double* kappa, const double* lam0,
+                       const double* x, int n, double* s, double* absBs, double* Bs, double* xnew,
+                       const int32_t* active, int batch, void* stream);
+int sb_compact_scale(const double* VtS, const double* evals, long long estride, const int32_t* mrows,
+                     const double* lam0, int kcap, int nvec, int n, int mbound, int mode, double* out,
+                     const int32_t* skip, int batch, void* stream);
+int sb_compact_axpy(const double* S, const double* T, const double* lam0, int kcap, int nvec, int n, int mode,
+                    double* out, const int32_t* skip, int batch, void* stream);
+int sb_compact_jd_coeff(const double* rvhat, const double* rv, const double* evals, long long estride,
+                        const int32_t* mrows, const double* lam0, const double* theta, int n, int mbound, int method,
+                        double* that, double* ed, const int32_t* dav_state, int batch, void* stream);
+int sb_compact_jd_finish(double* t, const double* rv, const double* ed, int n, int method, const int32_t* dav_state,
+                         int batch, void* stream);
+int sb_compact_lowest(const double* evals, long long estride, const int32_t* mrows, const double* lam0, int n,
+                      double* out, int batch, void* stream);
+int sb_qn_ras_c(const double* Vg, const double* evals, const double* Vt, const double* delta, int order, int n,
+                double* s, double* smag, double* alpha, int32_t* status, const int32_t* active, const double* sadd,
+                int npole, const int32_t* rowmap, const double* gperp, const double* gam, long long vstride,
+                int batch, void* stream);
+int sb_rfo_ras_c(const double* Vg, const double* evals, const double* Vt, const double* delta, int order, int n,
+                 int mode, double* s, double* smag, double* alpha, int32_t* status, const int32_t* active,
+                 const double* sadd, int npole, const int32_t* rowmap, const double* gperp, const double* gam,
+                 long long vstride, int batch, void* stream);
+int sb_davidson_init_c(const double* v0, const double* pl, const double* Pvt, int mode, double* V, int kcap, int n,
+                       int32_t* ksz, int32_t* ninit, int32_t* nhist, int32_t* dav_state, int32_t* status,
+                       const int32_t* part, const int32_t* mrows, const double* lam0, const double* gperp,
+                       long long estride, long long vstride, int batch, void* stream);
+
 /* ---- per-step bookkeeping (sella/peswrapper.py:578-602, optimize/optimize.py:362-434) ----
  * dpar = {rho_inc, rho_dec, sigma_inc, sigma_dec, delta_min} (host array of 5 doubles),
  * ipar = {order, eig, nsteps_per_diag, diag_every_n(<0: never)} (host array of 4 ints). */

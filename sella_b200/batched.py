@@ -63,7 +63,7 @@ class BatchedSella:
                  rs=None, nsteps_per_diag=3, diag_every_n=None, diag_maxiter=None,
                  eigensolver="jd0", update_method="TS-BFGS", kcap=16, eig_mode="update",
                  eig_refresh_every=0, constraints=None, threepoint=False, hessian_function=None, v0=None,
-                 spectrum=None):
+                 spectrum=None, track_B=False):
         require_cuda()
         d = _DEFAULTS["minimum" if order == 0 else "saddle"]
         self.surface = surface
@@ -151,7 +151,20 @@ class BatchedSella:
         self.status = zi(b)
         self.fmax, self.conv = z(b), zi(b)
         # approximate Hessian and its spectrum
-        self.B = z(b, n, n)
+        # "compact": B = lam0 I + VR^T diag(theta - lam0) VR with mrows[b] explicit eigenpairs in the first rows
+        # of (evals, Vt) and lam0 on the rest (csrc/compact.cu); the dense matrix is only materialised on
+        # request (property B).  "dense": B [b,n,n] and a full (evals, Vt), as in round 1.
+        want = self._spectrum_request
+        can = (eig_mode == "update" and constraints is None and self.eigensolver != 3 and self.kcap <= 16
+               and n <= 1536)
+        if want == "compact" and not can:
+            raise NotImplementedError("spectrum='compact' needs eig_mode='update', no constraints, kcap <= 16 and an "
+                                      "eigensolver other than mjd0 (those run on the dense representation)")
+        self.compact = can and want != "dense"
+        self._B = None if self.compact else z(b, n, n)
+        # compact only: ALSO carry the dense matrix through every update (sb_update_apply), as an
+        # independent check of the carried spectrum (tests); off on the hot path
+        self.tracked_B = z(b, n, n) if (self.compact and track_B) else None
         self.evals, self.Vt = z(b, n), z(b, n, n)
         self.eig_ws = K.EighWorkspace(b, n, dev)
         self.H_initialized = False
@@ -165,7 +178,7 @@ class BatchedSella:
         # update work space: one-pair (step) and kcap-pair (post-diagonalisation)
         self.up1 = {k: z(b, 1, n) for k in ("Ytil", "BS", "VtS", "aC", "aBS", "U", "J", "W", "Xw")}
         self.upk = {k: z(b, kc, n) for k in ("Ytil", "BS", "VtS", "aC", "aBS", "U", "J", "W", "Xw")}
-        self.lam0, self.skip = z(b), zi(b)
+        self.lam0, self.skip = torch.ones(b, **f64), zi(b)
         self.c2, self.s2 = z(b, 2, n), z(b, 2, n)
         if self.eig_mode == "update":
             self.sec1 = dict(P=z(b, 2, n), Z=z(b, 2, n), sig=z(b, 2))
@@ -173,6 +186,19 @@ class BatchedSella:
             self.Cmat = z(b, 32 * 33)
             self.nterm = zi(b)
             self.qwork = z(b, n, n)
+        if self.compact:
+            self.mrows = zi(b)                 # explicit eigenpairs per system
+            self._rb = 0                       # host-side bound on mrows (rows any pass has to visit)
+            self._mmin = 0                     # host-side lower bound on mrows (== n: no complement left anywhere)
+            self.cev, self.cvg, self.ccoef = z(b * n), z(b * n), z(b * n)      # pole lists, stride = width
+            self.rowmap = zi(b * n)
+            self.gperp, self.Wg, self.gam, self.kappa = z(b, n), z(b, n), z(b), z(b)
+            self.C4, self.T4 = z(b, 4, n), z(b, 4, n)
+            self.jd_ed = z(b, 2)
+            self.ncand = zi(b)
+            for sec, zc in ((self.sec1, 2), (self.seck, 2 * kc)):
+                for k in ("W1", "Qc", "D2", "W2"):
+                    sec[k] = z(b, zc, n)
         self._setup_constraints(constraints)
         if self.cons is not None and self.rs == "tr":
             # optimize.py:183-187: the spherical radius scales with the number of free coordinates
@@ -329,7 +355,7 @@ class BatchedSella:
         nl["Hc"] = nl["ints"].ldot(self.x, nl["Lmul"][:, nlin:].contiguous())
         if not self.H_initialized:
             return
-        torch.sub(self.B, nl["Hc"], out=nl["HL"])
+        torch.sub(self._B, nl["Hc"], out=nl["HL"])
         if self._projected_spectrum_by_update():
             return
         Pc = K.gemm(cn["Uc"], cn["Uc"], transA=True)                  # Ucons Ucons^T
@@ -371,7 +397,7 @@ class BatchedSella:
             nl["skip0"] = torch.zeros(b, dtype=torch.int32, device=self.dev)
             nl["nterm"] = torch.zeros(b, dtype=torch.int32, device=self.dev)
         U, J, A, A2, sec = nl["U16"], nl["J16"], nl["A"], nl["A2"], nl["sec"]
-        K.hv_ld(self.B, cn["Uc"], A, nc)
+        K.hv_ld(self._B, cn["Uc"], A, nc)
         K.hv_ld(nl["Hc"], cn["Uc"], A2, nc)
         A.sub_(A2)                                                     # rows a_i = (B - Hc) u_i
         G = K.gemm(cn["Uc"], A, transB=True)                           # G_ij = u_i . a_j
@@ -400,8 +426,11 @@ class BatchedSella:
 
     def _identity_model(self):
         b, n = self.batch, self.n
+        if self.compact:                   # lam0 = 1 and no explicit pairs IS the identity
+            self.eig_valid = True
+            return
         one = torch.ones(b, dtype=torch.float64, device=self.dev)
-        call("sb_fill_scaled_identity", _p(self.B), _p(self.evalsB), _p(self.VtB), _p(one), I(n), I(n), _p(None),
+        call("sb_fill_scaled_identity", _p(self._B), _p(self.evalsB), _p(self.VtB), _p(one), I(n), I(n), _p(None),
              I(b), _stream())
         if self.cons is not None:
             cn = self.cons
@@ -439,19 +468,160 @@ class BatchedSella:
         torch.cuda.synchronize()
         return {k: (len(v), sum(a.elapsed_time(z) for a, z in v) / len(v)) for k, v in (self.prof or {}).items()}
 
-    # ------------------------------------------------------------------ helpers
-    def _eigh(self, active=None):
-        K.eigh(self.B, active=active, evals=self.evals, Vt=self.Vt, ws=self.eig_ws, status=self.status)
+    # ------------------------------------------------------------------ compact representation
+    @property
+    def B(self):
+        """Dense approximate Hessian [b, n, n] (materialised from the compact representation on request)."""
+        if not self.compact:
+            return self._B
+        b, n = self.batch, self.n
+        eye = torch.eye(n, dtype=torch.float64, device=self.dev)
+        R = self._rb
+        out = self.lam0[:, None, None] * eye
+        if R > 0 and self.H_initialized:
+            live = (torch.arange(R, device=self.dev)[None, :] < self.mrows[:, None]).to(torch.float64)
+            d = (self.evals[:, :R] - self.lam0[:, None]) * live
+            VR = self.Vt[:, :R].contiguous()
+            out = out + K.gemm(VR, (d[:, :, None] * VR).contiguous(), transA=True)
+        return 0.5 * (out + out.transpose(1, 2))
 
-    def _update(self, S, Y, bufs, kvec, nv, active, bs_ready=False, abs_ready=False):
-        """ApproximateHessian.update (linalg.py:274-304) for S, Y of shape [b,kc,n]."""
+    def _hvr(self, X, Y, nvec, transposed=False, active=None):
+        """Pass over the explicit rows: Y[:, :, :R] = VR X (or Y = VR^T X[:, :, :R]); R = 0 leaves zeros."""
+        if self._rb > 0:
+            K.hv_rect(self.Vt, self._rb, X, Y, nvec, transposed=transposed, active=active)
+        else:
+            Y[:, :nvec].zero_()
+
+    def _spectral_apply(self, S, bufs, nv, active):
+        """bufs['BS'] = B S and bufs['aBS'] = |B| S from the compact spectrum (linalg.py:293 -> 174-195 and
+        hessian_update.py:118-125 need eigh(B) for this in the reference)."""
+        b, n, kc, R = self.batch, self.n, S.shape[1], self._rb
+        es = LL(n)
+        self._hvr(S, bufs["VtS"], nv, active=active)
+        for mode, key in ((0, "aBS"), (1, "BS")):
+            if R > 0:
+                call("sb_compact_scale", _p(bufs["VtS"]), _p(self.evals), es, _p(self.mrows), _p(self.lam0), I(kc), I(nv),
+                     I(n), I(R), I(mode), _p(bufs["aC"]), _p(self.skip), I(b), _stream())
+            self._hvr(bufs["aC"], bufs["Xw"], nv, transposed=True, active=active)
+            call("sb_compact_axpy", _p(S), _p(bufs["Xw"]), _p(self.lam0), I(kc), I(nv), I(n), I(mode), _p(bufs[key]),
+                 _p(self.skip), I(b), _stream())
+
+    def _update_compact(self, S, Y, bufs, kvec, nv, active, bs_ready=False, abs_ready=False):
+        """ApproximateHessian.update (linalg.py:274-304) on the compact representation: the secant update
+        Delta = sum_t sig_t p_t p_t^T enters as new explicit directions (the part of p_t outside span(VR))
+        plus one secular-equation update of the explicit eigenpairs."""
         b, n = self.batch, self.n
         kc = S.shape[1]
         first = not self.H_initialized
         call("sb_update_prep", _p(S), _p(Y), _p(bufs["Ytil"]), I(kc), _p(kvec), I(n), I(n), I(int(first)),
              I(2), _p(self.lam0), _p(self.skip), _p(self.status), _p(active), I(b), _stream())
         if first:
-            call("sb_fill_scaled_identity", _p(self.B), _p(self.evalsB), _p(self.VtB), _p(self.lam0), I(n),
+            # B = lam0 I (hessian_update.py:58-67): no explicit pairs yet; systems whose first update is a
+            # no-op keep the identity model (lam0 = 1)
+            self.mrows.zero_()
+            self._rb = self._mmin = 0
+            self.H_initialized = True
+            bs_ready = abs_ready = False
+        if not (bs_ready and (abs_ready or self.update_method != 0)):
+            self._spectral_apply(S, bufs, nv, active)
+        call("sb_update_mid", _p(S), _p(bufs["Ytil"]), _p(bufs["BS"]),
+             _p(bufs["aBS"] if self.update_method == 0 else None), _p(bufs["U"]), _p(bufs["J"]), _p(bufs["W"]),
+             _p(bufs["Xw"]), I(kc), _p(kvec), I(n), I(self.update_method), _p(self.skip), _p(self.status),
+             _p(self.Cmat), _p(None), _p(None), I(b), _stream())
+        if self.tracked_B is not None:
+            if first:
+                call("sb_fill_scaled_identity", _p(self.tracked_B), _p(None), _p(None), _p(self.lam0), I(n), I(n),
+                     _p(self.skip), I(b), _stream())
+            call("sb_update_apply", _p(self.tracked_B), _p(bufs["U"]), _p(bufs["J"]), _p(bufs["W"]), I(kc), _p(kvec),
+                 I(n), _p(self.skip), I(b), _stream())
+        sec = self.sec1 if kc == 1 else self.seck
+        zc, T = 2 * kc, 2 * nv
+        es, vs = LL(n), LL(n * n)
+
+        def run():
+            call("sb_lowrank_factor", _p(bufs["U"]), _p(bufs["J"]), _p(self.Cmat), I(kc), _p(kvec), I(n),
+                 _p(sec["P"]), _p(sec["sig"]), _p(self.nterm), _p(self.skip), I(b), _stream())
+            R = self._rb
+            if R == 0:
+                sec["Z"].zero_()
+            self._hvr(sec["P"], sec["Z"], T, active=active)
+            if self._mmin < n:
+                self._hvr(sec["Z"], sec["W1"], T, transposed=True, active=active)
+                call("sb_compact_append_a", _p(sec["P"]), _p(sec["W1"]), I(zc), _p(self.nterm), _p(self.mrows), I(n),
+                     _p(sec["Qc"]), _p(self.ncand), _p(self.skip), I(b), _stream())
+                self._hvr(sec["Qc"], sec["D2"], T, active=active)
+                self._hvr(sec["D2"], sec["W2"], T, transposed=True, active=active)
+                call("sb_compact_append_b", _p(sec["P"]), _p(sec["Qc"]), _p(sec["W2"]), I(zc), _p(self.nterm),
+                     _p(self.ncand), I(n), _p(self.evals), es, _p(self.Vt), vs, _p(self.mrows), _p(self.lam0),
+                     _p(sec["Z"]), _p(self.skip), I(b), _stream())
+                self._rb = min(n, R + T)
+            call("sb_secular_update_c", _p(self.evals), _p(self.Vt), _p(sec["Z"]), I(zc), _p(sec["sig"]),
+                 _p(self.nterm), I(n), _p(self.eig_ws.work), _p(self.qwork), _p(self.status), _p(self.skip),
+                 _p(self.mrows), I(self._rb), es, vs, I(b), _stream())
+        self._timed("eigen_update_k%d" % kc, run)
+        self._updates_since_refresh += 1
+        self.eig_valid = True
+
+    def _refresh_poles(self, active=None):
+        """Vg = VR g, g_perp and the merged pole list of the current model at the current gradient."""
+        b, n = self.batch, self.n
+        width = min(n, self._rb + 1)
+        self._hvr(self.g.view(b, 1, n), self.Vg.view(b, 1, n), 1, active=active)
+        self._hvr(self.Vg.view(b, 1, n), self.Wg.view(b, 1, n), 1, transposed=True, active=active)
+        call("sb_compact_prepare", _p(self.g), _p(self.Vg), _p(self.Wg), _p(self.evals), LL(n), _p(self.mrows),
+             _p(self.lam0), I(n), I(width), _p(self.gperp), _p(self.gam), _p(self.cev), _p(self.cvg), _p(self.rowmap),
+             _p(active), I(b), _stream())
+        return width
+
+    def _predict_compact(self, active):
+        """Restricted step from the compact spectral model; returns abs_ready (|B| s already formed)."""
+        b, n = self.batch, self.n
+        width = self._refresh_poles(active)
+        S1 = self.s.view(b, 1, n)
+        if self.rs == "tr":
+            if self.method == "qn":
+                call("sb_qn_tr", _p(self.cvg), _p(self.cev), _p(self.delta), I(self.order), I(width), _p(self.ccoef),
+                     _p(self.smag), _p(self.alpha), _p(self.status), _p(active), _p(None), I(b), _stream())
+            else:
+                call("sb_rfo_tr", _p(self.cvg), _p(self.cev), _p(self.delta), I(self.order), I(width),
+                     I(1 if self.method == "prfo" else 0), _p(self.ccoef), _p(self.smag), _p(self.alpha),
+                     _p(self.status), _p(active), _p(None), I(b), _stream())
+            call("sb_compact_finish", _p(self.ccoef), _p(self.rowmap), I(width), _p(self.evals), LL(n), _p(self.gam),
+                 I(n), I(self._rb), _p(self.C4), _p(self.kappa), _p(active), I(b), _stream())
+            self._hvr(self.C4, self.T4, 3, transposed=True, active=active)
+            # s, |B| s, B s and x + s from the one transposed pass
+            call("sb_compact_finish2", _p(self.T4), _p(self.gperp), _p(self.kappa), _p(self.lam0), _p(self.x), I(n),
+                 _p(self.s), _p(self.up1["aBS"]), _p(self.up1["BS"]), _p(self.xnew), _p(active), I(b), _stream())
+            return True
+        if self.method == "qn":
+            call("sb_qn_ras_c", _p(self.cvg), _p(self.cev), _p(self.Vt), _p(self.delta), I(self.order), I(n),
+                 _p(self.s), _p(self.smag), _p(self.alpha), _p(self.status), _p(active), _p(None), I(width),
+                 _p(self.rowmap), _p(self.gperp), _p(self.gam), LL(n * n), I(b), _stream())
+        else:
+            call("sb_rfo_ras_c", _p(self.cvg), _p(self.cev), _p(self.Vt), _p(self.delta), I(self.order), I(n),
+                 I(1 if self.method == "prfo" else 0), _p(self.s), _p(self.smag), _p(self.alpha), _p(self.status),
+                 _p(active), _p(None), I(width), _p(self.rowmap), _p(self.gperp), _p(self.gam), LL(n * n), I(b),
+                 _stream())
+        call("sb_axpy", _p(self.x), _p(self.s), _p(self.xnew), I(n), _p(active), I(b), _stream())
+        self.skip.zero_()
+        self._spectral_apply(S1, self.up1, 1, active)
+        return True
+
+    # ------------------------------------------------------------------ helpers
+    def _eigh(self, active=None):
+        K.eigh(self._B, active=active, evals=self.evals, Vt=self.Vt, ws=self.eig_ws, status=self.status)
+
+    def _update(self, S, Y, bufs, kvec, nv, active, bs_ready=False, abs_ready=False):
+        """ApproximateHessian.update (linalg.py:274-304) for S, Y of shape [b,kc,n]."""
+        if self.compact:
+            return self._update_compact(S, Y, bufs, kvec, nv, active, bs_ready, abs_ready)
+        b, n = self.batch, self.n
+        kc = S.shape[1]
+        first = not self.H_initialized
+        call("sb_update_prep", _p(S), _p(Y), _p(bufs["Ytil"]), I(kc), _p(kvec), I(n), I(n), I(int(first)),
+             I(2), _p(self.lam0), _p(self.skip), _p(self.status), _p(active), I(b), _stream())
+        if first:
+            call("sb_fill_scaled_identity", _p(self._B), _p(self.evalsB), _p(self.VtB), _p(self.lam0), I(n),
                  I(n), _p(self.skip), I(b), _stream())
             if self.cons is not None and "nl" not in self.cons:
                 # Bp = lam0 P_f + sigma P_c: eigenvectors = [Ufree; Ucons] rows, sigma > lam0
@@ -462,7 +632,7 @@ class BatchedSella:
             self.H_initialized = True
             bs_ready = False
         if not bs_ready:
-            K.hv_ld(self.B, S, bufs["BS"], nv, active=active)
+            K.hv_ld(self._B, S, bufs["BS"], nv, active=active)
         if first:
             abs_ready = False
         if self.update_method == 0 and not abs_ready:
@@ -477,7 +647,7 @@ class BatchedSella:
              _p(bufs["Xw"]), I(kc), _p(kvec), I(n), I(self.update_method), _p(self.skip), _p(self.status),
              _p(self.Cmat if track else None), _p(None), _p(None), I(b), _stream())
         self._timed("update_apply_k%d" % kc, lambda: call(
-            "sb_update_apply", _p(self.B), _p(bufs["U"]), _p(bufs["J"]), _p(bufs["W"]), I(kc), _p(kvec),
+            "sb_update_apply", _p(self._B), _p(bufs["U"]), _p(bufs["J"]), _p(bufs["W"]), I(kc), _p(kvec),
             I(n), _p(self.skip), I(b), _stream()))
         self._updates_since_refresh += 1
         if track and not (self.eig_refresh_every and self._updates_since_refresh >= self.eig_refresh_every):
@@ -514,11 +684,25 @@ class BatchedSella:
         Bnew = self.hessian_function(self.x)
         check_f64(Bnew)
         Bnew = 0.5 * (Bnew + Bnew.transpose(1, 2))
+        if self.compact:
+            # a dense Hessian has no complement left: all n eigenpairs become explicit (rows of Vt)
+            K.eigh(Bnew.contiguous(), active=part, evals=self.evals, Vt=self.Vt, ws=self.eig_ws, status=self.status)
+            if part is None:
+                self.mrows.fill_(self.n)
+                self._mmin = self.n
+            else:
+                self.mrows.copy_(torch.where(part > 0, torch.full_like(self.mrows, self.n), self.mrows))
+            self._rb = self.n
+            self.H_initialized = True
+            self.eig_valid = True
+            self._updates_since_refresh = 0
+            self.ndiag += 1
+            return
         if part is None:
-            self.B.copy_(Bnew)
+            self._B.copy_(Bnew)
         else:
             m = part.to(torch.bool)
-            self.B[m] = Bnew[m]
+            self._B[m] = Bnew[m]
         self.H_initialized = True
         if self.eig_mode == "update":
             self._direct_spectra()
@@ -530,7 +714,7 @@ class BatchedSella:
     def _direct_spectra(self):
         """Full eigensolves of B (and, with linear constraints, of Bp = P_f B P_f + sigma P_c)."""
         b, n = self.batch, self.n
-        K.eigh(self.B, evals=self.evalsB, Vt=self.VtB, ws=self.eig_ws, status=self.status)
+        K.eigh(self._B, evals=self.evalsB, Vt=self.VtB, ws=self.eig_ws, status=self.status)
         cn = self.cons
         if cn is not None and "nl" not in cn:
             Uc = cn["Uc"][0] if cn["shared"] else cn["Uc"]
@@ -538,7 +722,7 @@ class BatchedSella:
             eye = torch.eye(n, dtype=torch.float64, device=self.dev)
             Pf = (eye - Pc[0]).contiguous() if cn["shared"] else (eye.expand(b, n, n) - Pc).contiguous()
             sigma = 1.0 + 8.0 * torch.maximum(self.evalsB[:, 0].abs(), self.evalsB[:, -1].abs())
-            Bp = K.gemm(Pf, K.gemm(self.B, Pf))
+            Bp = K.gemm(Pf, K.gemm(self._B, Pf))
             Bp = 0.5 * (Bp + Bp.transpose(1, 2)) + sigma[:, None, None] * Pc
             K.eigh(Bp.contiguous(), evals=self.evals, Vt=self.Vt, ws=self.eig_ws, status=self.status)
         self._updates_since_refresh = 0
@@ -587,7 +771,7 @@ class BatchedSella:
         nl = self.cons.get("nl") if self.cons is not None else None
         if nl is not None:
             self._refresh_constraints()         # bases, Hc and the preconditioner at the current geometry
-        if not first and not self.eig_valid:
+        if not first and not self.eig_valid and not self.compact:
             self._eigh(active=part)             # spectrum of the preconditioner P = B
         v0 = self.g
         if first and self.v0 is not None:
@@ -599,9 +783,16 @@ class BatchedSella:
             v0 = self.cons["pg"]
             v0.copy_(self.g)
             self._project_free(v0.view(b, 1, n), 1, 1, part)            # Ufree^T g, lifted (peswrapper.py:524)
-        call("sb_davidson_init", _p(v0), _p(self.evals), _p(self.Vt), I(0 if first else 1), _p(self.V),
-             I(kc), I(n), _p(self.ksz), _p(self.ninit), _p(self.nhist), _p(self.dav_state), _p(self.status),
-             _p(part), I(b), _stream())
+        if self.compact:
+            if not first:
+                self._refresh_poles(part)          # g_perp of the CURRENT complement (fallback start vector)
+            call("sb_davidson_init_c", _p(v0), _p(self.evals), _p(self.Vt), I(0 if first else 1), _p(self.V),
+                 I(kc), I(n), _p(self.ksz), _p(self.ninit), _p(self.nhist), _p(self.dav_state), _p(self.status),
+                 _p(part), _p(self.mrows), _p(self.lam0), _p(self.gperp), LL(n), LL(n * n), I(b), _stream())
+        else:
+            call("sb_davidson_init", _p(v0), _p(self.evals), _p(self.Vt), I(0 if first else 1), _p(self.V),
+                 I(kc), I(n), _p(self.ksz), _p(self.ninit), _p(self.nhist), _p(self.dav_state), _p(self.status),
+                 _p(part), I(b), _stream())
         nstart = 1 if first else int(self.ninit.max().item())
         for j in range(nstart):
             m = ((self.dav_state == DAV_EXPAND) & (self.ninit > j)).to(torch.int32)
@@ -618,6 +809,16 @@ class BatchedSella:
             lanczos = int(self.eigensolver == 2)
             if first or lanczos:
                 tin = None
+            elif self.compact:
+                # (P - theta)^-1 through the compact spectrum: explicit rows + the complement's 1/(lam0 - theta)
+                self._hvr(self.rv, self.rvhat, 2, active=m)
+                call("sb_compact_jd_coeff", _p(self.rvhat), _p(self.rv), _p(self.evals), LL(n), _p(self.mrows),
+                     _p(self.lam0), _p(self.theta), I(n), I(self._rb), I(self.eigensolver), _p(self.that),
+                     _p(self.jd_ed), _p(self.dav_state), I(b), _stream())
+                self._hvr(self.that.view(b, 1, n), self.t.view(b, 1, n), 1, transposed=True, active=m)
+                call("sb_compact_jd_finish", _p(self.t), _p(self.rv), _p(self.jd_ed), I(n), I(self.eigensolver),
+                     _p(self.dav_state), I(b), _stream())
+                tin = self.t
             elif self.eigensolver == 3:
                 if not hasattr(self, "Vhat"):
                     self.Vhat = torch.zeros_like(self.V)
@@ -668,6 +869,26 @@ class BatchedSella:
             # B is None in the reference: the step model is the identity (linalg.py:319-334,
             # stepper.py:76-80) until the first update scales it (hessian_update.py:58-67)
             self._identity_model()
+        if self.compact:
+            abs_ready = self._predict_compact(active)
+            call("sb_ev_decide", _p(self.cev), I(min(n, self._rb + 1)), I(1), _p(self.since_diag), _p(self.ev),
+                 self._dpar, self._ipar, _p(active), I(b), _stream())
+            self.surface.evaluate(self.xnew, self.fnew, self.gnew, active=active)
+            call("sb_kick_finish", _p(self.x), _p(self.f), _p(self.g), _p(self.xnew), _p(self.fnew), _p(self.gnew),
+                 _p(self.s), _p(self.up1["BS"]), _p(self.smag), _p(self.dg), _p(self.delta), _p(self.rho),
+                 _p(self.nsteps), self._dpar, self._ipar, I(n), _p(active), I(b), _stream())
+            self._update_compact(self.s.view(b, 1, n), self.dg.view(b, 1, n), self.up1, None, 1, active,
+                                 bs_ready=True, abs_ready=abs_ready)
+            # ONE small read per step: does any system re-diagonalise, and how many explicit rows do the
+            # passes have to visit (the bound kept on the host grows by the number of TERMS per update, the
+            # true count by the number of NEW directions, usually half of that)
+            nev, self._rb, self._mmin = torch.stack((self.ev.max(), self.mrows.max(), self.mrows.min())).tolist()
+            if nev > 0:
+                if self.hessian_function is not None:
+                    self._calculate_hessian(self.ev)
+                else:
+                    self._diag(self.ev)
+            return
         cn = self.cons
         nl = cn.get("nl") if cn is not None else None
         if nl is not None:
@@ -685,7 +906,7 @@ class BatchedSella:
                  D(0.0), _p(cn["scons"]), LL(n), I(n), _p(active), I(b), _stream())
             call("sb_scons_measure", _p(cn["scons"]), _p(self.delta), I(0 if self.rs == "tr" else 1), I(n),
                  _p(cn["scons2"]), _p(cn["consval"]), _p(cn["naive"]), _p(cn["regular"]), I(b), _stream())
-            K.hv_ld(self.B, cn["scons"].view(b, 1, n), cn["gp"].view(b, 1, n), 1, active=active)
+            K.hv_ld(self._B, cn["scons"].view(b, 1, n), cn["gp"].view(b, 1, n), 1, active=active)
             call("sb_axpy", _p(self.g), _p(cn["gp"]), _p(cn["gp"]), I(n), _p(active), I(b), _stream())
             self._project_free(cn["gp"].view(b, 1, n), 1, 1, active)
             gvec, extra2, sadd = cn["gp"], cn["scons2"], cn["scons"]
@@ -737,7 +958,7 @@ class BatchedSella:
         call("sb_axpy", _p(self.x), _p(self.s), _p(self.xnew), I(n), _p(active), I(b), _stream())
         self.surface.evaluate(self.xnew, self.fnew, self.gnew, active=active)
         S1 = self.s.view(b, 1, n)
-        K.hv_ld(self.B, S1, self.up1["BS"], 1, active=active)
+        K.hv_ld(self._B, S1, self.up1["BS"], 1, active=active)
         call("sb_kick_finish", _p(self.x), _p(self.f), _p(self.g), _p(self.xnew), _p(self.fnew), _p(self.gnew),
              _p(self.s), _p(self.up1["BS"]), _p(self.smag), _p(self.dg), _p(self.delta), _p(self.rho),
              _p(self.nsteps), self._dpar, self._ipar, I(n), _p(active), I(b), _stream())
@@ -779,14 +1000,30 @@ class BatchedSella:
         """[b] lowest eigenvalue of the approximate Hessian B of every system (refreshes a stale spectrum)."""
         if not self.H_initialized:
             return torch.ones(self.batch, dtype=torch.float64, device=self.dev)
+        if self.compact:
+            out = torch.empty(self.batch, dtype=torch.float64, device=self.dev)
+            call("sb_compact_lowest", _p(self.evals), LL(self.n), _p(self.mrows), _p(self.lam0), I(self.n), _p(out),
+                 I(self.batch), _stream())
+            return out
         if not self.eig_valid:
             self._eigh(None)
             self.eig_valid = True
         return self.evalsB[:, 0].clone()
 
+    def explicit_pairs(self, i):
+        """(theta [m], VR [m, n], lam0, m) of system i as numpy arrays: the explicit eigenpairs of its
+        approximate Hessian; every other eigenvalue equals lam0 (dense representation: m = n)."""
+        if self.compact:
+            m = int(self.mrows[i])
+            return (self.evals[i, :m].cpu().numpy(), self.Vt[i, :m].cpu().numpy(), float(self.lam0[i]), m)
+        if not self.eig_valid:
+            self._eigh(None)
+            self.eig_valid = True
+        return self.evalsB[i].cpu().numpy(), self.VtB[i].cpu().numpy(), float(self.lam0[i]), self.n
+
     def rank_bound(self):
         """Upper bound (host-side count) on the number of distinct non-cluster eigenpairs of the model."""
-        return min(self.n, getattr(self, "_rank_bound", self.n))
+        return self._rb if self.compact else self.n
 
     def check_status(self):
         st = self.status.cpu().numpy()

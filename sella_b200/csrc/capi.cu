@@ -69,6 +69,21 @@ extern "C" int sb_ev_decide_impl(const double*, int, int, int*, int*, const doub
                                  cudaStream_t);
 extern "C" int sb_converged_impl(const double*, int, double, double*, int*, int, cudaStream_t);
 
+extern "C" int sb_hv_rect_impl(const double*, long long, int, const double*, double*, const int*, int, int, int, int,
+                               int, cudaStream_t);
+extern "C" int sb_secular_update_c_impl(double*, double*, double*, int, const double*, const int*, int, double*,
+                                        double*, int*, const int*, const int*, int, long long, long long, int,
+                                        cudaStream_t);
+extern "C" int sb_qn_ras_c_impl(const double*, const double*, const double*, const double*, int, int, double*,
+                                double*, double*, int*, const int*, const double*, int, const int*, const double*,
+                                const double*, long long, int, cudaStream_t);
+extern "C" int sb_rfo_ras_c_impl(const double*, const double*, const double*, const double*, int, int, int, double*,
+                                 double*, double*, int*, const int*, const double*, int, const int*, const double*,
+                                 const double*, long long, int, cudaStream_t);
+extern "C" int sb_davidson_init_c_impl(const double*, const double*, const double*, int, double*, int, int, int*,
+                                       int*, int*, int*, int*, const int*, const int*, const double*, const double*,
+                                       long long, long long, int, cudaStream_t);
+
 long long sb_launch_counter = 0;
 
 namespace {
@@ -119,6 +134,12 @@ int sb_hv_ld(const double* A, const double* X, double* Y, const int32_t* active,
              int ldv, int transposed, void* stream) {
     if (batch <= 0 || n <= 0 || nvec <= 0 || ldv < nvec) return -1;
     return sb_hv_ld_impl(A, X, Y, active, batch, n, nvec, ldv, transposed, (cudaStream_t)stream);
+}
+
+int sb_hv_rect(const double* A, long long astride, int mrows, const double* X, double* Y, const int32_t* active,
+               int batch, int n, int nvec, int ldv, int transposed, void* stream) {
+    if (batch <= 0 || n <= 0 || nvec <= 0 || ldv < nvec || mrows < 0 || mrows > n) return -1;
+    return sb_hv_rect_impl(A, astride, mrows, X, Y, active, batch, n, nvec, ldv, transposed, (cudaStream_t)stream);
 }
 
 int sb_quadratic_pes(const double* A, const double* xstar, const double* x, double* f, double* g,
@@ -297,6 +318,38 @@ int sb_secular_update(double* evals, double* Vt, double* Z, int zcap, const doub
                       int n, double* work, double* qwork, int32_t* status, const int32_t* skip, int batch,
                       void* stream) {
     return sb_secular_update_impl(evals, Vt, Z, zcap, sig, nterm, n, work, qwork, status, skip, batch, ST);
+}
+int sb_secular_update_c(double* evals, double* Vt, double* Z, int zcap, const double* sig, const int32_t* nterm,
+                        int n, double* work, double* qwork, int32_t* status, const int32_t* skip,
+                        const int32_t* mrows, int mcap, long long estride, long long vstride, int batch,
+                        void* stream) {
+    if (!mrows || mcap < 0) return -1;
+    return sb_secular_update_c_impl(evals, Vt, Z, zcap, sig, nterm, n, work, qwork, status, skip, mrows, mcap,
+                                    estride, vstride, batch, ST);
+}
+int sb_qn_ras_c(const double* Vg, const double* evals, const double* Vt, const double* delta, int order, int n,
+                double* s, double* smag, double* alpha, int32_t* status, const int32_t* active, const double* sadd,
+                int npole, const int32_t* rowmap, const double* gperp, const double* gam, long long vstride,
+                int batch, void* stream) {
+    if (n % 3 || npole < 1) return -1;
+    return sb_qn_ras_c_impl(Vg, evals, Vt, delta, order, n, s, smag, alpha, status, active, sadd, npole, rowmap, gperp,
+                            gam, vstride, batch, ST);
+}
+int sb_rfo_ras_c(const double* Vg, const double* evals, const double* Vt, const double* delta, int order, int n,
+                 int mode, double* s, double* smag, double* alpha, int32_t* status, const int32_t* active,
+                 const double* sadd, int npole, const int32_t* rowmap, const double* gperp, const double* gam,
+                 long long vstride, int batch, void* stream) {
+    if (n % 3 || mode < 0 || mode > 1 || npole < 1) return -1;
+    return sb_rfo_ras_c_impl(Vg, evals, Vt, delta, order, n, mode, s, smag, alpha, status, active, sadd, npole, rowmap,
+                             gperp, gam, vstride, batch, ST);
+}
+int sb_davidson_init_c(const double* v0, const double* pl, const double* Pvt, int mode, double* V, int kcap, int n,
+                       int32_t* ksz, int32_t* ninit, int32_t* nhist, int32_t* dav_state, int32_t* status,
+                       const int32_t* part, const int32_t* mrows, const double* lam0, const double* gperp,
+                       long long estride, long long vstride, int batch, void* stream) {
+    if (kcap > 32 || kcap < 2 || !mrows || !lam0 || !gperp) return -1;
+    return sb_davidson_init_c_impl(v0, pl, Pvt, mode, V, kcap, n, ksz, ninit, nhist, dav_state, status, part, mrows,
+                                   lam0, gperp, estride, vstride, batch, ST);
 }
 int sb_update_apply(double* B, const double* U, const double* J, const double* W, int kcap, const int32_t* kvec,
                     int n, const int32_t* skip, int batch, void* stream) {

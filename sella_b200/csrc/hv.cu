@@ -38,7 +38,8 @@ struct HvPlan {
 template <int NV>
 __global__ void __launch_bounds__(HV_THREADS, 1)
 hv_tma_kernel(const double* __restrict__ A, const double* __restrict__ X, double* __restrict__ Y,
-              const int* __restrict__ active, int batch, int n, int ldv, int R, int S) {
+              const int* __restrict__ active, int batch, int n, int ldv, int R, int S, int m, long long astride) {
+    // A[b] is m x n (the first m rows of a matrix whose systems are astride doubles apart)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tile_d = R * n, vec_d = NV * n;
     const int stage_d = tile_d + vec_d;
@@ -56,7 +57,7 @@ hv_tma_kernel(const double* __restrict__ A, const double* __restrict__ X, double
     }
     __syncthreads();
 
-    const int tps = (n + R - 1) / R;             // row tiles per system
+    const int tps = (m + R - 1) / R;             // row tiles per system
     const long long ntiles = (long long)batch * tps;
 
     if (warp == NCW) {
@@ -67,14 +68,14 @@ hv_tma_kernel(const double* __restrict__ A, const double* __restrict__ X, double
                 const int b = (int)(t / tps);
                 if (active && !active[b]) continue;
                 const int r0 = (int)(t % tps) * R;
-                const int rows = min(R, n - r0);
+                const int rows = min(R, m - r0);
                 const int s = it % S;
                 const uint32_t ph = (uint32_t)((it / S) & 1);
                 sb_mbar_wait(&empty[s], ph ^ 1u);
                 double* dst = stage_base + (size_t)s * stage_d;
                 const uint32_t tb = (uint32_t)rows * n * 8u, vb = (uint32_t)vec_d * 8u;
                 sb_mbar_expect_tx(&full[s], tb + vb);
-                sb_tma_load_1d(dst, A + ((size_t)b * n + r0) * n, tb, &full[s]);
+                sb_tma_load_1d(dst, A + (size_t)b * astride + (size_t)r0 * n, tb, &full[s]);
                 sb_tma_load_1d(dst + tile_d, X + (size_t)b * ldv * n, vb, &full[s]);
                 ++it;
             }
@@ -86,7 +87,7 @@ hv_tma_kernel(const double* __restrict__ A, const double* __restrict__ X, double
             const int b = (int)(t / tps);
             if (active && !active[b]) continue;
             const int r0 = (int)(t % tps) * R;
-            const int rows = min(R, n - r0);
+            const int rows = min(R, m - r0);
             const int s = it % S;
             const uint32_t ph = (uint32_t)((it / S) & 1);
             sb_mbar_wait(&full[s], ph);
@@ -135,7 +136,7 @@ hv_tma_kernel(const double* __restrict__ A, const double* __restrict__ X, double
 template <int NV>
 __global__ void __launch_bounds__(HV_THREADS, 1)
 hvt_tma_kernel(const double* __restrict__ A, const double* __restrict__ C, double* __restrict__ Y,
-               const int* __restrict__ active, int batch, int n, int ldv, int R, int S) {
+               const int* __restrict__ active, int batch, int n, int ldv, int R, int S, int m, long long astride) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tile_d = R * n;
     double* stage_base = reinterpret_cast<double*>(smem_raw);
@@ -158,7 +159,7 @@ hvt_tma_kernel(const double* __restrict__ A, const double* __restrict__ C, doubl
     }
     __syncthreads();
 
-    const int tps = (n + R - 1) / R;
+    const int tps = (m + R - 1) / R;
     const int ctid = threadIdx.x;                               // consumer thread id (< NCW*32)
     const int gsize = (NCW * 32) / G;                           // threads per row group
     const int grp = ctid / gsize, gt = ctid % gsize;
@@ -170,13 +171,13 @@ hvt_tma_kernel(const double* __restrict__ A, const double* __restrict__ C, doubl
         if (warp == NCW) {
             if (lane == 0) {
                 for (int tt = 0; tt < tps; ++tt, ++it) {
-                    const int r0 = tt * R, rows = min(R, n - r0);
+                    const int r0 = tt * R, rows = min(R, m - r0);
                     const int s = it % S;
                     const uint32_t ph = (uint32_t)((it / S) & 1);
                     sb_mbar_wait(&empty[s], ph ^ 1u);
                     const uint32_t tb = (uint32_t)rows * n * 8u;
                     sb_mbar_expect_tx(&full[s], tb);
-                    sb_tma_load_1d(stage_base + (size_t)s * tile_d, A + ((size_t)b * n + r0) * n, tb,
+                    sb_tma_load_1d(stage_base + (size_t)s * tile_d, A + (size_t)b * astride + (size_t)r0 * n, tb,
                                    &full[s]);
                 }
             }
@@ -185,7 +186,7 @@ hvt_tma_kernel(const double* __restrict__ A, const double* __restrict__ C, doubl
             continue;
         }
         // consumers: stage the coefficients of this system
-        for (int i = ctid; i < NV * n; i += NCW * 32) coef[i] = C[(size_t)b * ldv * n + i];
+        for (int i = ctid; i < NV * n; i += NCW * 32) coef[i] = (i % n) < m ? C[(size_t)b * ldv * n + i] : 0.0;
         asm volatile("bar.sync 1, %0;" ::"r"(NCW * 32));
 
         double2 acc[NV][MAXSLOT];
@@ -195,7 +196,7 @@ hvt_tma_kernel(const double* __restrict__ A, const double* __restrict__ C, doubl
             for (int q = 0; q < MAXSLOT; ++q) acc[v][q] = make_double2(0.0, 0.0);
 
         for (int tt = 0; tt < tps; ++tt, ++it) {
-            const int r0 = tt * R, rows = min(R, n - r0);
+            const int r0 = tt * R, rows = min(R, m - r0);
             const int s = it % S;
             const uint32_t ph = (uint32_t)((it / S) & 1);
             sb_mbar_wait(&full[s], ph);
@@ -259,15 +260,15 @@ hvt_tma_kernel(const double* __restrict__ A, const double* __restrict__ C, doubl
 template <int NV>
 __global__ void hv_ldg_kernel(const double* __restrict__ A, const double* __restrict__ X,
                               double* __restrict__ Y, const int* __restrict__ active, int batch, int n,
-                              int ldv) {
+                              int ldv, int m, long long astride) {
     const int b = blockIdx.x;
     if (active && !active[b]) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int r = warp; r < n; r += nw) {
+    for (int r = warp; r < m; r += nw) {
         double acc[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) acc[v] = 0.0;
-        const double* row = A + ((size_t)b * n + r) * n;
+        const double* row = A + (size_t)b * astride + (size_t)r * n;
         for (int j = lane; j < n; j += 32) {
             const double a = row[j];
 #pragma unroll
@@ -284,15 +285,15 @@ __global__ void hv_ldg_kernel(const double* __restrict__ A, const double* __rest
 template <int NV>
 __global__ void hvt_ldg_kernel(const double* __restrict__ A, const double* __restrict__ C,
                                double* __restrict__ Y, const int* __restrict__ active, int batch, int n,
-                               int ldv) {
+                               int ldv, int m, long long astride) {
     const int b = blockIdx.x;
     if (active && !active[b]) return;
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
         double acc[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) acc[v] = 0.0;
-        for (int r = 0; r < n; ++r) {
-            const double a = A[((size_t)b * n + r) * n + j];
+        for (int r = 0; r < m; ++r) {
+            const double a = A[(size_t)b * astride + (size_t)r * n + j];
 #pragma unroll
             for (int v = 0; v < NV; ++v) acc[v] = fma(C[((size_t)b * ldv + v) * n + r], a, acc[v]);
         }
@@ -312,14 +313,14 @@ void query_device() {
     cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
 }
 
-HvPlan plan_hv(int n, int nvec, bool transposed) {
+HvPlan plan_hv(int n, int nvec, bool transposed, int m) {
     HvPlan p;
     const int target = 48 * 1024;                 // bytes of A per stage
     int R = target / (n * 8);
     if (R >= 2 * NCW) R = (R / (2 * NCW)) * (2 * NCW);
     else if (R >= NCW) R = NCW;
     if (R < 1) R = 1;
-    if (R > n) R = n;
+    if (R > m) R = m < 1 ? 1 : m;
     p.rows = R;
     p.tile_doubles = R * n;
     p.vec_doubles = transposed ? 0 : nvec * n;
@@ -342,72 +343,82 @@ HvPlan plan_hv(int n, int nvec, bool transposed) {
 
 template <int NV>
 int launch_hv(const double* A, const double* X, double* Y, const int* active, int batch, int n,
-              int ldv, cudaStream_t st) {
+              int ldv, int m, long long astride, cudaStream_t st) {
     query_device();
-    if ((n & 1) || n < 16) {
+    if (m <= 0) return 0;
+    // TMA bulk copies need 16-byte aligned sources: even n and an even system stride
+    if ((n & 1) || n < 16 || (astride & 1)) {
         SB_COUNT(1);
-        hv_ldg_kernel<NV><<<batch, 256, 0, st>>>(A, X, Y, active, batch, n, ldv);
+        hv_ldg_kernel<NV><<<batch, 256, 0, st>>>(A, X, Y, active, batch, n, ldv, m, astride);
         return SB_LAUNCH_CHECK();
     }
-    HvPlan p = plan_hv(n, NV, false);
+    HvPlan p = plan_hv(n, NV, false, m);
     if (p.smem > (size_t)g_smem_optin) {
         SB_COUNT(1);
-        hv_ldg_kernel<NV><<<batch, 256, 0, st>>>(A, X, Y, active, batch, n, ldv);
+        hv_ldg_kernel<NV><<<batch, 256, 0, st>>>(A, X, Y, active, batch, n, ldv, m, astride);
         return SB_LAUNCH_CHECK();
     }
     cudaFuncSetAttribute(hv_tma_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-    const long long ntiles = (long long)batch * ((n + p.rows - 1) / p.rows);
+    const long long ntiles = (long long)batch * ((m + p.rows - 1) / p.rows);
     const int grid = (int)(ntiles < g_sms ? ntiles : g_sms);
     SB_COUNT(1);
-    hv_tma_kernel<NV><<<grid, HV_THREADS, p.smem, st>>>(A, X, Y, active, batch, n, ldv, p.rows, p.stages);
+    hv_tma_kernel<NV><<<grid, HV_THREADS, p.smem, st>>>(A, X, Y, active, batch, n, ldv, p.rows, p.stages, m, astride);
     return SB_LAUNCH_CHECK();
 }
 
 template <int NV>
 int launch_hvt(const double* A, const double* C, double* Y, const int* active, int batch, int n,
-               int ldv, cudaStream_t st) {
+               int ldv, int m, long long astride, cudaStream_t st) {
     query_device();
-    const bool tma_ok = !(n & 1) && n >= 16 && (n / 2) <= 4 * (NCW * 32);
-    HvPlan p = plan_hv(n, NV, true);
+    const bool tma_ok = !(n & 1) && n >= 16 && (n / 2) <= 4 * (NCW * 32) && !(astride & 1) && m > 0;
+    HvPlan p = plan_hv(n, NV, true, m);
     if (!tma_ok || p.smem > (size_t)g_smem_optin) {
         SB_COUNT(1);
-        hvt_ldg_kernel<NV><<<batch, 256, 0, st>>>(A, C, Y, active, batch, n, ldv);
+        hvt_ldg_kernel<NV><<<batch, 256, 0, st>>>(A, C, Y, active, batch, n, ldv, m, astride);
         return SB_LAUNCH_CHECK();
     }
     cudaFuncSetAttribute(hvt_tma_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     const int grid = batch < g_sms ? batch : g_sms;
     SB_COUNT(1);
-    hvt_tma_kernel<NV><<<grid, HV_THREADS, p.smem, st>>>(A, C, Y, active, batch, n, ldv, p.rows, p.stages);
+    hvt_tma_kernel<NV><<<grid, HV_THREADS, p.smem, st>>>(A, C, Y, active, batch, n, ldv, p.rows, p.stages, m, astride);
     return SB_LAUNCH_CHECK();
 }
 
 }  // namespace
 
 // X and Y are [b, ldv, n] with the first nvec slots in use; nvec is processed in
-// chunks of 4/2/1 vectors per pass over A (a chunk is a contiguous sub-block of each
-// system's vectors).
-extern "C" int sb_hv_ld_impl(const double* A, const double* X, double* Y, const int* active, int batch,
-                             int n, int nvec, int ldv, int transposed, cudaStream_t st) {
+// chunks of 4/3/2/1 vectors per pass over A (a chunk is a contiguous sub-block of each
+// system's vectors).  A[b]: the first m rows (length n) of a matrix with system stride astride.
+extern "C" int sb_hv_rect_impl(const double* A, long long astride, int m, const double* X, double* Y,
+                               const int* active, int batch, int n, int nvec, int ldv, int transposed,
+                               cudaStream_t st) {
     int done = 0;
     while (done < nvec) {
         const int left = nvec - done;
-        const int c = left >= 4 ? 4 : (left >= 2 ? 2 : 1);
+        const int c = left >= 4 ? 4 : left;
         const double* x = X + (size_t)done * n;
         double* y = Y + (size_t)done * n;
         int rc;
         if (!transposed) {
-            rc = c == 4   ? launch_hv<4>(A, x, y, active, batch, n, ldv, st)
-                 : c == 2 ? launch_hv<2>(A, x, y, active, batch, n, ldv, st)
-                          : launch_hv<1>(A, x, y, active, batch, n, ldv, st);
+            rc = c == 4   ? launch_hv<4>(A, x, y, active, batch, n, ldv, m, astride, st)
+                 : c == 3 ? launch_hv<3>(A, x, y, active, batch, n, ldv, m, astride, st)
+                 : c == 2 ? launch_hv<2>(A, x, y, active, batch, n, ldv, m, astride, st)
+                          : launch_hv<1>(A, x, y, active, batch, n, ldv, m, astride, st);
         } else {
-            rc = c == 4   ? launch_hvt<4>(A, x, y, active, batch, n, ldv, st)
-                 : c == 2 ? launch_hvt<2>(A, x, y, active, batch, n, ldv, st)
-                          : launch_hvt<1>(A, x, y, active, batch, n, ldv, st);
+            rc = c == 4   ? launch_hvt<4>(A, x, y, active, batch, n, ldv, m, astride, st)
+                 : c == 3 ? launch_hvt<3>(A, x, y, active, batch, n, ldv, m, astride, st)
+                 : c == 2 ? launch_hvt<2>(A, x, y, active, batch, n, ldv, m, astride, st)
+                          : launch_hvt<1>(A, x, y, active, batch, n, ldv, m, astride, st);
         }
         if (rc) return rc;
         done += c;
     }
     return 0;
+}
+
+extern "C" int sb_hv_ld_impl(const double* A, const double* X, double* Y, const int* active, int batch,
+                             int n, int nvec, int ldv, int transposed, cudaStream_t st) {
+    return sb_hv_rect_impl(A, (long long)n * n, n, X, Y, active, batch, n, nvec, ldv, transposed, st);
 }
 
 extern "C" int sb_hv_impl(const double* A, const double* X, double* Y, const int* active, int batch,

@@ -290,32 +290,40 @@ __global__ void __launch_bounds__(256)
 rfo_ras_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_, const double* __restrict__ Vt_,
                const double* __restrict__ delta_, int order, int n, int mode, double* __restrict__ s_out,
                double* __restrict__ smag, double* __restrict__ alpha_out, int* __restrict__ status,
-               const int* __restrict__ active, const double* __restrict__ sadd_) {
+               const int* __restrict__ active, const double* __restrict__ sadd_, int np,
+               const int* __restrict__ rowmap_, const double* __restrict__ gperp_, const double* __restrict__ gam_,
+               long long vstride) {
+    // np poles (np = n for the dense representation); pole i -> eigenvector row rowmap[i] of Vt
+    // (NULL: row i; -1: the unit vector gperp/gam; -2: padding), as in qn_ras_kernel
     const int b = blockIdx.x;
     if (active && !active[b]) return;
     extern __shared__ double sm[];
     double* c1 = sm;            // s_hat
-    double* c2 = c1 + n;        // ds_hat
-    double* s = c2 + n;
+    double* c2 = c1 + np;       // ds_hat
+    double* s = c2 + np;
     double* ds = s + n;
+    int* rm = reinterpret_cast<int*>(ds + n);
     __shared__ double best_val[8];
     __shared__ int best_idx[8];
     __shared__ double sh_alpha, sh_val, sh_dval;
     __shared__ int sh_go;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    const double* Vt = Vt_ + (size_t)b * n * n;
+    const double* Vt = Vt_ + (size_t)b * vstride;
+    const double* gp = gperp_ ? gperp_ + (size_t)b * n : nullptr;
+    const double ginv = (gam_ && gam_[b] > 0.0) ? 1.0 / gam_[b] : 0.0;
+    for (int i = tid; i < np; i += nt) rm[i] = rowmap_ ? rowmap_[(size_t)b * np + i] : i;
     const double delta = delta_[b];
     const int natoms = n / 3;
-    const int mo = order < n ? order : n;
+    const int mo = order < np ? order : np;
     Sys<NPL> S;
-    S.n = n;
+    S.n = np;
     double guess_a = 0.0, guess_b = 0.0;
     if (warp == 0) {
 #pragma unroll
         for (int u = 0; u < NPL; ++u) {
             const int i = lane + 32 * u;
-            S.lam[u] = i < n ? evals_[(size_t)b * n + i] : 0.0;
-            S.g[u] = i < n ? Vg_[(size_t)b * n + i] : 0.0;
+            S.lam[u] = i < np ? evals_[(size_t)b * np + i] : 0.0;
+            S.g[u] = i < np ? Vg_[(size_t)b * np + i] : 0.0;
             S.g2[u] = S.g[u] * S.g[u];
         }
     }
@@ -364,12 +372,12 @@ rfo_ras_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_
                     }
                 }
             };
-            if (mode == 0) block(0, n, mo == 0 ? 0 : (mo == n ? 1 : 2), mo, &guess_a);
-            else { block(0, mo, 1, mo, &guess_a); block(mo, n, 0, mo, &guess_b); }
+            if (mode == 0) block(0, np, mo == 0 ? 0 : (mo == np ? 1 : 2), mo, &guess_a);
+            else { block(0, mo, 1, mo, &guess_a); block(mo, np, 0, mo, &guess_b); }
 #pragma unroll
             for (int u = 0; u < NPL; ++u) {
                 const int i = lane + 32 * u;
-                if (i < n) { c1[i] = sreg[u]; c2[i] = dreg[u]; }
+                if (i < np) { c1[i] = sreg[u]; c2[i] = dreg[u]; }
             }
         }
         __syncthreads();
@@ -377,8 +385,10 @@ rfo_ras_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_
         for (int j = tid; j < n; j += nt) {
             double a = 0.0, d = 0.0;
 #pragma unroll 4
-            for (int i = 0; i < n; ++i) {
-                const double v = Vt[(size_t)i * n + j];
+            for (int i = 0; i < np; ++i) {
+                const int r = rm[i];
+                if (r < -1) continue;
+                const double v = r >= 0 ? Vt[(size_t)r * n + j] : gp[j] * ginv;
                 a = fma(v, c1[i], a);
                 d = fma(v, c2[i], d);
             }
@@ -468,16 +478,17 @@ extern "C" int sb_rfo_tr_impl(const double* Vg, const double* evals, const doubl
     return SB_LAUNCH_CHECK();
 }
 
-extern "C" int sb_rfo_ras_impl(const double* Vg, const double* evals, const double* Vt, const double* delta, int order,
-                               int n, int mode, double* s, double* smag, double* alpha, int* status,
-                               const int* active, const double* sadd, int batch, cudaStream_t st) {
-    const int npl = (n + 31) / 32;
-    const size_t smem = (size_t)4 * n * sizeof(double);
+extern "C" int sb_rfo_ras_c_impl(const double* Vg, const double* evals, const double* Vt, const double* delta,
+                                 int order, int n, int mode, double* s, double* smag, double* alpha, int* status,
+                                 const int* active, const double* sadd, int np, const int* rowmap, const double* gperp,
+                                 const double* gam, long long vstride, int batch, cudaStream_t st) {
+    const int npl = (np + 31) / 32;
+    const size_t smem = (size_t)(2 * np + 2 * n) * sizeof(double) + (size_t)(np + 2) * sizeof(int);
     SB_COUNT(1);
 #define SB_RFOR(N)                                                                                             \
     cudaFuncSetAttribute(rfo_ras_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
     rfo_ras_kernel<N><<<batch, 256, smem, st>>>(Vg, evals, Vt, delta, order, n, mode, s, smag, alpha, status, \
-                                                active, sadd)
+                                                active, sadd, np, rowmap, gperp, gam, vstride)
     if (npl <= 4) { SB_RFOR(4); }
     else if (npl <= 8) { SB_RFOR(8); }
     else if (npl <= 12) { SB_RFOR(12); }
@@ -488,4 +499,11 @@ extern "C" int sb_rfo_ras_impl(const double* Vg, const double* evals, const doub
     else return -2;
 #undef SB_RFOR
     return SB_LAUNCH_CHECK();
+}
+
+extern "C" int sb_rfo_ras_impl(const double* Vg, const double* evals, const double* Vt, const double* delta, int order,
+                               int n, int mode, double* s, double* smag, double* alpha, int* status,
+                               const int* active, const double* sadd, int batch, cudaStream_t st) {
+    return sb_rfo_ras_c_impl(Vg, evals, Vt, delta, order, n, mode, s, smag, alpha, status, active, sadd, n, nullptr,
+                             nullptr, nullptr, (long long)n * n, batch, st);
 }

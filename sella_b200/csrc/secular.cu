@@ -533,47 +533,62 @@ __global__ void __launch_bounds__(SECK_THREADS, 4)
 secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, double* __restrict__ Z_, int zcap,
                       const double* __restrict__ sig_, const int* __restrict__ nterm, int n,
                       double* __restrict__ work_, double* __restrict__ qwork_, int* __restrict__ status,
-                      const int* __restrict__ skip, int tile_doubles) {
+                      const int* __restrict__ skip, int tile_doubles, const int* __restrict__ mrows, int mc,
+                      long long estride, long long vstride) {
+    // m = number of (explicit) eigenpairs = rows of Vt that take part; mc >= m sizes the shared arrays;
+    // n = length of a row.  Dense representation: m = mc = n, estride = n, vstride = n*n.
     const int b = blockIdx.x;
     if (skip[b]) return;
     const int nterms = nterm[b];
     if (nterms == 0) return;
+    const int m = mrows ? mrows[b] : n;
+    if (m == 0) return;
     extern __shared__ double sm[];
     SecShared& S = *reinterpret_cast<SecShared*>(sm);
     double* d = sm + (sizeof(SecShared) + 7) / 8;   // current eigenvalues, row order
-    double* z = d + n;               // current z, row order
-    double* dd = z + n;              // non-deflated poles (ascending; mirrored when rho<0)
-    double* y2 = dd + n;             // squared weights of the non-deflated
-    double* zh = y2 + n;             // recomputed z (Gu-Eisenstat)
-    double* mu = zh + n;             // root offsets
-    double* rc = mu + n;             // rotation cosines
-    double* rs = rc + n;             // rotation sines
-    int* ord = reinterpret_cast<int*>(rs + n);   // sorted position -> row
-    int* nd = ord + n;               // non-deflated rows, ascending d
-    int* org = nd + n;               // origin pole index of each root
-    int* ia = org + n;               // rotation row a
-    int* ib = ia + n;                // rotation row b
-    double* tile = reinterpret_cast<double*>(ib + n + (n & 1));   // staging tile for the row update
+    double* z = d + mc;              // current z, row order
+    double* dd = z + mc;             // non-deflated poles (ascending; mirrored when rho<0)
+    double* y2 = dd + mc;            // squared weights of the non-deflated
+    double* zh = y2 + mc;            // recomputed z (Gu-Eisenstat)
+    double* mu = zh + mc;            // root offsets
+    double* rc = mu + mc;            // rotation cosines
+    double* rs = rc + mc;            // rotation sines
+    int* ord = reinterpret_cast<int*>(rs + mc);   // sorted position -> row
+    int* nd = ord + mc;              // non-deflated rows, ascending d
+    int* org = nd + mc;              // origin pole index of each root
+    int* ia = org + mc;              // rotation row a
+    int* ib = ia + mc;               // rotation row b
+    double* tile = reinterpret_cast<double*>(ib + mc + (mc & 1));   // staging tile for the row update
     const int tid = threadIdx.x, nt = blockDim.x;
-    double* Vt = Vt_ + (size_t)b * n * n;
+    double* Vt = Vt_ + (size_t)b * vstride;
     double* Z = Z_ + (size_t)b * zcap * n;
-    double* work = work_ + (size_t)b * n * n;
-    double* Qh = qwork_ + (size_t)b * n * n;
+    double* work = work_ + (size_t)b * vstride;
+    double* Qh = qwork_ + (size_t)b * vstride;
 
     long long tmark_ = clock64();
-    for (int i = tid; i < n; i += nt) { d[i] = evals_[(size_t)b * n + i]; ord[i] = i; }   // sorted on entry
+    for (int i = tid; i < m; i += nt) { d[i] = evals_[(size_t)b * estride + i]; ord[i] = i; }   // dense: sorted on entry
     __syncthreads();
+    if (mrows) {
+        // compact representation: freshly appended rows (eigenvalue lam0) sit at the end, out of order
+        for (int i = tid; i < m; i += nt) {
+            const double di = d[i];
+            int rank = 0;
+            for (int j = 0; j < m; ++j) { const double dj = d[j]; rank += (dj < di) || (dj == di && j < i); }
+            ord[rank] = i;
+        }
+        __syncthreads();
+    }
 
     for (int t = 0; t < nterms; ++t) {
         double* zt = Z + (size_t)t * n;
         double acc = 0.0;
-        for (int i = tid; i < n; i += nt) { const double v = zt[i]; z[i] = v; acc = fma(v, v, acc); }
+        for (int i = tid; i < m; i += nt) { const double v = zt[i]; z[i] = v; acc = fma(v, v, acc); }
         const double znorm2 = sb_block_sum(acc, S.scratch);
         double rho = sig_[(size_t)b * zcap + t] * znorm2;
         if (znorm2 == 0.0 || rho == 0.0) continue;
         const double zinv = 1.0 / sqrt(znorm2);
         double dmax = 0.0, zmax = 0.0;
-        for (int i = tid; i < n; i += nt) { z[i] *= zinv; dmax = fmax(dmax, fabs(d[i])); zmax = fmax(zmax, fabs(z[i])); }
+        for (int i = tid; i < m; i += nt) { z[i] *= zinv; dmax = fmax(dmax, fabs(d[i])); zmax = fmax(zmax, fabs(z[i])); }
         dmax = sb_warp_max(dmax); zmax = sb_warp_max(zmax);
         __syncthreads();
         if ((tid & 31) == 0) { S.scratch[40 + (tid >> 5)] = dmax; S.scratch[52 + (tid >> 5)] = zmax; }
@@ -590,10 +605,10 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
         // candidates (non-negligible z) in ascending-d order: ballot compaction
         if (tid == 0) S.flag = 0;
         __syncthreads();
-        for (int p0 = 0; p0 < n; p0 += nt) {
+        for (int p0 = 0; p0 < m; p0 += nt) {
             const int p = p0 + tid;
-            const int i = p < n ? ord[p] : 0;
-            const bool f = p < n && fabs(rho * z[i]) > tol;
+            const int i = p < m ? ord[p] : 0;
+            const bool f = p < m && fabs(rho * z[i]) > tol;
             const unsigned bal = __ballot_sync(0xffffffffu, f);
             if ((tid & 31) == 0) S.wcnt[tid >> 5] = __popc(bal);
             __syncthreads();
@@ -820,7 +835,7 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
         // eigenvector matrix (mirrored index space): Qh[i*r + j] = zh_i / (dd_i - lam_j), columns normalised
         const bool qsmem = r <= SEC_QS_MAX && (size_t)r * r <= (size_t)tile_doubles;
         if (qsmem) Qh = tile;
-        else Qh = qwork_ + (size_t)b * n * n;
+        else Qh = qwork_ + (size_t)b * vstride;
         for (int idx = tid; idx < r * r; idx += nt) {
             const int i = idx / r, j = idx % r;
             Qh[idx] = zh[i] / ((dd[i] - dd[org[j]]) - mu[j]);
@@ -925,10 +940,10 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
         __syncthreads();
         SEC_MARK(6);
         // ---------------- ascending order of the rows for the next term
-        for (int i = tid; i < n; i += nt) {
+        for (int i = tid; i < m; i += nt) {
             const double di = d[i];
             int rank = 0;
-            for (int j = 0; j < n; ++j) { const double dj = d[j]; rank += (dj < di) || (dj == di && j < i); }
+            for (int j = 0; j < m; ++j) { const double dj = d[j]; rank += (dj < di) || (dj == di && j < i); }
             ord[rank] = i;
         }
         __syncthreads();
@@ -939,25 +954,25 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
     // whose sorted value equals its own eigenvalue stays put, only the others are matched
     // (in ascending order) to the remaining slots.  This keeps a degenerate cluster in
     // place when one row crosses it, instead of shifting every member by one.
-    for (int p = tid; p < n; p += nt) dd[p] = d[ord[p]];            // sorted values
+    for (int p = tid; p < m; p += nt) dd[p] = d[ord[p]];            // sorted values
     __syncthreads();
-    for (int p = tid; p < n; p += nt) {
-        evals_[(size_t)b * n + p] = dd[p];
+    for (int p = tid; p < m; p += nt) {
+        evals_[(size_t)b * estride + p] = dd[p];
         org[p] = (d[p] == dd[p]) ? 1 : 0;                             // fixed point
     }
     __syncthreads();
-    for (int p = tid; p < n; p += nt) {
+    for (int p = tid; p < m; p += nt) {
         if (org[p]) continue;
         int kslot = 0;
         for (int q = 0; q < p; ++q) kslot += !org[q];
         ia[kslot] = p;                                                // kslot-th free slot
     }
     __syncthreads();
-    for (int i = tid; i < n; i += nt) {
+    for (int i = tid; i < m; i += nt) {
         if (org[i]) { ib[i] = i; continue; }
         const double di = d[i];
         int rank = 0;
-        for (int j = 0; j < n; ++j) {
+        for (int j = 0; j < m; ++j) {
             if (org[j]) continue;
             const double dj = d[j];
             rank += (dj < di) || (dj == di && j < i);
@@ -965,10 +980,10 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
         ib[ia[rank]] = i;                                             // slot -> row
     }
     __syncthreads();
-    for (int p = tid; p < n; p += nt) ord[p] = ib[p];
+    for (int p = tid; p < m; p += nt) ord[p] = ib[p];
     if (tid == 0) S.flag = 0;
     __syncthreads();
-    for (int p2 = tid; p2 < n; p2 += nt)
+    for (int p2 = tid; p2 < m; p2 += nt)
         if (ord[p2] != p2) {
             nd[atomicAdd(&S.flag, 1)] = p2;          // destinations that change
             const int dist = abs(ord[p2] - p2);
@@ -1037,10 +1052,14 @@ extern "C" int sb_secular_timing_impl(float* out3, int enable) {
     return 0;
 }
 
-extern "C" int sb_secular_update_impl(double* evals, double* Vt, double* Z, int zcap, const double* sig,
-                                      const int* nterm, int n, double* work, double* qwork, int* status,
-                                      const int* skip, int batch, cudaStream_t st) {
-    const size_t base = (size_t)n * (8 * sizeof(double) + 5 * sizeof(int)) + sizeof(SecShared) + 64;
+// Compact representation: only the first mrows[b] rows of Vt (explicit eigenpairs) take part; mcap is the
+// host-side bound on mrows that sizes the shared arrays.  mrows == NULL: dense (m = n).
+extern "C" int sb_secular_update_c_impl(double* evals, double* Vt, double* Z, int zcap, const double* sig,
+                                        const int* nterm, int n, double* work, double* qwork, int* status,
+                                        const int* skip, const int* mrows, int mcap, long long estride,
+                                        long long vstride, int batch, cudaStream_t st) {
+    const int mc = mrows ? (mcap < 1 ? 1 : (mcap > n ? n : mcap)) : n;
+    const size_t base = (size_t)mc * (8 * sizeof(double) + 5 * sizeof(int)) + sizeof(SecShared) + 64;
     int dev = 0, optin = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -1052,7 +1071,7 @@ extern "C" int sb_secular_update_impl(double* evals, double* Vt, double* Z, int 
     const size_t smem = base + tile_bytes;
     const int cpt = (n + SECK_THREADS - 1) / SECK_THREADS;
     if (sec_timing_on) cudaEventRecord(sec_ev[0], st);
-    if (n >= 32 && n < 4096 && !getenv("SB_NO_CLUSTER_QR")) {
+    if (!mrows && n >= 32 && n < 4096 && !getenv("SB_NO_CLUSTER_QR")) {
         // pre-phase: one block reflector for the degenerate cluster (all terms at once)
         const size_t qsm = ((size_t)n + SB_SCRATCH_DOUBLES + 2 * CQ_TMAX * CQ_TMAX + 2 * CQ_TMAX) * sizeof(double) + 64 +
                            ((size_t)n + 20) * sizeof(int);
@@ -1072,10 +1091,12 @@ extern "C" int sb_secular_update_impl(double* evals, double* Vt, double* Z, int 
     }
     if (sec_timing_on) cudaEventRecord(sec_ev[2], st);
     SB_COUNT(1);
+    const long long es = mrows ? estride : (long long)n;
+    const long long vs = mrows ? vstride : (long long)n * n;
 #define SB_SEC_LAUNCH(C)                                                                                          \
     cudaFuncSetAttribute(secular_update_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
     secular_update_kernel<C><<<batch, SECK_THREADS, smem, st>>>(evals, Vt, Z, zcap, sig, nterm, n, work, qwork,  \
-                                                               status, skip, tile_doubles)
+                                                               status, skip, tile_doubles, mrows, mc, es, vs)
     if (cpt <= 1) { SB_SEC_LAUNCH(1); }
     else if (cpt <= 2) { SB_SEC_LAUNCH(2); }
     else if (cpt <= 4) { SB_SEC_LAUNCH(4); }
@@ -1085,4 +1106,11 @@ extern "C" int sb_secular_update_impl(double* evals, double* Vt, double* Z, int 
 #undef SB_SEC_LAUNCH
     if (sec_timing_on) cudaEventRecord(sec_ev[3], st);
     return SB_LAUNCH_CHECK();
+}
+
+extern "C" int sb_secular_update_impl(double* evals, double* Vt, double* Z, int zcap, const double* sig,
+                                      const int* nterm, int n, double* work, double* qwork, int* status,
+                                      const int* skip, int batch, cudaStream_t st) {
+    return sb_secular_update_c_impl(evals, Vt, Z, zcap, sig, nterm, n, work, qwork, status, skip, nullptr, n, n,
+                                    (long long)n * n, batch, st);
 }

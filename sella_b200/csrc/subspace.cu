@@ -556,7 +556,11 @@ __global__ void __launch_bounds__(SS_THREADS)
 davidson_init_kernel(const double* __restrict__ v0_, const double* __restrict__ pl, const double* __restrict__ Pvt,
                      int mode, double* __restrict__ V_, int kcap, int n, int* __restrict__ ksz,
                      int* __restrict__ ninit, int* __restrict__ nhist, int* __restrict__ dav_state,
-                     int* __restrict__ status, const int* __restrict__ part) {
+                     int* __restrict__ status, const int* __restrict__ part, const int* __restrict__ mrows,
+                     const double* __restrict__ lam0, const double* __restrict__ gperp, long long estride,
+                     long long vstride) {
+    // mrows != NULL: compact representation -- only the first mrows[b] entries of pl / rows of Pvt are
+    // explicit eigenpairs, every other eigenvalue of the preconditioner equals lam0[b]
     const int b = blockIdx.x;
     if (part && !part[b]) {
         if (threadIdx.x == 0) dav_state[b] = DAV_IDLE;
@@ -571,10 +575,21 @@ davidson_init_kernel(const double* __restrict__ v0_, const double* __restrict__ 
     if (mode == 0) {
         for (int i = tid; i < n; i += nt) V[i] = v0_[(size_t)b * n + i];
     } else {
+        const int m = mrows ? mrows[b] : n;
         int nneg = 0;
-        for (int i = 0; i < n && i < kcap; ++i) nneg += (pl[(size_t)b * n + i] < 0.0);   // ascending
+        for (int i = 0; i < m && i < kcap; ++i) nneg += (pl[(size_t)b * estride + i] < 0.0);   // ascending
+        if (mrows && m < n && lam0[b] < 0.0) nneg = 0;    // (never: lam0 is a geometric mean of |Ritz values|)
         nstart = nneg < 1 ? 1 : nneg;
-        for (int i = tid; i < nstart * n; i += nt) V[i] = Pvt[(size_t)b * n * n + i];
+        // no negative eigenvalue: the lowest eigenvector.  In the compact representation that is row 0
+        // unless the complement's lam0 lies below every explicit eigenvalue; any unit vector of the
+        // complement is then "the" lowest eigenvector (eigh of a degenerate matrix returns an arbitrary
+        // one): the gradient's component in it
+        const bool from_complement = mrows && nneg == 0 && m < n && (m == 0 || pl[(size_t)b * estride] > lam0[b]);
+        if (from_complement) {
+            for (int i = tid; i < n; i += nt) V[i] = gperp[(size_t)b * n + i];
+        } else {
+            for (int i = tid; i < nstart * n; i += nt) V[i] = Pvt[(size_t)b * vstride + i];
+        }
     }
     __syncthreads();
     const int kept = mgs_block(V, nstart, n, nullptr, 0, 1e-15, 1e-6, 100, xs, scratch);
@@ -643,15 +658,25 @@ extern "C" int sb_mgs_impl(double* X, int nx, const double* Y, double* Ywork, in
     return SB_LAUNCH_CHECK();
 }
 
-extern "C" int sb_davidson_init_impl(const double* v0, const double* pl, const double* Pvt, int mode, double* V,
-                                     int kcap, int n, int* ksz, int* ninit, int* nhist, int* dav_state,
-                                     int* status, const int* part, int batch, cudaStream_t st) {
+extern "C" int sb_davidson_init_c_impl(const double* v0, const double* pl, const double* Pvt, int mode, double* V,
+                                       int kcap, int n, int* ksz, int* ninit, int* nhist, int* dav_state,
+                                       int* status, const int* part, const int* mrows, const double* lam0,
+                                       const double* gperp, long long estride, long long vstride, int batch,
+                                       cudaStream_t st) {
     const size_t smem = (size_t)(n + SB_SCRATCH_DOUBLES) * sizeof(double);
     cudaFuncSetAttribute(davidson_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     SB_COUNT(1);
     davidson_init_kernel<<<batch, SS_THREADS, smem, st>>>(v0, pl, Pvt, mode, V, kcap, n, ksz, ninit, nhist,
-                                                          dav_state, status, part);
+                                                          dav_state, status, part, mrows, lam0, gperp, estride,
+                                                          vstride);
     return SB_LAUNCH_CHECK();
+}
+
+extern "C" int sb_davidson_init_impl(const double* v0, const double* pl, const double* Pvt, int mode, double* V,
+                                     int kcap, int n, int* ksz, int* ninit, int* nhist, int* dav_state,
+                                     int* status, const int* part, int batch, cudaStream_t st) {
+    return sb_davidson_init_c_impl(v0, pl, Pvt, mode, V, kcap, n, ksz, ninit, nhist, dav_state, status, part, nullptr,
+                                   nullptr, nullptr, (long long)n, (long long)n * n, batch, st);
 }
 
 extern "C" int sb_davidson_rr_impl(double* V, double* AV, int kcap, const int* ksz, int n, double gamma,

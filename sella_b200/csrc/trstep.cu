@@ -108,29 +108,38 @@ qn_tr_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_, 
 // Quasi-Newton model + restricted atomic step (max per-atom displacement), Cartesian
 // coordinates with Ufree = I.  Streams Vt (rows = eigenvectors) once per alpha.
 // Out: s[b,n] (the step itself), smag, alpha.
+// The model is given as a list of np poles (np = n for the dense representation): pole i has
+// eigenvalue evals[b*np + i], gradient coefficient Vg[b*np + i] and eigenvector row rowmap[b*np + i] of
+// Vt (rowmap == NULL: row i); rowmap -1 = the unit vector gperp[b]/gam[b] (complement of the compact
+// representation), -2 = padding.
 __global__ void __launch_bounds__(TR_THREADS)
 qn_ras_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_, const double* __restrict__ Vt_,
               const double* __restrict__ delta_, int order, int n, double* __restrict__ s_out,
               double* __restrict__ smag, double* __restrict__ alpha_out, int* __restrict__ status,
-              const int* __restrict__ active, const double* __restrict__ sadd_) {
+              const int* __restrict__ active, const double* __restrict__ sadd_, int np, const int* __restrict__ rowmap_,
+              const double* __restrict__ gperp_, const double* __restrict__ gam_, long long vstride) {
     const int b = blockIdx.x;
     if (active && !active[b]) return;
     extern __shared__ double sm[];
     double* L = sm;
-    double* vg = L + n;
-    double* c1 = vg + n;        // c_i
-    double* c2 = c1 + n;        // c_i / den_i
-    double* s = c2 + n;         // step
+    double* vg = L + np;
+    double* c1 = vg + np;       // c_i
+    double* c2 = c1 + np;       // c_i / den_i
+    double* s = c2 + np;        // step
     double* ds = s + n;         // ds/dalpha
     double* scratch = ds + n;
+    int* rm = reinterpret_cast<int*>(scratch + SB_SCRATCH_DOUBLES);
     __shared__ double best_val[TR_THREADS / 32];
     __shared__ int best_idx[TR_THREADS / 32];
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    const double* Vt = Vt_ + (size_t)b * n * n;
-    for (int i = tid; i < n; i += nt) {
-        const double l = fabs(evals_[(size_t)b * n + i]);
+    const double* Vt = Vt_ + (size_t)b * vstride;
+    const double* gp = gperp_ ? gperp_ + (size_t)b * n : nullptr;
+    const double ginv = (gam_ && gam_[b] > 0.0) ? 1.0 / gam_[b] : 0.0;
+    for (int i = tid; i < np; i += nt) {
+        const double l = fabs(evals_[(size_t)b * np + i]);
         L[i] = i < order ? -l : l;
-        vg[i] = Vg_[(size_t)b * n + i];
+        vg[i] = Vg_[(size_t)b * np + i];
+        rm[i] = rowmap_ ? rowmap_[(size_t)b * np + i] : i;
     }
     __syncthreads();
     const double delta = delta_[b];
@@ -139,7 +148,7 @@ qn_ras_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_,
     S.alpha = 0.0; S.lo = 0.0; S.hi = INFINITY; S.iter = 0; S.status = 0;
     bool interior = false;
     for (;;) {
-        for (int i = tid; i < n; i += nt) {
+        for (int i = tid; i < np; i += nt) {
             const double sig = i < order ? -1.0 : 1.0;
             const double den = L[i] + S.alpha * sig;
             const double ci = vg[i] / den;
@@ -150,8 +159,10 @@ qn_ras_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_,
         // s = -V c1, ds = V c2 : column combination of the rows of Vt
         for (int j = tid; j < n; j += nt) {
             double a = 0.0, d = 0.0;
-            for (int i = 0; i < n; ++i) {
-                const double v = Vt[(size_t)i * n + j];
+            for (int i = 0; i < np; ++i) {
+                const int r = rm[i];
+                if (r < -1) continue;
+                const double v = r >= 0 ? Vt[(size_t)r * n + j] : gp[j] * ginv;
                 a = fma(v, c1[i], a);
                 d = fma(v, c2[i], d);
             }
@@ -190,7 +201,6 @@ qn_ras_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_,
         alpha_out[b] = S.alpha;
         if (S.status && status) atomicOr(&status[b], S.status);
     }
-    (void)scratch;
 }
 
 // out[b,0,:] = coef,  out[b,1,:] = |evals| * coef   (coefficients of s and |B| s in the
@@ -333,15 +343,23 @@ extern "C" int sb_qn_tr_impl(const double* Vg, const double* evals, const double
     return SB_LAUNCH_CHECK();
 }
 
-extern "C" int sb_qn_ras_impl(const double* Vg, const double* evals, const double* Vt, const double* delta,
-                              int order, int n, double* s, double* smag, double* alpha, int* status,
-                              const int* active, const double* sadd, int batch, cudaStream_t st) {
-    const size_t smem = (size_t)(6 * n + SB_SCRATCH_DOUBLES) * sizeof(double);
+extern "C" int sb_qn_ras_c_impl(const double* Vg, const double* evals, const double* Vt, const double* delta,
+                                int order, int n, double* s, double* smag, double* alpha, int* status,
+                                const int* active, const double* sadd, int np, const int* rowmap, const double* gperp,
+                                const double* gam, long long vstride, int batch, cudaStream_t st) {
+    const size_t smem = (size_t)(4 * np + 2 * n + SB_SCRATCH_DOUBLES) * sizeof(double) + (size_t)(np + 2) * sizeof(int);
     cudaFuncSetAttribute(qn_ras_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     SB_COUNT(1);
     qn_ras_kernel<<<batch, TR_THREADS, smem, st>>>(Vg, evals, Vt, delta, order, n, s, smag, alpha, status, active,
-                                                   sadd);
+                                                   sadd, np, rowmap, gperp, gam, vstride);
     return SB_LAUNCH_CHECK();
+}
+
+extern "C" int sb_qn_ras_impl(const double* Vg, const double* evals, const double* Vt, const double* delta,
+                              int order, int n, double* s, double* smag, double* alpha, int* status,
+                              const int* active, const double* sadd, int batch, cudaStream_t st) {
+    return sb_qn_ras_c_impl(Vg, evals, Vt, delta, order, n, s, smag, alpha, status, active, sadd, n, nullptr, nullptr,
+                            nullptr, (long long)n * n, batch, st);
 }
 
 extern "C" int sb_pack_coef_impl(const double* coef, const double* evals, double* out, int n, const int* active,

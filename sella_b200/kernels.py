@@ -98,6 +98,15 @@ def hv_ld(A, X, Y, nvec, transposed=False, active=None):
     return Y
 
 
+def hv_rect(A, m, X, Y, nvec, transposed=False, active=None):
+    """hv_ld on the first m rows of every A[b] (A: [b, rows, n] contiguous): transposed=False gives
+    Y[b,v,:m] = A[b,:m] @ X[b,v]; transposed=True gives Y[b,v,:] = A[b,:m].T @ X[b,v,:m]."""
+    b, rows, n = A.shape
+    call("sb_hv_rect", _p(A), LL(rows * n), I(int(m)), _p(X), _p(Y), _p(active), I(b), I(n), I(nvec), I(X.shape[1]),
+         I(int(transposed)), _stream())
+    return Y
+
+
 def mgs(X, Y=None, eps1=1e-15, eps2=1e-6, maxiter=100, active=None):
     """Batched modified_gram_schmidt: X [b,nx,n] (modified in place), Y [b,ny,n]."""
     require_cuda()

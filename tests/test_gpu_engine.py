@@ -50,16 +50,34 @@ def test_mgs_error_code():
     assert (nkept.cpu().numpy() == -2).all() and (status.cpu().numpy() & 1).all()
 
 
-@pytest.mark.parametrize("eig_mode", ["update", "direct"])
+def check_carried_spectrum(eng, B, nsys, atol=1e-10):
+    """The carried eigenpairs are those of the Hessian the engine reports: explicit pairs (theta_i, v_i)
+    with B v_i = theta_i v_i, orthonormal; the rest of the spectrum is lam0 (compact representation)."""
+    for i in range(nsys):
+        th, VR, lam0, m = eng.explicit_pairs(i)
+        n = B[i].shape[0]
+        full = np.sort(np.concatenate([th, np.full(n - m, lam0)]))
+        np.testing.assert_allclose(full, np.linalg.eigvalsh(B[i]), atol=atol)
+        np.testing.assert_allclose(B[i] @ VR.T, VR.T * th[None, :], atol=10 * atol)
+        np.testing.assert_allclose(VR @ VR.T, np.eye(m), atol=1e-12)
+        assert (np.diff(th) >= 0).all()
+
+
+@pytest.mark.parametrize("mode", ["compact", "dense", "direct"])
 @pytest.mark.parametrize("rs", ["tr", "ras"])
 @pytest.mark.parametrize("n", [30, 48, 96])
-def test_engine_matches_oracle_loop(n, rs, eig_mode):
-    """Every step of 5 independent searches equals the CPU oracle's trajectory."""
+def test_engine_matches_oracle_loop(n, rs, mode):
+    """Every step of 5 independent searches equals the CPU oracle's trajectory, for the three ways the
+    engine can hold the spectrum of B: compact (explicit pairs + lam0 on the complement, eigen-updated),
+    dense eigen-updated, and a fresh eigensolve whenever needed (the reference's way)."""
     from oracle.pes import CartesianPES
     from oracle.driver import SaddleSearch
     from sella_b200.synthetic import quadratic_func
     systems = [0, 1, 2, 3, 4]
-    eng, data = make_engine(n, systems, method="qn", rs=rs, eig_mode=eig_mode)
+    eig_mode = "direct" if mode == "direct" else "update"
+    eng, data = make_engine(n, systems, method="qn", rs=rs, eig_mode=eig_mode,
+                            spectrum=None if mode == "direct" else mode)
+    assert eng.compact == (mode == "compact")
     oracles = []
     for (A, xs, x0) in data:
         p = CartesianPES(quadratic_func(A, xs), x0)
@@ -75,19 +93,16 @@ def test_engine_matches_oracle_loop(n, rs, eig_mode):
     B = eng.B.cpu().numpy()
     for i, (p, o) in enumerate(oracles):
         np.testing.assert_allclose(B[i], p.H.B, rtol=1e-6, atol=1e-7)
-        assert np.array_equal(B[i], B[i].T)          # stored Hessian stays bitwise symmetric
+        assert np.array_equal(B[i], B[i].T)          # the Hessian stays bitwise symmetric
     if eig_mode == "update":
-        # the carried eigenpairs are those of the stored Hessian
-        w, Vt = eng.evals.cpu().numpy(), eng.Vt.cpu().numpy()
-        for i in range(len(systems)):
-            np.testing.assert_allclose(w[i], np.linalg.eigvalsh(B[i]), atol=1e-10)
-            np.testing.assert_allclose(B[i] @ Vt[i].T, Vt[i].T * w[i][None, :], atol=1e-9)
+        check_carried_spectrum(eng, B, len(systems))
 
 
+@pytest.mark.parametrize("spectrum", ["compact", "dense"])
 @pytest.mark.parametrize("rs", ["tr", "ras"])
 @pytest.mark.parametrize("method", ["prfo", "rfo"])
 @pytest.mark.parametrize("n", [30, 48, 96])
-def test_engine_rfo_models_match_oracle(n, method, rs):
+def test_engine_rfo_models_match_oracle(n, method, rs, spectrum):
     """P-RFO (Sella's default for saddles) and RFO through the arrow-head secular
     solver vs the oracle, which diagonalises the bordered matrix for every alpha."""
     from oracle.pes import CartesianPES
@@ -96,7 +111,7 @@ def test_engine_rfo_models_match_oracle(n, method, rs):
     systems = [0, 1, 2, 3]
     if method == "rfo" and rs == "ras":
         pytest.skip("plain rfo on a saddle with a tiny atomic radius is ill-posed in the reference itself")
-    eng, data = make_engine(n, systems, method=method, rs=rs)
+    eng, data = make_engine(n, systems, method=method, rs=rs, spectrum=spectrum)
     oracles = []
     for (A, xs, x0) in data:
         p = CartesianPES(quadratic_func(A, xs), x0)
@@ -439,3 +454,69 @@ def test_engine_with_hessian_function_and_v0():
         eng2.step()
     for i, (p, o) in enumerate(oracles):
         np.testing.assert_allclose(eng2.x[i].cpu().numpy(), p.get_x(), rtol=0, atol=1e-8)
+
+
+@pytest.mark.parametrize("spectrum", ["compact", "dense"])
+def test_engine_bench_setting_step_by_step(spectrum):
+    """The exact setting bench.py times (3N = 384, prfo + trust radius, TS-BFGS, jd0 capped at 5 vectors,
+    re-diagonalisation every 3rd step), 4 systems x 25 steps, every step against the oracle: positions,
+    trust radii, and the step vector itself."""
+    from oracle.pes import CartesianPES
+    from oracle.driver import SaddleSearch
+    from sella_b200.synthetic import quadratic_func
+    n, systems = 384, [0, 1, 2, 3]
+    kw = dict(method="prfo", rs="tr", diag_maxiter=5, diag_every_n=3)
+    eng, data = make_engine(n, systems, kcap=8, spectrum=spectrum, **kw)
+    oracles = []
+    for (A, xs, x0) in data:
+        p = CartesianPES(quadratic_func(A, xs), x0)
+        oracles.append((p, SaddleSearch(p, **kw)))
+    worst_x = worst_s = 0.0
+    for t in range(25):
+        eng.step()
+        x = eng.x.cpu().numpy(); delta = eng.delta.cpu().numpy(); s = eng.s.cpu().numpy()
+        for i, (p, o) in enumerate(oracles):
+            o.step()
+            sref = o.history[-1]["s"]
+            worst_x = max(worst_x, float(np.abs(x[i] - p.get_x()).max()))
+            worst_s = max(worst_s, float(np.abs(s[i] - sref).max() / np.abs(sref).max()))
+            np.testing.assert_allclose(x[i], p.get_x(), rtol=0, atol=1e-8, err_msg="system %d step %d" % (i, t))
+            np.testing.assert_allclose(delta[i], o.delta, rtol=1e-8 if t < 10 else 1e-6)
+            # the step is a function of (x, g, B): it inherits the ~1e-9 drift of the trajectory, not more
+            assert np.abs(s[i] - sref).max() <= 1e-7 * np.abs(sref).max() + 1e-10, (i, t)
+    eng.check_status()
+    lam = eng.lowest_evals().cpu().numpy()
+    for i, (p, o) in enumerate(oracles):
+        np.testing.assert_allclose(lam[i], p.H.evals[0], rtol=1e-9)
+    print("bench-setting parity (%s): max |dx| %.2e, max rel |ds| %.2e" % (spectrum, worst_x, worst_s))
+
+
+@pytest.mark.parametrize("spectrum", ["compact", "dense"])
+def test_carried_spectrum_after_300_updates(spectrum):
+    """Hundreds of chained eigen-updates without a single fresh eigensolve: the carried pairs must stay
+    orthonormal and remain eigenpairs of the Hessian they describe (the engine never refreshes by default)."""
+    n, systems = 96, [0, 1, 2]
+    eng, data = make_engine(n, systems, method="prfo", rs="tr", diag_maxiter=5, diag_every_n=3, kcap=8,
+                            spectrum=spectrum, **(dict(track_B=True) if spectrum == "compact" else {}))
+    # keep the searches moving: a converged search stops producing updates (steps < 1e-8 are skipped),
+    # so the surface is shifted every 30 steps (x* moves, the Hessian model keeps accumulating)
+    for t in range(200):
+        eng.step()
+        if t % 30 == 29:
+            eng.surface.xstar += 0.05
+            eng._evaluated = False
+            eng.surface.evaluate(eng.x, eng.f, eng.g)
+    eng.check_status()
+    assert eng.ndiag >= 45                      # 200 step updates + >= 45 block updates (rank up to 10 each)
+    # the dense matrix carried INDEPENDENTLY through all updates by sb_update_apply
+    B = (eng.tracked_B if spectrum == "compact" else eng._B).cpu().numpy()
+    if spectrum == "compact":
+        np.testing.assert_allclose(eng.B.cpu().numpy(), B, atol=1e-10)
+    for i in range(len(systems)):
+        th, VR, lam0, m = eng.explicit_pairs(i)
+        np.testing.assert_allclose(VR @ VR.T, np.eye(m), atol=1e-10)
+        np.testing.assert_allclose(B[i] @ VR.T, VR.T * th[None, :], atol=1e-10 * max(1.0, np.abs(th).max()))
+        full = np.sort(np.concatenate([th, np.full(n - m, lam0)]))
+        np.testing.assert_allclose(full, np.linalg.eigvalsh(B[i]), atol=1e-10 * max(1.0, np.abs(th).max()))
+    if spectrum == "compact":
+        assert int(eng.mrows.min()) == n        # long past the point where the explicit rank reaches 3N

@@ -156,6 +156,10 @@ def test_eigh_large_sizes(n):
         np.testing.assert_allclose(w[i].sum(), np.trace(A[i]), rtol=0, atol=1e-11 * scale * n ** 0.5)
 
 
+def p_B(pes):
+    return pes.H.B
+
+
 @pytest.mark.parametrize("n", [768, 1536])
 def test_engine_large_sizes_match_oracle(n):
     """C4/C5 sizes: a few steps of two searches against the oracle, and the carried eigenpairs
@@ -180,6 +184,9 @@ def test_engine_large_sizes_match_oracle(n):
             o.step()
             np.testing.assert_allclose(x[i], p.get_x(), rtol=0, atol=1e-8)
     eng.check_status()
-    B, w, Vt = eng.B.cpu().numpy(), eng.evals.cpu().numpy(), eng.Vt.cpu().numpy()
+    B = eng.B.cpu().numpy()
     for i in range(2):
-        np.testing.assert_allclose(B[i] @ Vt[i].T, Vt[i].T * w[i][None, :], atol=1e-10)
+        th, VR, lam0, m = eng.explicit_pairs(i)
+        assert eng.compact and m < n                      # a handful of steps: far from the dense limit
+        np.testing.assert_allclose(B[i] @ VR.T, VR.T * th[None, :], atol=1e-10)
+        np.testing.assert_allclose(p_B(orc[i][0]), B[i], rtol=1e-6, atol=1e-7)
