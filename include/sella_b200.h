@@ -308,7 +308,11 @@ int sb_trtri(const double* R, double* Rinv, double* work, int n, int32_t* status
  *   sb_compact_append_b : candidates projected once more (W2 = VR^T (VR Qc)), re-orthonormalised,
  *                         appended as rows mrows.. with eigenvalue lam0; Z[b,t,mrows+j] = q_j.p_t;
  *                         mrows[b] += number appended
- *   sb_secular_update_c : sb_secular_update on the first mrows[b] rows (mcap: HOST bound on mrows)
+ *   sb_secular_update_c : sb_secular_update on the first mrows[b] rows (mcap: HOST bound on mrows).  With
+ *                         aux (int32 [b, mcap + 4]) and nterm_max (HOST bound on nterm) the work is split:
+ *                         per rank-one term one solve launch (deflation, secular roots, rotation matrix),
+ *                         the rotation of the eigenvector rows as a batched fp64 tensor-core GEMM and a
+ *                         copy back, then the final sort; aux == NULL: one launch does everything
  *   sb_compact_prepare  : merged ascending pole list (width entries, stride width) for sb_qn_tr /
  *                         sb_rfo_tr / the *_ras_c kernels: explicit eigenvalues with coefficients Vg = VR g,
  *                         the complement as ONE pole lam0 with coefficient |g_perp| (g_perp = g - Wg,
@@ -321,7 +325,7 @@ int sb_trtri(const double* R, double* Rinv, double* work, int n, int32_t* status
  *                         mode 0: f = |.| (the |B| S of TS-BFGS, hessian_update.py:118-125), 1: f = id
  *   sb_compact_jd_coeff / sb_compact_jd_finish : Jacobi-Davidson correction (eigensolvers.py:115-139)
  *                         in the eigenbasis of the preconditioner, method 0 jd0, 1 gd
- *   sb_compact_lowest   : lowest eigenvalue of B per system
+ *   sb_compact_lowest   : the k lowest eigenvalues of B per system (out [b,k]; the test of optimize.py:369-371)
  *   sb_qn_ras_c / sb_rfo_ras_c / sb_davidson_init_c : the dense kernels of the same name on a pole
  *                         list / the compact rows                                                      */
 int sb_hv_rect(const double* A, long long astride, int mrows, const double* X, double* Y, const int32_t* active,
@@ -333,8 +337,8 @@ int sb_compact_append_b(const double* P, const double* Qc, const double* W2, int
                         int32_t* mrows, const double* lam0, double* Z, const int32_t* skip, int batch, void* stream);
 int sb_secular_update_c(double* evals, double* Vt, double* Z, int zcap, const double* sig, const int32_t* nterm,
                         int n, double* work, double* qwork, int32_t* status, const int32_t* skip,
-                        const int32_t* mrows, int mcap, long long estride, long long vstride, int batch,
-                        void* stream);
+                        const int32_t* mrows, int mcap, long long estride, long long vstride, int nterm_max,
+                        int32_t* aux, int batch, void* stream);
 int sb_compact_prepare(const double* g, const double* Vg, const double* Wg, const double* evals, long long estride,
                        const int32_t* mrows, const double* lam0, int n, int width, double* gperp, double* gam,
                        double* cev, double* cvg, int32_t* rowmap, const int32_t* active, int batch, void* stream);
@@ -355,7 +359,10 @@ int sb_compact_jd_coeff(const double* rvhat, const double* rv, const double* eva
 int sb_compact_jd_finish(double* t, const double* rv, const double* ed, int n, int method, const int32_t* dav_state,
                          int batch, void* stream);
 int sb_compact_lowest(const double* evals, long long estride, const int32_t* mrows, const double* lam0, int n,
-                      double* out, int batch, void* stream);
+                      int k, double* out, int batch, void* stream);
+/* out[b,v,:] = mask[:] * X[b,v,:], v < nvec: the projection onto the free coordinates when whole Cartesian
+ * coordinates are fixed (Constraints.fix_translation(i): Ufree of sella/peswrapper.py:51-69 is a permutation) */
+int sb_mask_vec(const double* X, const double* mask, double* out, int ldv, int nvec, int n, int batch, void* stream);
 int sb_qn_ras_c(const double* Vg, const double* evals, const double* Vt, const double* delta, int order, int n,
                 double* s, double* smag, double* alpha, int32_t* status, const int32_t* active, const double* sadd,
                 int npole, const int32_t* rowmap, const double* gperp, const double* gam, long long vstride,

@@ -13,14 +13,16 @@ dev = torch.device("cuda:0")
 up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
 
-def run(n, method, rs, nsteps, **kw):
+def run(n, method, rs, nsteps, nfix=0, **kw):
     systems = [0, 1, 2]
     data = [quadratic_system(b, n) for b in systems]
+    C = np.eye(n)[:nfix] if nfix else None
     eng = BatchedSella(QuadraticSurface(up(np.stack([d[0] for d in data])), up(np.stack([d[1] for d in data]))),
-                       up(np.stack([d[2] for d in data])), method=method, rs=rs, spectrum="compact", track_B=True, **kw)
+                       up(np.stack([d[2] for d in data])), method=method, rs=rs, spectrum="compact", track_B=True,
+                       constraints=None if C is None else (C, None), **kw)
     orc = []
     for (A, xs, x0) in data:
-        p = CartesianPES(quadratic_func(A, xs), x0)
+        p = CartesianPES(quadratic_func(A, xs), x0, C, None if C is None else C @ x0)
         orc.append((p, SaddleSearch(p, method=method, rs=rs, **{k: v for k, v in kw.items() if k in ("diag_maxiter", "diag_every_n")})))
     print("=== n=%d %s %s %s" % (n, method, rs, kw))
     for t in range(nsteps):
@@ -44,7 +46,7 @@ def run(n, method, rs, nsteps, **kw):
             if m:
                 orth = max(orth, np.abs(VR @ VR.T - np.eye(m)).max())
         print("step %2d dx %.2e  |Btrack-Bspec| %.2e  |Btrack-Boracle| %.2e  orth %.2e  mrows %s rb %d status %s delta %s"
-              % (t, max(dx), errB, errO, orth, eng.mrows.cpu().tolist(), eng._rb, eng.status.cpu().tolist(),
+              % (t, max(dx), errB, errO, orth, (eng.mrows.cpu().tolist(), eng.sp.mrows.cpu().tolist()), eng._rb, eng.status.cpu().tolist(),
                  np.round(eng.delta.cpu().numpy(), 6).tolist()))
         if not np.isfinite(max(dx)) or max(dx) > 1e-3:
             print("diverged; stopping this case")
@@ -57,3 +59,6 @@ if __name__ == "__main__":
     run(30, "qn", "ras", 8)
     run(48, "prfo", "tr", 10, diag_maxiter=5, diag_every_n=3)
     run(48, "prfo", "ras", 6)
+    run(30, "qn", "tr", 10, nfix=6)
+    run(48, "prfo", "ras", 8, nfix=6)
+    run(48, "prfo", "tr", 10, nfix=9, diag_maxiter=5, diag_every_n=3)

@@ -57,6 +57,24 @@ class QuadraticSurface:
              _p(self._work), _p(active), I(self.batch), I(self.n), _stream())
 
 
+class _Spec:
+    """One compact spectrum: mrows[b] explicit eigenpairs in the first rows of (evals, Vt); every other
+    eigenvalue is lam0[b] (shared by the spectra of B and of its projection).  rb / mmin: host-side upper /
+    lower bounds on mrows (rows the passes visit; mmin == n: no complement left in any system)."""
+
+    def __init__(self, batch, n, dev, evals=None, Vt=None):
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.evals = torch.zeros(batch, n, **f64) if evals is None else evals
+        self.Vt = torch.zeros(batch, n, n, **f64) if Vt is None else Vt
+        self.mrows = torch.zeros(batch, dtype=torch.int32, device=dev)
+        self.rb = 0
+        self.mmin = 0
+
+    def reset(self):
+        self.mrows.zero_()
+        self.rb = self.mmin = 0
+
+
 class BatchedSella:
     def __init__(self, surface, x0, order=1, delta0=None, sigma_inc=None, sigma_dec=None,
                  rho_dec=None, rho_inc=None, eig=None, eta=1e-4, method=None, gamma=0.1,
@@ -155,12 +173,23 @@ class BatchedSella:
         # of (evals, Vt) and lam0 on the rest (csrc/compact.cu); the dense matrix is only materialised on
         # request (property B).  "dense": B [b,n,n] and a full (evals, Vt), as in round 1.
         want = self._spectrum_request
-        can = (eig_mode == "update" and constraints is None and self.eigensolver != 3 and self.kcap <= 16
-               and n <= 1536)
+        fixed = self._single_coordinate_constraints(constraints, x0)
+        can = (eig_mode == "update" and (constraints is None or (fixed is not None and hessian_function is None))
+               and self.eigensolver != 3 and self.kcap <= 16 and n <= 1536)
         if want == "compact" and not can:
-            raise NotImplementedError("spectrum='compact' needs eig_mode='update', no constraints, kcap <= 16 and an "
-                                      "eigensolver other than mjd0 (those run on the dense representation)")
+            raise NotImplementedError("spectrum='compact' needs eig_mode='update', kcap <= 16, an eigensolver other "
+                                      "than mjd0 and either no constraints or fixed Cartesian coordinates that hold "
+                                      "at x0 (everything else runs on the dense representation)")
         self.compact = can and want != "dense"
+        # fixed Cartesian coordinates (what Constraints.fix_translation(i) yields; peswrapper.py:51-69 makes
+        # Ufree a signed permutation then): the projection onto the free space is a 0/1 mask
+        self.fmask = None
+        if self.compact and fixed is not None and len(fixed):
+            mk = np.ones(n)
+            mk[fixed] = 0.0
+            self.fmask = torch.from_numpy(mk).to(dev)
+            self.nfree = n - len(fixed)
+            constraints = None
         self._B = None if self.compact else z(b, n, n)
         # compact only: ALSO carry the dense matrix through every update (sb_update_apply), as an
         # independent check of the carried spectrum (tests); off on the hot path
@@ -187,9 +216,19 @@ class BatchedSella:
             self.nterm = zi(b)
             self.qwork = z(b, n, n)
         if self.compact:
-            self.mrows = zi(b)                 # explicit eigenpairs per system
-            self._rb = 0                       # host-side bound on mrows (rows any pass has to visit)
-            self._mmin = 0                     # host-side lower bound on mrows (== n: no complement left anywhere)
+            # sp: spectrum of the step model (B projected onto the free coordinates); spB: spectrum of B itself
+            # (|B| S and B S of the secant update, the "lowest mode went positive" test) -- one object when
+            # nothing is fixed
+            self.sp = _Spec(b, n, dev, self.evals, self.Vt)
+            self.spB = self.sp if self.fmask is None else _Spec(b, n, dev)
+            self.gm = self.g if self.fmask is None else z(b, n)               # P_f g
+            # rotation of the eigenvector rows per rank-one term: a batched DMMA GEMM over the whole GPU
+            # (split mode of sb_secular_update_c) once there are enough rows for 64 x 64 tiles to pay
+            import os
+            self.split_rotation = os.environ.get("SB_SPLIT_ROTATION", "1") != "0"
+            self.split_min_rows = int(os.environ.get("SB_SPLIT_MIN_ROWS", "24"))
+            self.sec_aux = zi(b, n + 4)
+            self.lowk = z(b, max(1, self.order))
             self.cev, self.cvg, self.ccoef = z(b * n), z(b * n), z(b * n)      # pole lists, stride = width
             self.rowmap = zi(b * n)
             self.gperp, self.Wg, self.gam, self.kappa = z(b, n), z(b, n), z(b), z(b)
@@ -199,6 +238,12 @@ class BatchedSella:
             for sec, zc in ((self.sec1, 2), (self.seck, 2 * kc)):
                 for k in ("W1", "Qc", "D2", "W2"):
                     sec[k] = z(b, zc, n)
+            if self.fmask is not None:
+                for bufs, kk in ((self.up1, 1), (self.upk, kc)):
+                    bufs["Um"], bufs["Jm"] = z(b, kk, n), z(b, kk, n)
+                if self.rs == "tr":
+                    # optimize.py:183-187: the spherical radius scales with the number of free coordinates
+                    self.delta.fill_(float(delta0 * self.nfree))
         self._setup_constraints(constraints)
         if self.cons is not None and self.rs == "tr":
             # optimize.py:183-187: the spherical radius scales with the number of free coordinates
@@ -469,47 +514,106 @@ class BatchedSella:
         return {k: (len(v), sum(a.elapsed_time(z) for a, z in v) / len(v)) for k, v in (self.prof or {}).items()}
 
     # ------------------------------------------------------------------ compact representation
+    @staticmethod
+    def _single_coordinate_constraints(constraints, x0):
+        """Indices of the fixed Cartesian coordinates if `constraints` = (C, c) holds single coordinates at
+        their current values (rows of the identity, one matrix for the whole batch), else None."""
+        if constraints is None or len(constraints) != 2:
+            return None
+        C, c = constraints
+        C = np.asarray(C, dtype=np.float64)
+        if C.ndim != 2 or C.shape[0] == 0:
+            return None
+        nz = C != 0.0
+        if not ((nz.sum(axis=1) == 1).all() and (C[nz] == 1.0).all() and (nz.sum(axis=0) <= 1).all()):
+            return None
+        idx = np.argmax(nz, axis=1)
+        if c is not None:
+            cur = x0[:, torch.from_numpy(idx).to(x0.device)].cpu().numpy()
+            if not np.array_equal(np.broadcast_to(np.asarray(c, dtype=np.float64), cur.shape), cur):
+                return None             # a target away from the current value: the scons machinery (dense path)
+        return idx
+
+    @property
+    def mrows(self):
+        return self.spB.mrows
+
+    @property
+    def _rb(self):
+        return self.spB.rb
+
     @property
     def B(self):
         """Dense approximate Hessian [b, n, n] (materialised from the compact representation on request)."""
         if not self.compact:
             return self._B
+        sp = self.spB
         b, n = self.batch, self.n
         eye = torch.eye(n, dtype=torch.float64, device=self.dev)
-        R = self._rb
+        R = sp.rb
         out = self.lam0[:, None, None] * eye
         if R > 0 and self.H_initialized:
-            live = (torch.arange(R, device=self.dev)[None, :] < self.mrows[:, None]).to(torch.float64)
-            d = (self.evals[:, :R] - self.lam0[:, None]) * live
-            VR = self.Vt[:, :R].contiguous()
+            live = (torch.arange(R, device=self.dev)[None, :] < sp.mrows[:, None]).to(torch.float64)
+            d = (sp.evals[:, :R] - self.lam0[:, None]) * live
+            VR = sp.Vt[:, :R].contiguous()
             out = out + K.gemm(VR, (d[:, :, None] * VR).contiguous(), transA=True)
         return 0.5 * (out + out.transpose(1, 2))
 
-    def _hvr(self, X, Y, nvec, transposed=False, active=None):
+    def _hvr(self, sp, X, Y, nvec, transposed=False, active=None):
         """Pass over the explicit rows: Y[:, :, :R] = VR X (or Y = VR^T X[:, :, :R]); R = 0 leaves zeros."""
-        if self._rb > 0:
-            K.hv_rect(self.Vt, self._rb, X, Y, nvec, transposed=transposed, active=active)
+        if sp.rb > 0:
+            K.hv_rect(sp.Vt, sp.rb, X, Y, nvec, transposed=transposed, active=active)
         else:
             Y[:, :nvec].zero_()
 
-    def _spectral_apply(self, S, bufs, nv, active):
-        """bufs['BS'] = B S and bufs['aBS'] = |B| S from the compact spectrum (linalg.py:293 -> 174-195 and
+    def _mask(self, X, out, nvec):
+        """out[:, :nvec] = P_f X[:, :nvec] for fixed Cartesian coordinates (a 0/1 mask)."""
+        call("sb_mask_vec", _p(X), _p(self.fmask), _p(out), I(X.shape[1]), I(nvec), I(self.n), I(self.batch), _stream())
+
+    def _spectral_apply(self, sp, S, bufs, nv, active):
+        """bufs['BS'] = B S and bufs['aBS'] = |B| S from a compact spectrum (linalg.py:293 -> 174-195 and
         hessian_update.py:118-125 need eigh(B) for this in the reference)."""
-        b, n, kc, R = self.batch, self.n, S.shape[1], self._rb
+        b, n, kc, R = self.batch, self.n, S.shape[1], sp.rb
         es = LL(n)
-        self._hvr(S, bufs["VtS"], nv, active=active)
+        self._hvr(sp, S, bufs["VtS"], nv, active=active)
         for mode, key in ((0, "aBS"), (1, "BS")):
             if R > 0:
-                call("sb_compact_scale", _p(bufs["VtS"]), _p(self.evals), es, _p(self.mrows), _p(self.lam0), I(kc), I(nv),
+                call("sb_compact_scale", _p(bufs["VtS"]), _p(sp.evals), es, _p(sp.mrows), _p(self.lam0), I(kc), I(nv),
                      I(n), I(R), I(mode), _p(bufs["aC"]), _p(self.skip), I(b), _stream())
-            self._hvr(bufs["aC"], bufs["Xw"], nv, transposed=True, active=active)
+            self._hvr(sp, bufs["aC"], bufs["Xw"], nv, transposed=True, active=active)
             call("sb_compact_axpy", _p(S), _p(bufs["Xw"]), _p(self.lam0), I(kc), I(nv), I(n), I(mode), _p(bufs[key]),
                  _p(self.skip), I(b), _stream())
 
+    def _eigen_update(self, sp, U, J, kc, kvec, nv, active):
+        """(lam0, theta, VR) of M  ->  of M + U J^T + J U^T - U sym(C) U^T (C = self.Cmat): the part of the
+        update outside span(VR) joins VR as new rows with eigenvalue lam0, then ONE secular-equation
+        update of the explicit pairs."""
+        b, n = self.batch, self.n
+        sec = self.sec1 if kc == 1 else self.seck
+        zc, T = 2 * kc, 2 * nv
+        es, vs = LL(n), LL(n * n)
+        call("sb_lowrank_factor", _p(U), _p(J), _p(self.Cmat), I(kc), _p(kvec), I(n),
+             _p(sec["P"]), _p(sec["sig"]), _p(self.nterm), _p(self.skip), I(b), _stream())
+        R = sp.rb
+        self._hvr(sp, sec["P"], sec["Z"], T, active=active)
+        if sp.mmin < n:
+            self._hvr(sp, sec["Z"], sec["W1"], T, transposed=True, active=active)
+            call("sb_compact_append_a", _p(sec["P"]), _p(sec["W1"]), I(zc), _p(self.nterm), _p(sp.mrows), I(n),
+                 _p(sec["Qc"]), _p(self.ncand), _p(self.skip), I(b), _stream())
+            self._hvr(sp, sec["Qc"], sec["D2"], T, active=active)
+            self._hvr(sp, sec["D2"], sec["W2"], T, transposed=True, active=active)
+            call("sb_compact_append_b", _p(sec["P"]), _p(sec["Qc"]), _p(sec["W2"]), I(zc), _p(self.nterm),
+                 _p(self.ncand), I(n), _p(sp.evals), es, _p(sp.Vt), vs, _p(sp.mrows), _p(self.lam0),
+                 _p(sec["Z"]), _p(self.skip), I(b), _stream())
+            sp.rb = min(n, R + T)
+        split = self.split_rotation and sp.rb >= self.split_min_rows
+        call("sb_secular_update_c", _p(sp.evals), _p(sp.Vt), _p(sec["Z"]), I(zc), _p(sec["sig"]),
+             _p(self.nterm), I(n), _p(self.eig_ws.work), _p(self.qwork), _p(self.status), _p(self.skip),
+             _p(sp.mrows), I(sp.rb), es, vs, I(T if split else 0), _p(self.sec_aux if split else None), I(b),
+             _stream())
+
     def _update_compact(self, S, Y, bufs, kvec, nv, active, bs_ready=False, abs_ready=False):
-        """ApproximateHessian.update (linalg.py:274-304) on the compact representation: the secant update
-        Delta = sum_t sig_t p_t p_t^T enters as new explicit directions (the part of p_t outside span(VR))
-        plus one secular-equation update of the explicit eigenpairs."""
+        """ApproximateHessian.update (linalg.py:274-304) on the compact representation."""
         b, n = self.batch, self.n
         kc = S.shape[1]
         first = not self.H_initialized
@@ -518,12 +622,12 @@ class BatchedSella:
         if first:
             # B = lam0 I (hessian_update.py:58-67): no explicit pairs yet; systems whose first update is a
             # no-op keep the identity model (lam0 = 1)
-            self.mrows.zero_()
-            self._rb = self._mmin = 0
+            self.sp.reset()
+            self.spB.reset()
             self.H_initialized = True
             bs_ready = abs_ready = False
         if not (bs_ready and (abs_ready or self.update_method != 0)):
-            self._spectral_apply(S, bufs, nv, active)
+            self._spectral_apply(self.spB, S, bufs, nv, active)
         call("sb_update_mid", _p(S), _p(bufs["Ytil"]), _p(bufs["BS"]),
              _p(bufs["aBS"] if self.update_method == 0 else None), _p(bufs["U"]), _p(bufs["J"]), _p(bufs["W"]),
              _p(bufs["Xw"]), I(kc), _p(kvec), I(n), I(self.update_method), _p(self.skip), _p(self.status),
@@ -534,50 +638,36 @@ class BatchedSella:
                      _p(self.skip), I(b), _stream())
             call("sb_update_apply", _p(self.tracked_B), _p(bufs["U"]), _p(bufs["J"]), _p(bufs["W"]), I(kc), _p(kvec),
                  I(n), _p(self.skip), I(b), _stream())
-        sec = self.sec1 if kc == 1 else self.seck
-        zc, T = 2 * kc, 2 * nv
-        es, vs = LL(n), LL(n * n)
 
         def run():
-            call("sb_lowrank_factor", _p(bufs["U"]), _p(bufs["J"]), _p(self.Cmat), I(kc), _p(kvec), I(n),
-                 _p(sec["P"]), _p(sec["sig"]), _p(self.nterm), _p(self.skip), I(b), _stream())
-            R = self._rb
-            if R == 0:
-                sec["Z"].zero_()
-            self._hvr(sec["P"], sec["Z"], T, active=active)
-            if self._mmin < n:
-                self._hvr(sec["Z"], sec["W1"], T, transposed=True, active=active)
-                call("sb_compact_append_a", _p(sec["P"]), _p(sec["W1"]), I(zc), _p(self.nterm), _p(self.mrows), I(n),
-                     _p(sec["Qc"]), _p(self.ncand), _p(self.skip), I(b), _stream())
-                self._hvr(sec["Qc"], sec["D2"], T, active=active)
-                self._hvr(sec["D2"], sec["W2"], T, transposed=True, active=active)
-                call("sb_compact_append_b", _p(sec["P"]), _p(sec["Qc"]), _p(sec["W2"]), I(zc), _p(self.nterm),
-                     _p(self.ncand), I(n), _p(self.evals), es, _p(self.Vt), vs, _p(self.mrows), _p(self.lam0),
-                     _p(sec["Z"]), _p(self.skip), I(b), _stream())
-                self._rb = min(n, R + T)
-            call("sb_secular_update_c", _p(self.evals), _p(self.Vt), _p(sec["Z"]), I(zc), _p(sec["sig"]),
-                 _p(self.nterm), I(n), _p(self.eig_ws.work), _p(self.qwork), _p(self.status), _p(self.skip),
-                 _p(self.mrows), I(self._rb), es, vs, I(b), _stream())
+            self._eigen_update(self.spB, bufs["U"], bufs["J"], kc, kvec, nv, active)
+            if self.fmask is not None:
+                # the same update seen by the projected Hessian: (B + Delta)_ff = B_ff + Delta_ff
+                self._mask(bufs["U"], bufs["Um"], nv)
+                self._mask(bufs["J"], bufs["Jm"], nv)
+                self._eigen_update(self.sp, bufs["Um"], bufs["Jm"], kc, kvec, nv, active)
         self._timed("eigen_update_k%d" % kc, run)
         self._updates_since_refresh += 1
         self.eig_valid = True
 
     def _refresh_poles(self, active=None):
-        """Vg = VR g, g_perp and the merged pole list of the current model at the current gradient."""
-        b, n = self.batch, self.n
-        width = min(n, self._rb + 1)
-        self._hvr(self.g.view(b, 1, n), self.Vg.view(b, 1, n), 1, active=active)
-        self._hvr(self.Vg.view(b, 1, n), self.Wg.view(b, 1, n), 1, transposed=True, active=active)
-        call("sb_compact_prepare", _p(self.g), _p(self.Vg), _p(self.Wg), _p(self.evals), LL(n), _p(self.mrows),
+        """Vg = VR (P_f g), g_perp and the merged pole list of the step model at the current gradient."""
+        b, n, sp = self.batch, self.n, self.sp
+        width = min(n, sp.rb + 1)
+        if self.fmask is not None:
+            self._mask(self.g.view(b, 1, n), self.gm.view(b, 1, n), 1)
+        self._hvr(sp, self.gm.view(b, 1, n), self.Vg.view(b, 1, n), 1, active=active)
+        self._hvr(sp, self.Vg.view(b, 1, n), self.Wg.view(b, 1, n), 1, transposed=True, active=active)
+        call("sb_compact_prepare", _p(self.gm), _p(self.Vg), _p(self.Wg), _p(sp.evals), LL(n), _p(sp.mrows),
              _p(self.lam0), I(n), I(width), _p(self.gperp), _p(self.gam), _p(self.cev), _p(self.cvg), _p(self.rowmap),
              _p(active), I(b), _stream())
         return width
 
     def _predict_compact(self, active):
-        """Restricted step from the compact spectral model; returns abs_ready (|B| s already formed)."""
-        b, n = self.batch, self.n
+        """Restricted step from the compact spectral model; returns True when B s and |B| s of the FULL
+        Hessian are already in up1 (no fixed coordinates: the model is B itself)."""
+        b, n, sp = self.batch, self.n, self.sp
         width = self._refresh_poles(active)
-        S1 = self.s.view(b, 1, n)
         if self.rs == "tr":
             if self.method == "qn":
                 call("sb_qn_tr", _p(self.cvg), _p(self.cev), _p(self.delta), I(self.order), I(width), _p(self.ccoef),
@@ -586,26 +676,57 @@ class BatchedSella:
                 call("sb_rfo_tr", _p(self.cvg), _p(self.cev), _p(self.delta), I(self.order), I(width),
                      I(1 if self.method == "prfo" else 0), _p(self.ccoef), _p(self.smag), _p(self.alpha),
                      _p(self.status), _p(active), _p(None), I(b), _stream())
-            call("sb_compact_finish", _p(self.ccoef), _p(self.rowmap), I(width), _p(self.evals), LL(n), _p(self.gam),
-                 I(n), I(self._rb), _p(self.C4), _p(self.kappa), _p(active), I(b), _stream())
-            self._hvr(self.C4, self.T4, 3, transposed=True, active=active)
+            call("sb_compact_finish", _p(self.ccoef), _p(self.rowmap), I(width), _p(sp.evals), LL(n), _p(self.gam),
+                 I(n), I(sp.rb), _p(self.C4), _p(self.kappa), _p(active), I(b), _stream())
+            self._hvr(sp, self.C4, self.T4, 3, transposed=True, active=active)
             # s, |B| s, B s and x + s from the one transposed pass
             call("sb_compact_finish2", _p(self.T4), _p(self.gperp), _p(self.kappa), _p(self.lam0), _p(self.x), I(n),
                  _p(self.s), _p(self.up1["aBS"]), _p(self.up1["BS"]), _p(self.xnew), _p(active), I(b), _stream())
-            return True
+            return self.fmask is None
         if self.method == "qn":
-            call("sb_qn_ras_c", _p(self.cvg), _p(self.cev), _p(self.Vt), _p(self.delta), I(self.order), I(n),
+            call("sb_qn_ras_c", _p(self.cvg), _p(self.cev), _p(sp.Vt), _p(self.delta), I(self.order), I(n),
                  _p(self.s), _p(self.smag), _p(self.alpha), _p(self.status), _p(active), _p(None), I(width),
                  _p(self.rowmap), _p(self.gperp), _p(self.gam), LL(n * n), I(b), _stream())
         else:
-            call("sb_rfo_ras_c", _p(self.cvg), _p(self.cev), _p(self.Vt), _p(self.delta), I(self.order), I(n),
+            call("sb_rfo_ras_c", _p(self.cvg), _p(self.cev), _p(sp.Vt), _p(self.delta), I(self.order), I(n),
                  I(1 if self.method == "prfo" else 0), _p(self.s), _p(self.smag), _p(self.alpha), _p(self.status),
                  _p(active), _p(None), I(width), _p(self.rowmap), _p(self.gperp), _p(self.gam), LL(n * n), I(b),
                  _stream())
         call("sb_axpy", _p(self.x), _p(self.s), _p(self.xnew), I(n), _p(active), I(b), _stream())
         self.skip.zero_()
-        self._spectral_apply(S1, self.up1, 1, active)
+        self._spectral_apply(self.spB, self.s.view(b, 1, n), self.up1, 1, active)
         return True
+
+    def _step_compact(self, active):
+        b, n = self.batch, self.n
+        ready = self._predict_compact(active)
+        # optimize.py:369-371 looks at the lowest `order` eigenvalues of the Hessian itself (Unred = I)
+        call("sb_compact_lowest", _p(self.spB.evals), LL(n), _p(self.spB.mrows), _p(self.lam0), I(n),
+             I(max(1, self.order)), _p(self.lowk), I(b), _stream())
+        call("sb_ev_decide", _p(self.lowk), I(max(1, self.order)), I(1), _p(self.since_diag), _p(self.ev),
+             self._dpar, self._ipar, _p(active), I(b), _stream())
+        self.surface.evaluate(self.xnew, self.fnew, self.gnew, active=active)
+        # rho needs s.(B s): s lives in the free space, where the model's B s is the Hessian's
+        call("sb_kick_finish", _p(self.x), _p(self.f), _p(self.g), _p(self.xnew), _p(self.fnew), _p(self.gnew),
+             _p(self.s), _p(self.up1["BS"]), _p(self.smag), _p(self.dg), _p(self.delta), _p(self.rho),
+             _p(self.nsteps), self._dpar, self._ipar, I(n), _p(active), I(b), _stream())
+        self._update_compact(self.s.view(b, 1, n), self.dg.view(b, 1, n), self.up1, None, 1, active,
+                             bs_ready=ready, abs_ready=ready)
+        # ONE small read per step: does any system re-diagonalise, and how many explicit rows do the
+        # passes have to visit (the bound kept on the host grows by the number of TERMS per update, the
+        # true count by the number of NEW directions, usually half of that)
+        stats = [self.ev.max(), self.spB.mrows.max(), self.spB.mrows.min()]
+        if self.sp is not self.spB:
+            stats += [self.sp.mrows.max(), self.sp.mrows.min()]
+        vals = torch.stack(stats).tolist()
+        nev, self.spB.rb, self.spB.mmin = vals[:3]
+        if self.sp is not self.spB:
+            self.sp.rb, self.sp.mmin = vals[3:]
+        if nev > 0:
+            if self.hessian_function is not None:
+                self._calculate_hessian(self.ev)
+            else:
+                self._diag(self.ev)
 
     # ------------------------------------------------------------------ helpers
     def _eigh(self, active=None):
@@ -686,13 +807,14 @@ class BatchedSella:
         Bnew = 0.5 * (Bnew + Bnew.transpose(1, 2))
         if self.compact:
             # a dense Hessian has no complement left: all n eigenpairs become explicit (rows of Vt)
-            K.eigh(Bnew.contiguous(), active=part, evals=self.evals, Vt=self.Vt, ws=self.eig_ws, status=self.status)
+            sp = self.sp
+            K.eigh(Bnew.contiguous(), active=part, evals=sp.evals, Vt=sp.Vt, ws=self.eig_ws, status=self.status)
             if part is None:
-                self.mrows.fill_(self.n)
-                self._mmin = self.n
+                sp.mrows.fill_(self.n)
+                sp.mmin = self.n
             else:
-                self.mrows.copy_(torch.where(part > 0, torch.full_like(self.mrows, self.n), self.mrows))
-            self._rb = self.n
+                sp.mrows.copy_(torch.where(part > 0, torch.full_like(sp.mrows, self.n), sp.mrows))
+            sp.rb = self.n
             self.H_initialized = True
             self.eig_valid = True
             self._updates_since_refresh = 0
@@ -745,6 +867,10 @@ class BatchedSella:
         call("sb_hvp_finish", _p(vec), LL(vstride), _p(self.gplus), _p(gbase), _p(self.signnorm), D(eta_eff),
              _p(self.AV), _p(self.Vs), _p(self.AVs), I(self.kcap), _p(self.ksz), _p(self.nhist), I(n),
              _p(mask), I(maskval), I(b), _stream())
+        if self.compact and self.fmask is not None:
+            # Uproj^T (H v), linalg.py:92-93: the subspace image lives in the free space (a 0/1 mask here);
+            # the operator history (Vs, AVs) keeps the unprojected product, as the reference does
+            self._mask(self.AV, self.AV, self.kcap)
         if self.cons is not None:
             # Uproj^T (H v): the subspace image lives in the free space (linalg.py:92-93); the
             # operator history (Vs, AVs) keeps the unprojected vector, as the reference does
@@ -786,9 +912,12 @@ class BatchedSella:
         if self.compact:
             if not first:
                 self._refresh_poles(part)          # g_perp of the CURRENT complement (fallback start vector)
-            call("sb_davidson_init_c", _p(v0), _p(self.evals), _p(self.Vt), I(0 if first else 1), _p(self.V),
+            if first and self.fmask is not None:
+                self._mask(self.g.view(b, 1, n), self.gm.view(b, 1, n), 1)
+                v0 = self.gm                       # Ufree^T g (peswrapper.py:524)
+            call("sb_davidson_init_c", _p(v0), _p(self.sp.evals), _p(self.sp.Vt), I(0 if first else 1), _p(self.V),
                  I(kc), I(n), _p(self.ksz), _p(self.ninit), _p(self.nhist), _p(self.dav_state), _p(self.status),
-                 _p(part), _p(self.mrows), _p(self.lam0), _p(self.gperp), LL(n), LL(n * n), I(b), _stream())
+                 _p(part), _p(self.sp.mrows), _p(self.lam0), _p(self.gperp), LL(n), LL(n * n), I(b), _stream())
         else:
             call("sb_davidson_init", _p(v0), _p(self.evals), _p(self.Vt), I(0 if first else 1), _p(self.V),
                  I(kc), I(n), _p(self.ksz), _p(self.ninit), _p(self.nhist), _p(self.dav_state), _p(self.status),
@@ -811,11 +940,11 @@ class BatchedSella:
                 tin = None
             elif self.compact:
                 # (P - theta)^-1 through the compact spectrum: explicit rows + the complement's 1/(lam0 - theta)
-                self._hvr(self.rv, self.rvhat, 2, active=m)
-                call("sb_compact_jd_coeff", _p(self.rvhat), _p(self.rv), _p(self.evals), LL(n), _p(self.mrows),
-                     _p(self.lam0), _p(self.theta), I(n), I(self._rb), I(self.eigensolver), _p(self.that),
+                self._hvr(self.sp, self.rv, self.rvhat, 2, active=m)
+                call("sb_compact_jd_coeff", _p(self.rvhat), _p(self.rv), _p(self.sp.evals), LL(n), _p(self.sp.mrows),
+                     _p(self.lam0), _p(self.theta), I(n), I(self.sp.rb), I(self.eigensolver), _p(self.that),
                      _p(self.jd_ed), _p(self.dav_state), I(b), _stream())
-                self._hvr(self.that.view(b, 1, n), self.t.view(b, 1, n), 1, transposed=True, active=m)
+                self._hvr(self.sp, self.that.view(b, 1, n), self.t.view(b, 1, n), 1, transposed=True, active=m)
                 call("sb_compact_jd_finish", _p(self.t), _p(self.rv), _p(self.jd_ed), I(n), I(self.eigensolver),
                      _p(self.dav_state), I(b), _stream())
                 tin = self.t
@@ -870,25 +999,7 @@ class BatchedSella:
             # stepper.py:76-80) until the first update scales it (hessian_update.py:58-67)
             self._identity_model()
         if self.compact:
-            abs_ready = self._predict_compact(active)
-            call("sb_ev_decide", _p(self.cev), I(min(n, self._rb + 1)), I(1), _p(self.since_diag), _p(self.ev),
-                 self._dpar, self._ipar, _p(active), I(b), _stream())
-            self.surface.evaluate(self.xnew, self.fnew, self.gnew, active=active)
-            call("sb_kick_finish", _p(self.x), _p(self.f), _p(self.g), _p(self.xnew), _p(self.fnew), _p(self.gnew),
-                 _p(self.s), _p(self.up1["BS"]), _p(self.smag), _p(self.dg), _p(self.delta), _p(self.rho),
-                 _p(self.nsteps), self._dpar, self._ipar, I(n), _p(active), I(b), _stream())
-            self._update_compact(self.s.view(b, 1, n), self.dg.view(b, 1, n), self.up1, None, 1, active,
-                                 bs_ready=True, abs_ready=abs_ready)
-            # ONE small read per step: does any system re-diagonalise, and how many explicit rows do the
-            # passes have to visit (the bound kept on the host grows by the number of TERMS per update, the
-            # true count by the number of NEW directions, usually half of that)
-            nev, self._rb, self._mmin = torch.stack((self.ev.max(), self.mrows.max(), self.mrows.min())).tolist()
-            if nev > 0:
-                if self.hessian_function is not None:
-                    self._calculate_hessian(self.ev)
-                else:
-                    self._diag(self.ev)
-            return
+            return self._step_compact(active)
         cn = self.cons
         nl = cn.get("nl") if cn is not None else None
         if nl is not None:
@@ -984,7 +1095,11 @@ class BatchedSella:
         b, n = self.batch, self.n
         cn = self.cons
         if cn is None:
-            call("sb_converged", _p(self.g), I(n), D(float(fmax)), _p(self.fmax), _p(self.conv), I(b), _stream())
+            gsrc = self.g
+            if self.compact and self.fmask is not None:
+                self._mask(self.g.view(b, 1, n), self.gm.view(b, 1, n), 1)      # |P_f g| per atom
+                gsrc = self.gm
+            call("sb_converged", _p(gsrc), I(n), D(float(fmax)), _p(self.fmax), _p(self.conv), I(b), _stream())
             return self.conv
         if "nl" in cn and (cn["nl"]["x_basis"] is None or not torch.equal(cn["nl"]["x_basis"], self.x)):
             self._refresh_bases()
@@ -1002,8 +1117,8 @@ class BatchedSella:
             return torch.ones(self.batch, dtype=torch.float64, device=self.dev)
         if self.compact:
             out = torch.empty(self.batch, dtype=torch.float64, device=self.dev)
-            call("sb_compact_lowest", _p(self.evals), LL(self.n), _p(self.mrows), _p(self.lam0), I(self.n), _p(out),
-                 I(self.batch), _stream())
+            call("sb_compact_lowest", _p(self.spB.evals), LL(self.n), _p(self.spB.mrows), _p(self.lam0), I(self.n),
+                 I(1), _p(out), I(self.batch), _stream())
             return out
         if not self.eig_valid:
             self._eigh(None)
@@ -1014,8 +1129,9 @@ class BatchedSella:
         """(theta [m], VR [m, n], lam0, m) of system i as numpy arrays: the explicit eigenpairs of its
         approximate Hessian; every other eigenvalue equals lam0 (dense representation: m = n)."""
         if self.compact:
-            m = int(self.mrows[i])
-            return (self.evals[i, :m].cpu().numpy(), self.Vt[i, :m].cpu().numpy(), float(self.lam0[i]), m)
+            sp = self.spB
+            m = int(sp.mrows[i])
+            return (sp.evals[i, :m].cpu().numpy(), sp.Vt[i, :m].cpu().numpy(), float(self.lam0[i]), m)
         if not self.eig_valid:
             self._eigh(None)
             self.eig_valid = True
@@ -1023,7 +1139,7 @@ class BatchedSella:
 
     def rank_bound(self):
         """Upper bound (host-side count) on the number of distinct non-cluster eigenpairs of the model."""
-        return self._rb if self.compact else self.n
+        return self.spB.rb if self.compact else self.n
 
     def check_status(self):
         st = self.status.cpu().numpy()

@@ -73,7 +73,7 @@ extern "C" int sb_hv_rect_impl(const double*, long long, int, const double*, dou
                                int, cudaStream_t);
 extern "C" int sb_secular_update_c_impl(double*, double*, double*, int, const double*, const int*, int, double*,
                                         double*, int*, const int*, const int*, int, long long, long long, int,
-                                        cudaStream_t);
+                                        cudaStream_t, int, int*);
 extern "C" int sb_qn_ras_c_impl(const double*, const double*, const double*, const double*, int, int, double*,
                                 double*, double*, int*, const int*, const double*, int, const int*, const double*,
                                 const double*, long long, int, cudaStream_t);
@@ -321,11 +321,11 @@ int sb_secular_update(double* evals, double* Vt, double* Z, int zcap, const doub
 }
 int sb_secular_update_c(double* evals, double* Vt, double* Z, int zcap, const double* sig, const int32_t* nterm,
                         int n, double* work, double* qwork, int32_t* status, const int32_t* skip,
-                        const int32_t* mrows, int mcap, long long estride, long long vstride, int batch,
-                        void* stream) {
+                        const int32_t* mrows, int mcap, long long estride, long long vstride, int nterm_max,
+                        int32_t* aux, int batch, void* stream) {
     if (!mrows || mcap < 0) return -1;
     return sb_secular_update_c_impl(evals, Vt, Z, zcap, sig, nterm, n, work, qwork, status, skip, mrows, mcap,
-                                    estride, vstride, batch, ST);
+                                    estride, vstride, batch, ST, nterm_max, aux);
 }
 int sb_qn_ras_c(const double* Vg, const double* evals, const double* Vt, const double* delta, int order, int n,
                 double* s, double* smag, double* alpha, int32_t* status, const int32_t* active, const double* sadd,

@@ -340,15 +340,31 @@ __global__ void jd_finish_kernel(double* __restrict__ t, const double* __restric
     t[(size_t)b * n + i] += method == 1 ? r * inv0 : (eps * v - r) * inv0;
 }
 
-// lowest eigenvalue of B per system: min(theta_0, lam0 if m < n)
+// the k lowest eigenvalues of B per system (ascending): the explicit theta merged with lam0 (multiplicity n - m)
 __global__ void lowest_kernel(const double* __restrict__ evals_, long long estride, const int* __restrict__ mrows,
-                              const double* __restrict__ lam0, int n, double* __restrict__ out, int batch) {
+                              const double* __restrict__ lam0, int n, int k, double* __restrict__ out, int batch) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
     const int m = mrows[b];
-    double v = lam0[b];
-    if (m > 0) { const double t0 = evals_[(size_t)b * estride]; v = (m < n) ? fmin(t0, v) : t0; }
-    out[b] = v;
+    const double l0 = lam0[b];
+    int i = 0, c = n - m;            // next explicit index, copies of lam0 left
+    for (int j = 0; j < k; ++j) {
+        double v;
+        if (i < m && (c == 0 || evals_[(size_t)b * estride + i] <= l0)) v = evals_[(size_t)b * estride + i++];
+        else if (c > 0) { v = l0; --c; }
+        else v = l0;                 // k > n
+        out[(size_t)b * k + j] = v;
+    }
+}
+
+// out[b,v,:] = mask[:] * X[b,v,:]  for v < nv  (projection onto the free Cartesian coordinates)
+__global__ void mask_kernel(const double* __restrict__ X, const double* __restrict__ mask, double* __restrict__ out,
+                            int ld, int nv, int n) {
+    const int b = blockIdx.y;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)nv * n) return;
+    const size_t o = (size_t)b * ld * n + idx;
+    out[o] = X[o] * mask[idx % n];
 }
 
 }  // namespace
@@ -445,9 +461,18 @@ int sb_compact_jd_finish(double* t, const double* rv, const double* ed, int n, i
 }
 
 int sb_compact_lowest(const double* evals, long long estride, const int32_t* mrows, const double* lam0, int n,
-                      double* out, int batch, void* stream) {
+                      int k, double* out, int batch, void* stream) {
+    if (k < 1) return -1;
     SB_COUNT(1);
-    lowest_kernel<<<(batch + 127) / 128, 128, 0, ST>>>(evals, estride, mrows, lam0, n, out, batch);
+    lowest_kernel<<<(batch + 127) / 128, 128, 0, ST>>>(evals, estride, mrows, lam0, n, k, out, batch);
+    return SB_LAUNCH_CHECK();
+}
+
+int sb_mask_vec(const double* X, const double* mask, double* out, int ldv, int nvec, int n, int batch, void* stream) {
+    if (nvec < 1 || nvec > ldv || n < 1 || batch < 1) return -1;
+    dim3 grid((unsigned)(((size_t)nvec * n + 255) / 256), batch);
+    SB_COUNT(1);
+    mask_kernel<<<grid, 256, 0, ST>>>(X, mask, out, ldv, nvec, n);
     return SB_LAUNCH_CHECK();
 }
 

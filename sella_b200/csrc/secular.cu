@@ -534,7 +534,12 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
                       const double* __restrict__ sig_, const int* __restrict__ nterm, int n,
                       double* __restrict__ work_, double* __restrict__ qwork_, int* __restrict__ status,
                       const int* __restrict__ skip, int tile_doubles, const int* __restrict__ mrows, int mc,
-                      long long estride, long long vstride) {
+                      long long estride, long long vstride, int t_only, int* __restrict__ aux_, int auxs) {
+    // t_only == -1: the whole update in this launch (all terms, rotation of the rows included, final sort).
+    // Split mode (compact representation): t_only >= 0 processes term t_only only -- deflation, secular roots,
+    // Qh into qwork, the row map and r into aux -- and leaves the rotation of the rows (a batched GEMM) to
+    // secular_apply_kernel / secular_copyback_kernel; the eigenvalues stay in ROW order in evals between
+    // launches.  t_only == -2: only the final sort + row permutation.
     // m = number of (explicit) eigenpairs = rows of Vt that take part; mc >= m sizes the shared arrays;
     // n = length of a row.  Dense representation: m = mc = n, estride = n, vstride = n*n.
     const int b = blockIdx.x;
@@ -566,6 +571,8 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
     double* Qh = qwork_ + (size_t)b * vstride;
 
     long long tmark_ = clock64();
+    int* aux = aux_ ? aux_ + (size_t)b * auxs : nullptr;
+    if (t_only >= 0 && tid == 0) aux[0] = 0;
     for (int i = tid; i < m; i += nt) { d[i] = evals_[(size_t)b * estride + i]; ord[i] = i; }   // dense: sorted on entry
     __syncthreads();
     if (mrows) {
@@ -579,7 +586,9 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
         __syncthreads();
     }
 
-    for (int t = 0; t < nterms; ++t) {
+    const int t_begin = t_only >= 0 ? t_only : 0;
+    const int t_end = t_only >= 0 ? min(t_only + 1, nterms) : (t_only == -2 ? 0 : nterms);
+    for (int t = t_begin; t < t_end; ++t) {
         double* zt = Z + (size_t)t * n;
         double acc = 0.0;
         for (int i = tid; i < m; i += nt) { const double v = zt[i]; z[i] = v; acc = fma(v, v, acc); }
@@ -833,7 +842,7 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
         }
         __syncthreads();
         // eigenvector matrix (mirrored index space): Qh[i*r + j] = zh_i / (dd_i - lam_j), columns normalised
-        const bool qsmem = r <= SEC_QS_MAX && (size_t)r * r <= (size_t)tile_doubles;
+        const bool qsmem = t_only < 0 && r <= SEC_QS_MAX && (size_t)r * r <= (size_t)tile_doubles;
         if (qsmem) Qh = tile;
         else Qh = qwork_ + (size_t)b * vstride;
         for (int idx = tid; idx < r * r; idx += nt) {
@@ -853,6 +862,11 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
         // ---------------- new eigenvectors: row_new(j) = sum_i Qh[i][j] row_old(i)   (mirrored index i,j)
         {
             auto rowof = [&](int i) { return neg ? nd[r - 1 - i] : nd[i]; };
+            if (t_only >= 0) {
+                // split mode: hand (r, row map, Qh) to the GEMM kernels
+                for (int i = tid; i < r; i += nt) aux[4 + i] = rowof(i);
+                if (tid == 0) aux[0] = r;
+            } else {
             // out[j][col] = sum_i Qh[i][j] old[rowof(i)][col], column chunks staged in smem
             {
                 // warps own blocks of 8 new rows, lanes own 4 columns of a 128-column chunk; old rows
@@ -917,6 +931,7 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
                 const int j = idx / n, col = idx % n;
                 Vt[(size_t)rowof(j) * n + col] = work[(size_t)j * n + col];
             }
+            }
             SEC_MARK(5);
             // pending z vectors: z_s[row(j)] <- sum_i Qh[i][j] z_s[row(i)]
             for (int s2 = t + 1; s2 < nterms; ++s2) {
@@ -949,6 +964,10 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
         __syncthreads();
     }
     SEC_MARK(7);
+    if (t_only >= 0) {
+        for (int i = tid; i < m; i += nt) evals_[(size_t)b * estride + i] = d[i];      // row order, until the final sort
+        return;
+    }
     // ---------------- write back: evals ascending, rows of Vt permuted (new[p] = old[ord[p]])
     // Rows with equal eigenvalues are interchangeable: a row that already sits in a slot
     // whose sorted value equals its own eigenvalue stays put, only the others are matched
@@ -1013,6 +1032,132 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
     (void)status;
 }
 
+// ------------------------------------------------------------------------------
+// Rotation of the eigenvector rows of one rank-one term (split mode), a batched GEMM on the fp64
+// tensor-core path (DMMA m8n8k4):
+//     work[j][c] = sum_i Qh[i][j] * Vt[rowmap[i]][c],   j < r, c < n        (r, rowmap, Qh per system)
+// 64 x 64 output tiles, K blocks of 16 staged through a 3-deep cp.async ring (8-byte copies: Qh rows
+// start at arbitrary offsets), 8 warps of 16 x 32, padded shared tiles (row stride 68 doubles: the
+// fragment reads of a half warp fall into 16 different bank pairs).
+constexpr int AP_BM = 64, AP_BN = 64, AP_BK = 16, AP_THREADS = 256, AP_LD = 68, AP_STAGES = 3;
+
+__device__ __forceinline__ void sec_dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void sec_cp8(double* dst, const double* src, bool valid) {
+    const int sz = valid ? 8 : 0;                        // src-size 0: the 8 bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sb_smem_u32(dst)), "l"(src), "r"(sz) : "memory");
+}
+
+__global__ void __launch_bounds__(AP_THREADS)
+secular_apply_kernel(const double* __restrict__ Vt_, const double* __restrict__ qwork_, double* __restrict__ work_,
+                     const int* __restrict__ aux_, int auxs, int n, long long vstride, const int* __restrict__ skip) {
+    const int b = blockIdx.z;
+    if (skip && skip[b]) return;
+    const int* aux = aux_ + (size_t)b * auxs;
+    const int r = aux[0];
+    const int m0 = blockIdx.y * AP_BM, n0 = blockIdx.x * AP_BN;
+    if (m0 >= r) return;
+    extern __shared__ double sm[];
+    double* As = sm;                                              // [STAGES][BK][LD]   As[k][j]
+    double* Bs = sm + (size_t)AP_STAGES * AP_BK * AP_LD;          // [STAGES][BK][LD]   Bs[k][c]
+    const double* Vt = Vt_ + (size_t)b * vstride;
+    const double* Qh = qwork_ + (size_t)b * vstride;
+    double* work = work_ + (size_t)b * vstride;
+    const int* rowmap = aux + 4;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = (warp >> 1) * 16, wn = (warp & 1) * 32;
+    const int gid = lane >> 2, tig = lane & 3;
+    double acc[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    const int nk = (r + AP_BK - 1) / AP_BK;
+    auto stage = [&](int kb, int slot) {
+        const int k0 = kb * AP_BK;
+        double* as = As + (size_t)slot * AP_BK * AP_LD;
+        double* bs = Bs + (size_t)slot * AP_BK * AP_LD;
+#pragma unroll
+        for (int e = tid; e < AP_BK * AP_BM; e += AP_THREADS) {
+            const int kk = e / AP_BM, mm = e % AP_BM;
+            const int gk = k0 + kk, gm = m0 + mm;
+            const bool ok = gk < r && gm < r;
+            sec_cp8(as + kk * AP_LD + mm, Qh + (ok ? (size_t)gk * r + gm : 0), ok);
+        }
+#pragma unroll
+        for (int e = tid; e < AP_BK * AP_BN; e += AP_THREADS) {
+            const int kk = e / AP_BN, nn = e % AP_BN;
+            const int gk = k0 + kk, gn = n0 + nn;
+            const bool ok = gk < r && gn < n;
+            sec_cp8(bs + kk * AP_LD + nn, Vt + (ok ? (size_t)rowmap[gk] * n + gn : 0), ok);
+        }
+    };
+#pragma unroll
+    for (int p = 0; p < AP_STAGES - 1; ++p) {
+        if (p < nk) stage(p, p);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int kb = 0; kb < nk; ++kb) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(AP_STAGES - 2) : "memory");
+        __syncthreads();
+        {
+            const int nxt = kb + AP_STAGES - 1;
+            if (nxt < nk) stage(nxt, nxt % AP_STAGES);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        const double* as = As + (size_t)(kb % AP_STAGES) * AP_BK * AP_LD;
+        const double* bs = Bs + (size_t)(kb % AP_STAGES) * AP_BK * AP_LD;
+#pragma unroll
+        for (int ks = 0; ks < AP_BK; ks += 4) {
+            double af[2], bf[4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) af[i] = as[(ks + tig) * AP_LD + wm + 8 * i + gid];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = bs[(ks + tig) * AP_LD + wn + 8 * j + gid];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sec_dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gm = m0 + wm + 8 * i + gid, gn = n0 + wn + 8 * j + 2 * tig;
+            if (gm < r) {
+                if (gn + 1 < n && !(n & 1)) *reinterpret_cast<double2*>(work + (size_t)gm * n + gn) = make_double2(acc[i][j][0], acc[i][j][1]);
+                else {
+                    if (gn < n) work[(size_t)gm * n + gn] = acc[i][j][0];
+                    if (gn + 1 < n) work[(size_t)gm * n + gn + 1] = acc[i][j][1];
+                }
+            }
+        }
+}
+
+// Vt[rowmap[j]][:] = work[j][:] for j < r  (warp per row)
+__global__ void secular_copyback_kernel(double* __restrict__ Vt_, const double* __restrict__ work_,
+                                        const int* __restrict__ aux_, int auxs, int n, long long vstride,
+                                        const int* __restrict__ skip) {
+    const int b = blockIdx.y;
+    if (skip && skip[b]) return;
+    const int* aux = aux_ + (size_t)b * auxs;
+    const int r = aux[0];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int j = blockIdx.x * nw + warp;
+    if (j >= r) return;
+    const double* src = work_ + (size_t)b * vstride + (size_t)j * n;
+    double* dst = Vt_ + (size_t)b * vstride + (size_t)aux[4 + j] * n;
+    if (!(n & 1)) {
+        for (int c = lane; c < (n >> 1); c += 32) reinterpret_cast<double2*>(dst)[c] = reinterpret_cast<const double2*>(src)[c];
+    } else {
+        for (int c = lane; c < n; c += 32) dst[c] = src[c];
+    }
+}
+
 }  // namespace
 
 extern "C" int sb_secular_profile_impl(unsigned long long* out16, int reset) {
@@ -1057,7 +1202,7 @@ extern "C" int sb_secular_timing_impl(float* out3, int enable) {
 extern "C" int sb_secular_update_c_impl(double* evals, double* Vt, double* Z, int zcap, const double* sig,
                                         const int* nterm, int n, double* work, double* qwork, int* status,
                                         const int* skip, const int* mrows, int mcap, long long estride,
-                                        long long vstride, int batch, cudaStream_t st) {
+                                        long long vstride, int batch, cudaStream_t st, int nterm_max, int* aux) {
     const int mc = mrows ? (mcap < 1 ? 1 : (mcap > n ? n : mcap)) : n;
     const size_t base = (size_t)mc * (8 * sizeof(double) + 5 * sizeof(int)) + sizeof(SecShared) + 64;
     int dev = 0, optin = 0;
@@ -1093,16 +1238,38 @@ extern "C" int sb_secular_update_c_impl(double* evals, double* Vt, double* Z, in
     SB_COUNT(1);
     const long long es = mrows ? estride : (long long)n;
     const long long vs = mrows ? vstride : (long long)n * n;
-#define SB_SEC_LAUNCH(C)                                                                                          \
+    const int auxs = mc + 4;
+#define SB_SEC_LAUNCH(C, TONLY)                                                                                   \
     cudaFuncSetAttribute(secular_update_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
     secular_update_kernel<C><<<batch, SECK_THREADS, smem, st>>>(evals, Vt, Z, zcap, sig, nterm, n, work, qwork,  \
-                                                               status, skip, tile_doubles, mrows, mc, es, vs)
-    if (cpt <= 1) { SB_SEC_LAUNCH(1); }
-    else if (cpt <= 2) { SB_SEC_LAUNCH(2); }
-    else if (cpt <= 4) { SB_SEC_LAUNCH(4); }
-    else if (cpt <= 8) { SB_SEC_LAUNCH(8); }
-    else if (cpt <= 16) { SB_SEC_LAUNCH(16); }
+                                                               status, skip, tile_doubles, mrows, mc, es, vs,    \
+                                                               TONLY, aux, auxs)
+#define SB_SEC_DISPATCH(TONLY)                          \
+    if (cpt <= 1) { SB_SEC_LAUNCH(1, TONLY); }          \
+    else if (cpt <= 2) { SB_SEC_LAUNCH(2, TONLY); }     \
+    else if (cpt <= 4) { SB_SEC_LAUNCH(4, TONLY); }     \
+    else if (cpt <= 8) { SB_SEC_LAUNCH(8, TONLY); }     \
+    else if (cpt <= 16) { SB_SEC_LAUNCH(16, TONLY); }   \
     else return -2;
+    if (mrows && aux && nterm_max > 0) {
+        // split mode: per term one solve launch (CTA per system), the rotation of the rows as a batched
+        // DMMA GEMM over the whole GPU and the copy back; the final sort + row permutation last
+        const size_t apsm = (size_t)2 * AP_STAGES * AP_BK * AP_LD * sizeof(double);
+        cudaFuncSetAttribute(secular_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apsm);
+        const int tmax = nterm_max < zcap ? nterm_max : zcap;
+        for (int t = 0; t < tmax; ++t) {
+            SB_COUNT(3);
+            SB_SEC_DISPATCH(t)
+            dim3 ga((n + AP_BN - 1) / AP_BN, (mc + AP_BM - 1) / AP_BM, batch);
+            secular_apply_kernel<<<ga, AP_THREADS, apsm, st>>>(Vt, qwork, work, aux, auxs, n, vs, skip);
+            dim3 gc((mc + 7) / 8, batch);
+            secular_copyback_kernel<<<gc, 256, 0, st>>>(Vt, work, aux, auxs, n, vs, skip);
+        }
+        SB_SEC_DISPATCH(-2)
+    } else {
+        SB_SEC_DISPATCH(-1)
+    }
+#undef SB_SEC_DISPATCH
 #undef SB_SEC_LAUNCH
     if (sec_timing_on) cudaEventRecord(sec_ev[3], st);
     return SB_LAUNCH_CHECK();
@@ -1112,5 +1279,5 @@ extern "C" int sb_secular_update_impl(double* evals, double* Vt, double* Z, int 
                                       const int* nterm, int n, double* work, double* qwork, int* status,
                                       const int* skip, int batch, cudaStream_t st) {
     return sb_secular_update_c_impl(evals, Vt, Z, zcap, sig, nterm, n, work, qwork, status, skip, nullptr, n, n,
-                                    (long long)n * n, batch, st);
+                                    (long long)n * n, batch, st, 0, nullptr);
 }
