@@ -34,6 +34,7 @@ namespace {
 constexpr int CP_THREADS = 256;
 constexpr double CP_EPS = 2.220446049250313e-16;
 constexpr int CP_TMAX = 32;            // rank-one terms per update (2 * kcap, kcap <= 16)
+constexpr double CP_DROP = 4.0e-13;    // smallest out-of-span remainder of a unit update vector that is kept
 
 // dots[j] = basis_j . xs for j < cnt (warp per basis vector), then xs -= sum_j dots[j] basis_j
 __device__ void cgs_sweep(double* xs, int n, const double* __restrict__ basis, size_t bstride, int cnt, double* dots) {
@@ -81,8 +82,11 @@ append_a_kernel(const double* __restrict__ P_, const double* __restrict__ W1_, i
             double acc = 0.0;
             for (int e = tid; e < n; e += nt) acc = fma(xs[e], xs[e], acc);
             const double nrm = sqrt(sb_block_sum(acc, scratch));
-            // p_t has unit length: a remainder this small carries no information (and no weight)
-            if (!(nrm > 64.0 * CP_EPS) || cnt >= n - m) continue;
+            // p_t has unit length and p_perp carries an absolute error of a few eps (plus the orthogonality
+            // defect of VR): a remainder below ~2000 eps is noise.  Kept, it would become a unit vector with
+            // O(1) components inside span(VR) and pollute every later candidate through its projection;
+            // dropped, at most |sigma| * 4e-13 of the update is lost.
+            if (!(nrm > CP_DROP) || cnt >= n - m) continue;
             const double inv = 1.0 / nrm;
             for (int e = tid; e < n; e += nt) Qc[(size_t)cnt * n + e] = xs[e] * inv;
             ++cnt;

@@ -34,7 +34,7 @@ class CompactSpectrum:
         return f(self.lam0) * x + self.VR.T @ ((f(self.theta) - f(self.lam0)) * c)
 
     # ------------------------------------------------------------------ eigen-update
-    def update(self, P, sig, drop_tol=64 * 2.3e-16):
+    def update(self, P, sig, drop_tol=4e-13):
         """B <- B + sum_t sig_t p_t p_t^T with orthonormal rows p_t of P [T, n].
         kernels: hv (Z = VR P^T), hvt (W = VR^T Z), append_a (p_perp, MGS among the candidates), hv + hvt
         again on the unit candidates, append_b (final MGS, rows appended with eigenvalue lam0, their
