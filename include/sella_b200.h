@@ -376,6 +376,22 @@ int sb_davidson_init_c(const double* v0, const double* pl, const double* Pvt, in
                        const int32_t* part, const int32_t* mrows, const double* lam0, const double* gperp,
                        long long estride, long long vstride, int batch, void* stream);
 
+/* diagnostic: average milliseconds (HOST float) of `reps` launches of the rotation GEMM of sb_secular_update_c's
+ * split mode (work[j,:] = sum_i Qh[i,j] Vt[i,:], r rows per system, 2 r^2 n flops per system); aux: int32
+ * [batch, r + 4] scratch.  Synchronises. */
+int sb_secular_apply_bench(const double* Vt, const double* qwork, double* work, int32_t* aux, int r, int n,
+                           long long vstride, int batch, int reps, float* ms_host, void* stream);
+
+/* diagnostic: measured fp64 throughput of the device in TFLOP/s (HOST double), kind 0 = DFMA pipe, 1 = DMMA
+ * (mma.sync m8n8k4 f64) tensor path; scratch: sms * ctas_per_sm * 256 doubles of device memory.  The
+ * denominator of the compute rooflines in bench.py (MEASURED_PEAKS.json has no fp64 figure).  Synchronises. */
+int sb_fp64_peak(int kind, int iters, int ctas_per_sm, double* scratch, double* tflops_host);
+
+/* M[b] <- scale * M[b] + diag * I (n x n, in place): the identity step model on the free space of
+ * position-dependent constraints, Bp = P_f + sigma P_c = I + (sigma - 1) Ucons Ucons^T (the projected
+ * Hessian of an uninitialised ApproximateHessian is None, sella/peswrapper.py:363-386, sella/linalg.py:306-317) */
+int sb_add_scaled_identity(double* M, double scale, double diag, int n, int batch, void* stream);
+
 /* ---- per-step bookkeeping (sella/peswrapper.py:578-602, optimize/optimize.py:362-434) ----
  * dpar = {rho_inc, rho_dec, sigma_inc, sigma_dec, delta_min} (host array of 5 doubles),
  * ipar = {order, eig, nsteps_per_diag, diag_every_n(<0: never)} (host array of 4 ints). */

@@ -22,4 +22,4 @@ for t in range(26):
         tot = sum(out[:9]) or 1
         print("step %2d diag %d rows %d..%d total %.3f Mcyc/system  " % (t, eng.ndiag - nd0, int(eng.mrows.min()), int(eng.mrows.max()), tot / b / 1e6)
               + "  ".join("%s %.0f%%" % (nm, 100 * out[i] / tot) for i, nm in enumerate(names))
-              + "   moved rows/CTA %.1f" % (out[9] / max(1, out[10])), flush=True)
+              + "   secular iterations/root %.1f (roots/system %.1f) max %d, >=8: %d, >=20: %d" % (out[14] / max(1, out[15]), out[15] / b, out[13], out[12], out[11]), flush=True)

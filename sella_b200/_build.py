@@ -16,7 +16,7 @@ LIB = os.path.join(CSRC, "libsella_b200.so")
 OBJDIR = os.path.join(CSRC, "_build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC"]
+         "-Xcompiler", "-fPIC"] + os.environ.get("SB_NVCC_EXTRA", "").split()
 
 
 def sources():

@@ -399,6 +399,12 @@ class BatchedSella:
         self._refresh_bases()
         nl["Hc"] = nl["ints"].ldot(self.x, nl["Lmul"][:, nlin:].contiguous())
         if not self.H_initialized:
+            # B is None in the reference: the projected Lagrangian Hessian is None as well (peswrapper.py:363-
+            # 386 skips Hc then), i.e. the step model is the identity on the free space (stepper.py:76-80):
+            # Bp = P_f + sigma P_c at the current geometry
+            Pc = K.gemm(cn["Uc"], cn["Uc"], transA=True)
+            call("sb_add_scaled_identity", _p(Pc), D(7.0), D(1.0), I(n), I(b), _stream())      # I + 7 Pc, in place
+            K.eigh(Pc, evals=self.evals, Vt=self.Vt, ws=self.eig_ws, status=self.status)
             return
         torch.sub(self._B, nl["Hc"], out=nl["HL"])
         if self._projected_spectrum_by_update():
@@ -480,7 +486,8 @@ class BatchedSella:
         if self.cons is not None:
             cn = self.cons
             if "nl" in cn:
-                raise NotImplementedError("eig=False starts with position-dependent constraints are not batched yet")
+                self.eig_valid = True          # the model spectrum is rebuilt per geometry (_refresh_constraints)
+                return
             self.Vt.copy_(cn["Q"].expand(b, n, n) if cn["shared"] else cn["Q"])
             self.evals.fill_(1.0)
             self.evals[:, cn["nfree"]:] = 8.0
@@ -926,7 +933,10 @@ class BatchedSella:
         for j in range(nstart):
             m = ((self.dav_state == DAV_EXPAND) & (self.ninit > j)).to(torch.int32)
             self._hvp(self.V[:, j], kc * n, m, 1, m)
-        maxiter_eff = n if self.diag_maxiter is None else min(n, int(self.diag_maxiter))
+        # rayleigh_ritz stops at min(n, maxiter) vectors with n the dimension of the FREE space
+        # (eigensolvers.py:31-66: A is the projected operator of peswrapper.py:531-537)
+        nfree = self.cons["nfree"] if self.cons is not None else (self.nfree if getattr(self, "fmask", None) is not None else n)
+        maxiter_eff = nfree if self.diag_maxiter is None else min(nfree, int(self.diag_maxiter))
         rounds = nstart
         while True:
             call("sb_davidson_rr", _p(self.V), _p(self.AV), I(kc), _p(self.ksz), I(n), D(self.gamma),
@@ -1131,7 +1141,9 @@ class BatchedSella:
         if self.compact:
             sp = self.spB
             m = int(sp.mrows[i])
-            return (sp.evals[i, :m].cpu().numpy(), sp.Vt[i, :m].cpu().numpy(), float(self.lam0[i]), m)
+            th, VR = sp.evals[i, :m].cpu().numpy(), sp.Vt[i, :m].cpu().numpy()
+            order = np.argsort(th, kind="stable")            # the explicit pairs are stored in any order
+            return th[order], VR[order], float(self.lam0[i]), m
         if not self.eig_valid:
             self._eigh(None)
             self.eig_valid = True

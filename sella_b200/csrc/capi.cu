@@ -109,11 +109,43 @@ __global__ void dot_kernel(const double* __restrict__ x, const double* __restric
     if (threadIdx.x == 0) f[b] = scale * acc;
 }
 
+// M[b] <- scale * M[b] + diag * I
+__global__ void add_scaled_identity_kernel(double* __restrict__ M, double scale, double diag, int n) {
+    const int b = blockIdx.y;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * n) return;
+    const int i = (int)(idx / n), j = (int)(idx % n);
+    double* p = M + (size_t)b * n * n + idx;
+    *p = scale * *p + (i == j ? diag : 0.0);
+}
+
 }  // namespace
 
 extern "C" {
 
-int sb_version(void) { return 1; }
+int sb_version(void) { return 2; }
+
+extern "C" int sb_secular_apply_bench_impl(const double*, const double*, double*, int*, int, int, long long, int, int,
+                                           float*, cudaStream_t);
+int sb_secular_apply_bench(const double* Vt, const double* qwork, double* work, int32_t* aux, int r, int n,
+                           long long vstride, int batch, int reps, float* ms_host, void* stream) {
+    if (r < 1 || r > n || (long long)r * n > vstride || reps < 1 || !ms_host) return -1;
+    return sb_secular_apply_bench_impl(Vt, qwork, work, aux, r, n, vstride, batch, reps, ms_host,
+                                       (cudaStream_t)stream);
+}
+extern "C" int sb_fp64_peak_impl(int, int, int, double*, double*);
+int sb_fp64_peak(int kind, int iters, int ctas_per_sm, double* scratch, double* tflops_host) {
+    if (kind < 0 || kind > 1 || iters < 1 || ctas_per_sm < 1 || !scratch || !tflops_host) return -1;
+    return sb_fp64_peak_impl(kind, iters, ctas_per_sm, scratch, tflops_host);
+}
+
+int sb_add_scaled_identity(double* M, double scale, double diag, int n, int batch, void* stream) {
+    if (n < 1 || batch < 1) return -1;
+    dim3 grid((unsigned)(((size_t)n * n + 255) / 256), batch);
+    SB_COUNT(1);
+    add_scaled_identity_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(M, scale, diag, n);
+    return SB_LAUNCH_CHECK();
+}
 
 long long sb_launch_count(void) { return sb_launch_counter; }
 

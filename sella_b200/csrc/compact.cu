@@ -154,7 +154,8 @@ append_b_kernel(const double* __restrict__ P_, const double* __restrict__ Qc_, c
 // Merged ascending pole list for the restricted-step kernels (width entries per system, stride
 // width): explicit eigenvalues with coefficients Vg = VR g; if m < n the complement as ONE pole lam0
 // with coefficient |g_perp| at its sorted position, followed by zero-weight copies of lam0 as padding.
-// rowmap: explicit row index, -1 = complement pole, -2 = padding.
+// rowmap: explicit row index, -1 = complement pole, -2 = padding.  The explicit pairs may be stored in
+// any order (evals[i] belongs to row i): they are ranked here.
 __global__ void __launch_bounds__(CP_THREADS)
 prepare_kernel(const double* __restrict__ g_, const double* __restrict__ Vg_, const double* __restrict__ Wg_,
                const double* __restrict__ evals_, long long estride, const int* __restrict__ mrows,
@@ -163,12 +164,12 @@ prepare_kernel(const double* __restrict__ g_, const double* __restrict__ Vg_, co
                const int* __restrict__ active) {
     const int b = blockIdx.x;
     if (active && !active[b]) return;
+    extern __shared__ double evs[];                 // width doubles
     __shared__ double scratch[SB_SCRATCH_DOUBLES];
     __shared__ int spos;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int m = min(mrows[b], width);
     const double l0 = lam0[b];
-    const double* ev = evals_ + (size_t)b * estride;
     const bool cluster = m < n;
     double acc = 0.0;
     for (int e = tid; e < n; e += nt) {
@@ -178,25 +179,28 @@ prepare_kernel(const double* __restrict__ g_, const double* __restrict__ Vg_, co
     }
     const double gm = sqrt(sb_block_sum(acc, scratch));
     if (tid == 0) { spos = 0; gam[b] = gm; }
+    for (int i = tid; i < m; i += nt) evs[i] = evals_[(size_t)b * estride + i];
     __syncthreads();
     int cntl = 0;
-    for (int i = tid; i < m; i += nt) cntl += (ev[i] < l0) ? 1 : 0;
+    for (int i = tid; i < m; i += nt) cntl += (evs[i] < l0) ? 1 : 0;
     if (cntl) atomicAdd(&spos, cntl);
     __syncthreads();
     const int pos = spos;
     const int nfill = width - m;           // complement pole (if any) + padding
-    for (int idx = tid; idx < width; idx += nt) {
-        double e, c; int r;
-        if (idx < pos) { e = ev[idx]; c = Vg_[(size_t)b * n + idx]; r = idx; }
-        else if (idx < pos + nfill) {
-            e = l0;
-            const bool first = (idx == pos) && cluster;
-            c = first ? gm : 0.0;
-            r = first ? -1 : -2;
-        } else { r = idx - nfill; e = ev[r]; c = Vg_[(size_t)b * n + r]; }
-        cev[(size_t)b * width + idx] = e;
-        cvg[(size_t)b * width + idx] = c;
-        rowmap[(size_t)b * width + idx] = r;
+    for (int i = tid; i < m; i += nt) {
+        const double ei = evs[i];
+        int rank = 0;
+        for (int j = 0; j < m; ++j) { const double ej = evs[j]; rank += (ej < ei) || (ej == ei && j < i); }
+        const int idx = rank < pos ? rank : rank + nfill;
+        cev[(size_t)b * width + idx] = ei;
+        cvg[(size_t)b * width + idx] = Vg_[(size_t)b * n + i];
+        rowmap[(size_t)b * width + idx] = i;
+    }
+    for (int f = tid; f < nfill; f += nt) {
+        const bool first = (f == 0) && cluster;
+        cev[(size_t)b * width + pos + f] = l0;
+        cvg[(size_t)b * width + pos + f] = first ? gm : 0.0;
+        rowmap[(size_t)b * width + pos + f] = first ? -1 : -2;
     }
 }
 
@@ -344,21 +348,26 @@ __global__ void jd_finish_kernel(double* __restrict__ t, const double* __restric
     t[(size_t)b * n + i] += method == 1 ? r * inv0 : (eps * v - r) * inv0;
 }
 
-// the k lowest eigenvalues of B per system (ascending): the explicit theta merged with lam0 (multiplicity n - m)
+// the k lowest eigenvalues of B per system (ascending): the explicit theta (any storage order) merged with
+// lam0 (multiplicity n - m); k <= 8
 __global__ void lowest_kernel(const double* __restrict__ evals_, long long estride, const int* __restrict__ mrows,
                               const double* __restrict__ lam0, int n, int k, double* __restrict__ out, int batch) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
     const int m = mrows[b];
-    const double l0 = lam0[b];
-    int i = 0, c = n - m;            // next explicit index, copies of lam0 left
-    for (int j = 0; j < k; ++j) {
-        double v;
-        if (i < m && (c == 0 || evals_[(size_t)b * estride + i] <= l0)) v = evals_[(size_t)b * estride + i++];
-        else if (c > 0) { v = l0; --c; }
-        else v = l0;                 // k > n
-        out[(size_t)b * k + j] = v;
-    }
+    double best[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) best[j] = INFINITY;
+    auto insert = [&](double v) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < k && v < best[j]) { const double t = best[j]; best[j] = v; v = t; }
+        }
+    };
+    for (int i = 0; i < m; ++i) insert(evals_[(size_t)b * estride + i]);
+    const int copies = min(k, n - m);
+    for (int c = 0; c < copies; ++c) insert(lam0[b]);
+    for (int j = 0; j < k; ++j) out[(size_t)b * k + j] = isinf(best[j]) ? lam0[b] : best[j];
 }
 
 // out[b,v,:] = mask[:] * X[b,v,:]  for v < nv  (projection onto the free Cartesian coordinates)
@@ -404,8 +413,10 @@ int sb_compact_prepare(const double* g, const double* Vg, const double* Wg, cons
                        double* cev, double* cvg, int32_t* rowmap, const int32_t* active, int batch, void* stream) {
     if (width < 1 || width > n || batch < 1) return -1;
     SB_COUNT(1);
-    prepare_kernel<<<batch, CP_THREADS, 0, ST>>>(g, Vg, Wg, evals, estride, mrows, lam0, n, width, gperp, gam, cev,
-                                                 cvg, rowmap, active);
+    const size_t smem = (size_t)width * sizeof(double);
+    cudaFuncSetAttribute(prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    prepare_kernel<<<batch, CP_THREADS, smem, ST>>>(g, Vg, Wg, evals, estride, mrows, lam0, n, width, gperp, gam, cev,
+                                                    cvg, rowmap, active);
     return SB_LAUNCH_CHECK();
 }
 
@@ -466,7 +477,7 @@ int sb_compact_jd_finish(double* t, const double* rv, const double* ed, int n, i
 
 int sb_compact_lowest(const double* evals, long long estride, const int32_t* mrows, const double* lam0, int n,
                       int k, double* out, int batch, void* stream) {
-    if (k < 1) return -1;
+    if (k < 1 || k > 8) return -1;
     SB_COUNT(1);
     lowest_kernel<<<(batch + 127) / 128, 128, 0, ST>>>(evals, estride, mrows, lam0, n, k, out, batch);
     return SB_LAUNCH_CHECK();

@@ -91,6 +91,34 @@ gemm_kernel(int transA, int transB, int M, int N, int K, double alpha, const dou
             }
 }
 
+// fp64 peak micro-benchmarks (bench.py: the denominator of the tensor/FMA rooflines; MEASURED_PEAKS.json
+// carries no fp64 figure).  kind 0: dependent-chain-free DFMA from registers (8 accumulators per thread);
+// kind 1: DMMA m8n8k4 from registers (4 accumulator tiles per warp).  Each thread writes one value so
+// that nothing is optimised away.
+__global__ void __launch_bounds__(256)
+fp64_peak_kernel(int kind, int iters, double* __restrict__ out) {
+    const double seed = 1.0 + 1e-9 * (threadIdx.x + blockIdx.x);
+    double a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = seed + i;
+    const double x = 0.999999, y = 1e-7;
+    if (kind == 0) {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = fma(a[i], x, y);
+        }
+    } else {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dmma_8x8x4(a[2 * i], a[2 * i + 1], x, y);
+        }
+    }
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += a[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = t;
+}
+
 constexpr int QR_THREADS = 256;
 constexpr int QR_NB = 16;          // panel width
 
@@ -356,4 +384,29 @@ extern "C" int sb_trtri_impl(const double* R, double* X, double* work, int n, in
     const int rc = trtri_rec(R, X, work, n, 0, n, status, active, batch, st);
     if (rc) return rc;
     return SB_LAUNCH_CHECK();
+}
+
+// TFLOP/s of the fp64 FMA pipe (kind 0) or of the fp64 tensor-core path (kind 1) on the current device:
+// `ctas_per_sm` CTAs of 256 threads per SM, `iters` iterations; scratch: sms*ctas_per_sm*256 doubles.
+// Synchronises the device (diagnostic, not on any product path).
+extern "C" int sb_fp64_peak_impl(int kind, int iters, int ctas_per_sm, double* scratch, double* tflops) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = sms * ctas_per_sm;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    fp64_peak_kernel<<<grid, 256>>>(kind, iters / 8 + 1, scratch);       // warm-up
+    cudaEventRecord(e0);
+    fp64_peak_kernel<<<grid, 256>>>(kind, iters, scratch);
+    cudaEventRecord(e1);
+    cudaError_t err = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (err != cudaSuccess) return (int)err;
+    // kind 0: 8 FMA = 16 flops per thread and iteration; kind 1: 4 DMMA of 8x8x4 = 4 * 512 flops per warp
+    const double flops = kind == 0 ? (double)grid * 256 * 16.0 * iters : (double)grid * 8 * 4.0 * 512.0 * iters;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    return 0;
 }

@@ -145,6 +145,9 @@ lowrank_factor_kernel(const double* __restrict__ U_, const double* __restrict__ 
     if (tid == 0) nterm[b] = r;
 }
 
+// optional in-kernel phase profile (cycles, summed over CTAs by thread 0); [14] secular iterations, [15] roots
+__device__ unsigned long long sec_prof[16];
+
 // ------------------------------------------------------------------------------
 // One secular root of  f(lam) = 1 + rho * sum_i y_i^2 / (e_i - lam),  rho > 0,
 // e ascending, in (e_j, e_{j+1})  (j = r-1: (e_{r-1}, e_{r-1} + rho*|y|^2)).
@@ -173,7 +176,35 @@ __device__ void secular_root(const double* __restrict__ e, const double* __restr
     // with (geometric) bisection as the safeguard
     const double w = rho * y2[org];
     double mu = (org == j) ? ((j + 1 < r) ? 0.25 * gap : 0.5 * gap) : -0.25 * gap;
+    {
+        // first guess from the pole-exact model expanded AT the pole: q(0) + q'(0) t - w/t = 0.  A pole
+        // with a tiny weight (a direction the update barely touches: most explicit pairs of a compact
+        // spectrum) has its root at a distance ~ w/q(0) from it, many orders of magnitude inside the
+        // bracket; started from the middle of the bracket the safeguarded iteration needs dozens of
+        // (geometric) bisection steps to get there, started here two or three
+        double q0 = 0.0, dq0 = 0.0;
+        for (int i = lane; i < r; i += 32) {
+            if (i == org) continue;
+            const double den = e[i] - eo;
+            const double t = y2[i] / den;
+            q0 += rho * t;
+            dq0 += rho * t / den;
+        }
+        q0 = 1.0 + sb_warp_sum(q0);
+        dq0 = sb_warp_sum(dq0);
+        const double sq0 = sqrt(fma(q0, q0, 4.0 * dq0 * w));
+        double cand;
+        if (dq0 > 0.0) {
+            if (org == j) cand = q0 <= 0.0 ? (sq0 - q0) / (2.0 * dq0) : 2.0 * w / (q0 + sq0);
+            else cand = q0 >= 0.0 ? -(q0 + sq0) / (2.0 * dq0) : -2.0 * w / (sq0 - q0);
+        } else {
+            cand = (q0 != 0.0) ? w / q0 : mu;
+        }
+        if (cand > lo && cand < hi) mu = cand;
+    }
+    int nit_ = 0;
     for (int it = 0; it < 200; ++it) {
+        ++nit_;
         double q = 0.0, dq = 0.0, qa = 0.0;
         for (int i = lane; i < r; i += 32) {
             if (i == org) continue;
@@ -203,6 +234,146 @@ __device__ void secular_root(const double* __restrict__ e, const double* __restr
         }
         if (!(next > lo && next < hi)) {
             if (org == j) {
+                if (lo > 0.0 && hi > 4.0 * lo) next = sqrt(lo) * sqrt(hi);
+                else if (lo == 0.0) next = (hi > 1e-290) ? hi * 0.0625 : 0.5 * hi;
+                else next = 0.5 * (lo + hi);
+            } else {
+                if (hi < 0.0 && lo < 4.0 * hi) next = -sqrt(-lo) * sqrt(-hi);
+                else if (hi == 0.0) next = (lo < -1e-290) ? lo * 0.0625 : 0.5 * lo;
+                else next = 0.5 * (lo + hi);
+            }
+        }
+        if (fabs(next - mu) <= 2.0 * SEC_EPS * fabs(next) || next == mu) { mu = next; break; }
+        mu = next;
+        if (hi - lo <= 2.0 * SEC_EPS * fmax(fabs(lo), fabs(hi))) break;
+    }
+    *org_out = org;
+    *mu_out = mu;
+#ifdef SB_SEC_COUNT_ITERS
+    if (lane == 0) { atomicAdd(&sec_prof[14], (unsigned long long)nit_); atomicAdd(&sec_prof[15], 1ull); }
+#endif
+}
+
+// Reciprocal for the secular sums: hardware approximation (2^-23) + two Newton steps, i.e. full fp64
+// accuracy up to the last bit at a fifth of the instructions of an IEEE division.  The root search does
+// O(r^2) of these per rank-one term: with one thread per root they are what the solve kernel spends its
+// time on.
+__device__ __forceinline__ double sec_rcp(double a) {
+    if (!(fabs(a) > 1e-290 && fabs(a) < 1e290)) return 1.0 / a;       // 0, denormals, huge, NaN: the IEEE path
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    double e = fma(-a, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-a, x, 1.0);
+    x = fma(x, e, x);
+    return x;
+}
+
+// One secular root with ONE THREAD per root (split-mode solve kernel: r-way parallel over the roots, plain
+// loops over the r poles in shared memory -- all threads of a warp read the same e[i], y2[i], a broadcast).
+// Iteration: the "middle way" of LAPACK's dlaed4 (Li 1994): f = 1 + psi + phi with psi the poles up to j and
+// phi the poles above; psi is modelled as s + a/(delta_j - eta), phi as S + b/(delta_{j+1} - eta) (value and
+// slope matched), so BOTH neighbouring poles are exact and each step solves a quadratic.  A Taylor model of
+// everything but the nearest pole (secular_root above) needs 10-35 steps when the other neighbour is close
+// (gaps of 1e-8 are common in a compact spectrum) and the slowest root sets the time of the whole CTA; this
+// one needs at most ~7.  First guess: both neighbouring poles exact, the rest frozen at the origin pole.
+__device__ void secular_root_serial(const double* __restrict__ e, const double* __restrict__ y2, int r, double rho,
+                                    int j, double ysum, int* org_out, double* mu_out) {
+    const bool last = j + 1 >= r;
+    const double left = e[j];
+    const double gap = last ? rho * ysum : (e[j + 1] - e[j]);
+    int org = j;
+    if (!last) {
+        const double mid = 0.5 * gap;
+        double f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;
+        int i = 0;
+        for (; i + 3 < r; i += 4) {
+            f0 = fma(y2[i], sec_rcp((e[i] - left) - mid), f0);
+            f1 = fma(y2[i + 1], sec_rcp((e[i + 1] - left) - mid), f1);
+            f2 = fma(y2[i + 2], sec_rcp((e[i + 2] - left) - mid), f2);
+            f3 = fma(y2[i + 3], sec_rcp((e[i + 3] - left) - mid), f3);
+        }
+        for (; i < r; ++i) f0 = fma(y2[i], sec_rcp((e[i] - left) - mid), f0);
+        if (1.0 + rho * ((f0 + f1) + (f2 + f3)) < 0.0) org = j + 1;
+    }
+    const double eo = e[org];
+    double lo, hi;
+    if (org == j) { lo = 0.0; hi = last ? gap : 0.5 * gap; }
+    else { lo = -0.5 * gap; hi = 0.0; }
+    const double dj = e[j] - eo;                            // 0, or -gap when the origin is pole j+1
+    const double dj1 = last ? 0.0 : e[j + 1] - eo;
+    const double w = rho * y2[org];
+    double mu = (org == j) ? (last ? 0.5 * gap : 0.25 * gap) : -0.25 * gap;
+    {
+        // first guess: R0 - w/t + wK/(D - t) = 0 with R0 = 1 + rho sum over the OTHER poles of y2/(e - eo)
+        const int other = last ? -1 : (org == j ? j + 1 : j);
+        double r0 = 0.0, r1 = 0.0;
+        int i = 0;
+        auto term = [&](int k) {
+            const bool skip = (k == org) || (k == other);
+            return (skip ? 0.0 : y2[k]) * sec_rcp(skip ? 1.0 : e[k] - eo);
+        };
+        for (; i + 1 < r; i += 2) { r0 += term(i); r1 += term(i + 1); }
+        for (; i < r; ++i) r0 += term(i);
+        const double R0 = 1.0 + rho * (r0 + r1);
+        double cand = mu;
+        if (other < 0) {
+            if (R0 > 0.0) cand = w / R0;
+        } else {
+            const double D = e[other] - eo, wK = rho * y2[other];
+            // -R0 t^2 + (R0 D + w + wK) t - w D = 0
+            const double qa_ = -R0, qb_ = fma(R0, D, w + wK), qc_ = -w * D;
+            const double disc = fma(qb_, qb_, -4.0 * qa_ * qc_);
+            if (disc >= 0.0) {
+                const double sq = sqrt(disc);
+                const double qq = -0.5 * (qb_ + (qb_ >= 0.0 ? sq : -sq));
+                const double x1 = qq != 0.0 ? qc_ / qq : mu, x2 = qa_ != 0.0 ? qq / qa_ : mu;
+                cand = (x1 > lo && x1 < hi) ? x1 : x2;
+            }
+        }
+        if (cand > lo && cand < hi) mu = cand;
+    }
+    for (int it = 0; it < 200; ++it) {
+        // psi, psi' over the poles <= j and phi, phi' over the poles > j at the current iterate
+        double ps0 = 0.0, ps1 = 0.0, dp0 = 0.0, dp1 = 0.0, ph0 = 0.0, ph1 = 0.0, dh0 = 0.0, dh1 = 0.0, qa0 = 0.0, qa1 = 0.0;
+        auto term = [&](int k, double& ps, double& dp, double& ph, double& dh, double& qa) {
+            const double rc = sec_rcp((e[k] - eo) - mu);
+            const double t = y2[k] * rc, t2 = t * rc;
+            const bool lower = k <= j;
+            ps += lower ? t : 0.0;  dp += lower ? t2 : 0.0;
+            ph += lower ? 0.0 : t;  dh += lower ? 0.0 : t2;
+            qa += fabs(t);
+        };
+        int i = 0;
+        for (; i + 1 < r; i += 2) { term(i, ps0, dp0, ph0, dh0, qa0); term(i + 1, ps1, dp1, ph1, dh1, qa1); }
+        for (; i < r; ++i) term(i, ps0, dp0, ph0, dh0, qa0);
+        const double psi = rho * (ps0 + ps1), dpsi = rho * (dp0 + dp1), phi = rho * (ph0 + ph1), dphi = rho * (dh0 + dh1);
+        const double qa = rho * (qa0 + qa1);
+        const double f = 1.0 + psi + phi;
+        if (fabs(f) <= 4.0 * SEC_EPS * (1.0 + qa)) break;
+        if (f < 0.0) lo = mu; else hi = mu;
+        const double Dj = dj - mu;
+        const double a = dpsi * Dj * Dj, sA = psi - dpsi * Dj;
+        double next = 0.0;
+        bool ok = false;
+        if (last) {
+            const double c = 1.0 + sA;
+            if (c != 0.0) { next = mu + Dj + a / c; ok = next > lo && next < hi; }
+        } else {
+            const double Dj1 = dj1 - mu;
+            const double bB = dphi * Dj1 * Dj1, sB = phi - dphi * Dj1;
+            const double c = 1.0 + sA + sB;
+            const double Bc = c * (Dj + Dj1) + a + bB;
+            const double C0 = c * Dj * Dj1 + a * Dj1 + bB * Dj;
+            double disc = fma(Bc, Bc, -4.0 * c * C0);
+            if (disc < 0.0) disc = 0.0;
+            const double sq = sqrt(disc);
+            const double qq = 0.5 * (Bc + (Bc >= 0.0 ? sq : -sq));
+            if (qq != 0.0) { next = mu + C0 / qq; ok = next > lo && next < hi; }
+            if (!ok && c != 0.0) { next = mu + qq / c; ok = next > lo && next < hi; }
+        }
+        if (!ok) {
+            if (lo >= 0.0) {
                 if (lo > 0.0 && hi > 4.0 * lo) next = sqrt(lo) * sqrt(hi);
                 else if (lo == 0.0) next = (hi > 1e-290) ? hi * 0.0625 : 0.5 * hi;
                 else next = 0.5 * (lo + hi);
@@ -466,8 +637,6 @@ cluster_reflect_kernel(double* __restrict__ Vt_, const double* __restrict__ work
     }
 }
 
-// optional in-kernel phase profile (cycles, summed over CTAs by thread 0)
-__device__ unsigned long long sec_prof[16];
 #define SEC_MARK(ph)                                                        \
     do {                                                                    \
         if (tid == 0) {                                                     \
@@ -528,8 +697,8 @@ __device__ void apply_rotations(double* __restrict__ Vt, int n, const int* __res
 // Applies nterm[b] rank-one updates (sig, Z = Vt P^T) to (evals, Vt).
 // Zs: [b, zcap, n] (row t = V^T p_t in the CURRENT row order of Vt), work: [b, n, n],
 // qwork: [b, n, n].  On exit evals ascending, Vt rows permuted accordingly.
-template <int CPT>
-__global__ void __launch_bounds__(SECK_THREADS, 4)
+template <int CPT, bool SPLIT>
+__global__ void __launch_bounds__(SECK_THREADS, SPLIT ? 6 : 4)
 secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, double* __restrict__ Z_, int zcap,
                       const double* __restrict__ sig_, const int* __restrict__ nterm, int n,
                       double* __restrict__ work_, double* __restrict__ qwork_, int* __restrict__ status,
@@ -766,8 +935,11 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
                 if (fabs(rho * z[i]) <= tol) continue;
                 if (prev < 0) { prev = i; continue; }
                 double s = z[prev], c = z[i];
-                const double tau = hypot(c, s);
                 const double tt = d[i] - d[prev];
+                // |tt c s| <= tol with c = z_i/tau, s = -z_prev/tau, tau^2 = z_i^2 + z_prev^2: test without the
+                // square root and the divisions first (almost no pair merges)
+                if (!(fabs(tt * c * s) <= 2.0 * tol * (c * c + s * s))) { nd[r++] = prev; prev = i; continue; }
+                const double tau = hypot(c, s);
                 c /= tau; s = -s / tau;
                 if (fabs(tt * c * s) <= tol) {
                     z[i] = tau; z[prev] = 0.0;
@@ -823,46 +995,69 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
             acc += v * v;
         }
         const double ysum = sb_block_sum(acc, S.scratch);
-        for (int j = tid >> 5; j < r; j += nt >> 5) {      // one warp per root
-            int o; double m;
-            if (r == 1) { o = 0; m = arho * y2[0]; }
-            else secular_root(dd, y2, r, arho, j, ysum, &o, &m);
-            if ((tid & 31) == 0) { org[j] = o; mu[j] = m; }
+        if constexpr (SPLIT) {
+            for (int j = tid; j < r; j += nt) {                // one thread per root
+                int o; double m_;
+                if (r == 1) { o = 0; m_ = arho * y2[0]; }
+                else secular_root_serial(dd, y2, r, arho, j, ysum, &o, &m_);
+                org[j] = o; mu[j] = m_;
+            }
+        } else {
+            for (int j = tid >> 5; j < r; j += nt >> 5) {      // one warp per root
+                int o; double m_;
+                if (r == 1) { o = 0; m_ = arho * y2[0]; }
+                else secular_root(dd, y2, r, arho, j, ysum, &o, &m_);
+                if ((tid & 31) == 0) { org[j] = o; mu[j] = m_; }
+            }
         }
         __syncthreads();
         // Gu-Eisenstat: zh_i^2 = (lam_i - dd_i)/rho * prod_{j != i} (lam_j - dd_i)/(dd_j - dd_i)
         for (int i = tid; i < r; i += nt) {
             double prod = ((dd[org[i]] - dd[i]) + mu[i]) / arho;
-            for (int j = 0; j < r; ++j) {
-                if (j == i) continue;
-                prod *= ((dd[org[j]] - dd[i]) + mu[j]) / (dd[j] - dd[i]);
+            {
+                const double di = dd[i];
+                double p0 = 1.0, p1 = 1.0, p2 = 1.0, p3 = 1.0;
+                auto fac = [&](int j) {
+                    const bool self = j == i;
+                    return self ? 1.0 : ((dd[org[j]] - di) + mu[j]) * sec_rcp(dd[j] - di);
+                };
+                int j = 0;
+                for (; j + 3 < r; j += 4) { p0 *= fac(j); p1 *= fac(j + 1); p2 *= fac(j + 2); p3 *= fac(j + 3); }
+                for (; j < r; ++j) p0 *= fac(j);
+                prod *= (p0 * p1) * (p2 * p3);
             }
             const int src = neg ? nd[r - 1 - i] : nd[i];
             zh[i] = copysign(sqrt(fabs(prod)), z[src]);
         }
         __syncthreads();
         // eigenvector matrix (mirrored index space): Qh[i*r + j] = zh_i / (dd_i - lam_j), columns normalised
-        const bool qsmem = t_only < 0 && r <= SEC_QS_MAX && (size_t)r * r <= (size_t)tile_doubles;
+        const bool qsmem = !SPLIT && r <= SEC_QS_MAX && (size_t)r * r <= (size_t)tile_doubles;
         if (qsmem) Qh = tile;
         else Qh = qwork_ + (size_t)b * vstride;
+        // column norms straight from (zh, dd, roots) in shared memory, then Qh written once, normalised
+        for (int j = tid; j < r; j += nt) {
+            const double base = dd[org[j]], m_ = mu[j];
+            double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
+            int i = 0;
+            for (; i + 3 < r; i += 4) {
+                const double q0 = zh[i] * sec_rcp((dd[i] - base) - m_), q1 = zh[i + 1] * sec_rcp((dd[i + 1] - base) - m_);
+                const double q2 = zh[i + 2] * sec_rcp((dd[i + 2] - base) - m_), q3 = zh[i + 3] * sec_rcp((dd[i + 3] - base) - m_);
+                n0 = fma(q0, q0, n0); n1 = fma(q1, q1, n1); n2 = fma(q2, q2, n2); n3 = fma(q3, q3, n3);
+            }
+            for (; i < r; ++i) { const double q = zh[i] * sec_rcp((dd[i] - base) - m_); n0 = fma(q, q, n0); }
+            y2[j] = 1.0 / sqrt((n0 + n1) + (n2 + n3));     // y2 is free again (weights consumed by the roots / zh)
+        }
+        __syncthreads();
         for (int idx = tid; idx < r * r; idx += nt) {
             const int i = idx / r, j = idx % r;
-            Qh[idx] = zh[i] / ((dd[i] - dd[org[j]]) - mu[j]);
+            Qh[idx] = zh[i] * sec_rcp((dd[i] - dd[org[j]]) - mu[j]) * y2[j];
         }
-        __syncthreads();
-        for (int j = tid; j < r; j += nt) {
-            double nrm = 0.0;
-            for (int i = 0; i < r; ++i) { const double q = Qh[(size_t)i * r + j]; nrm = fma(q, q, nrm); }
-            y2[j] = 1.0 / sqrt(nrm);           // y2 is free again (weights consumed by the roots / zh)
-        }
-        __syncthreads();
-        for (int idx = tid; idx < r * r; idx += nt) Qh[idx] *= y2[idx % r];
         __syncthreads();
         SEC_MARK(4);
         // ---------------- new eigenvectors: row_new(j) = sum_i Qh[i][j] row_old(i)   (mirrored index i,j)
         {
             auto rowof = [&](int i) { return neg ? nd[r - 1 - i] : nd[i]; };
-            if (t_only >= 0) {
+            if constexpr (SPLIT) {
                 // split mode: hand (r, row map, Qh) to the GEMM kernels
                 for (int i = tid; i < r; i += nt) aux[4 + i] = rowof(i);
                 if (tid == 0) aux[0] = r;
@@ -1158,7 +1353,39 @@ __global__ void secular_copyback_kernel(double* __restrict__ Vt_, const double* 
     }
 }
 
+__global__ void apply_bench_fill_kernel(int* __restrict__ aux_, int auxs, int r) {
+    int* aux = aux_ + (size_t)blockIdx.x * auxs;
+    if (threadIdx.x == 0) aux[0] = r;
+    for (int i = threadIdx.x; i < r; i += blockDim.x) aux[4 + i] = i;
+}
+
 }  // namespace
+
+// diagnostic (bench.py roofline of the rotation GEMM): `reps` launches of secular_apply_kernel with r rows for
+// every system (identity row map; Vt, qwork hold whatever they hold), average milliseconds per launch.
+extern "C" int sb_secular_apply_bench_impl(const double* Vt, const double* qwork, double* work, int* aux, int r,
+                                           int n, long long vstride, int batch, int reps, float* ms_out,
+                                           cudaStream_t st) {
+    const int auxs = r + 4;
+    apply_bench_fill_kernel<<<batch, 128, 0, st>>>(aux, auxs, r);
+    const size_t apsm = (size_t)2 * AP_STAGES * AP_BK * AP_LD * sizeof(double);
+    cudaFuncSetAttribute(secular_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apsm);
+    dim3 ga((n + AP_BN - 1) / AP_BN, (r + AP_BM - 1) / AP_BM, batch);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    secular_apply_kernel<<<ga, AP_THREADS, apsm, st>>>(Vt, qwork, work, aux, auxs, n, vstride, nullptr);
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < reps; ++i)
+        secular_apply_kernel<<<ga, AP_THREADS, apsm, st>>>(Vt, qwork, work, aux, auxs, n, vstride, nullptr);
+    cudaEventRecord(e1, st);
+    cudaError_t err = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (err != cudaSuccess) return (int)err;
+    *ms_out = ms / reps;
+    return SB_LAUNCH_CHECK();
+}
 
 extern "C" int sb_secular_profile_impl(unsigned long long* out16, int reset) {
     cudaError_t e = cudaMemcpyFromSymbol(out16, sec_prof, sizeof(unsigned long long) * 16);
@@ -1240,10 +1467,17 @@ extern "C" int sb_secular_update_c_impl(double* evals, double* Vt, double* Z, in
     const long long vs = mrows ? vstride : (long long)n * n;
     const int auxs = mc + 4;
 #define SB_SEC_LAUNCH(C, TONLY)                                                                                   \
-    cudaFuncSetAttribute(secular_update_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-    secular_update_kernel<C><<<batch, SECK_THREADS, smem, st>>>(evals, Vt, Z, zcap, sig, nterm, n, work, qwork,  \
-                                                               status, skip, tile_doubles, mrows, mc, es, vs,    \
-                                                               TONLY, aux, auxs)
+    if ((TONLY) == -1) {                                                                                          \
+        cudaFuncSetAttribute(secular_update_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        secular_update_kernel<C, false><<<batch, SECK_THREADS, smem, st>>>(evals, Vt, Z, zcap, sig, nterm, n, work,   \
+                                                                          qwork, status, skip, tile_doubles, mrows,   \
+                                                                          mc, es, vs, TONLY, aux, auxs);              \
+    } else {                                                                                                      \
+        cudaFuncSetAttribute(secular_update_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        secular_update_kernel<C, true><<<batch, SECK_THREADS, smem, st>>>(evals, Vt, Z, zcap, sig, nterm, n, work,    \
+                                                                         qwork, status, skip, tile_doubles, mrows,    \
+                                                                         mc, es, vs, TONLY, aux, auxs);               \
+    }
 #define SB_SEC_DISPATCH(TONLY)                          \
     if (cpt <= 1) { SB_SEC_LAUNCH(1, TONLY); }          \
     else if (cpt <= 2) { SB_SEC_LAUNCH(2, TONLY); }     \
@@ -1265,7 +1499,8 @@ extern "C" int sb_secular_update_c_impl(double* evals, double* Vt, double* Z, in
             dim3 gc((mc + 7) / 8, batch);
             secular_copyback_kernel<<<gc, 256, 0, st>>>(Vt, work, aux, auxs, n, vs, skip);
         }
-        SB_SEC_DISPATCH(-2)
+        // no final sort: in the compact representation the explicit pairs may sit in any order (evals[i]
+        // belongs to row i); every consumer ranks them on the fly
     } else {
         SB_SEC_DISPATCH(-1)
     }

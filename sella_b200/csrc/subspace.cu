@@ -576,19 +576,44 @@ davidson_init_kernel(const double* __restrict__ v0_, const double* __restrict__ 
         for (int i = tid; i < n; i += nt) V[i] = v0_[(size_t)b * n + i];
     } else {
         const int m = mrows ? mrows[b] : n;
-        int nneg = 0;
-        for (int i = 0; i < m && i < kcap; ++i) nneg += (pl[(size_t)b * estride + i] < 0.0);   // ascending
-        if (mrows && m < n && lam0[b] < 0.0) nneg = 0;    // (never: lam0 is a geometric mean of |Ritz values|)
+        // rows with a negative eigenvalue, most negative first (at most kcap); none: the lowest one.
+        // Dense representation: pl ascending, so these are the leading rows; compact: any storage order
+        __shared__ int sel[32];
+        __shared__ int nsel_s, lowest_s;
+        if (tid == 0) {
+            int cnt = 0, lowest = 0;
+            if (!mrows) {
+                for (int i = 0; i < m && i < kcap; ++i) if (pl[(size_t)b * estride + i] < 0.0) sel[cnt++] = i;
+            } else {
+                for (int i = 0; i < m; ++i) {
+                    const double v = pl[(size_t)b * estride + i];
+                    if (v < pl[(size_t)b * estride + lowest]) lowest = i;
+                    if (v < 0.0) {
+                        int p = cnt < kcap ? cnt : kcap - 1;            // insertion, ascending, capacity kcap
+                        if (cnt == kcap && !(v < pl[(size_t)b * estride + sel[kcap - 1]])) continue;
+                        while (p > 0 && pl[(size_t)b * estride + sel[p - 1]] > v) { sel[p] = sel[p - 1]; --p; }
+                        sel[p] = i;
+                        if (cnt < kcap) ++cnt;
+                    }
+                }
+                if (m < n && lam0[b] < 0.0) cnt = 0;    // (never: lam0 is a geometric mean of |Ritz values|)
+            }
+            if (cnt == 0) sel[0] = lowest;
+            nsel_s = cnt; lowest_s = lowest;
+        }
+        __syncthreads();
+        const int nneg = nsel_s;
         nstart = nneg < 1 ? 1 : nneg;
-        // no negative eigenvalue: the lowest eigenvector.  In the compact representation that is row 0
-        // unless the complement's lam0 lies below every explicit eigenvalue; any unit vector of the
+        // no negative eigenvalue: the lowest eigenvector.  In the compact representation that is an explicit
+        // row unless the complement's lam0 lies below every explicit eigenvalue; any unit vector of the
         // complement is then "the" lowest eigenvector (eigh of a degenerate matrix returns an arbitrary
         // one): the gradient's component in it
-        const bool from_complement = mrows && nneg == 0 && m < n && (m == 0 || pl[(size_t)b * estride] > lam0[b]);
+        const bool from_complement = mrows && nneg == 0 && m < n &&
+                                     (m == 0 || pl[(size_t)b * estride + lowest_s] > lam0[b]);
         if (from_complement) {
             for (int i = tid; i < n; i += nt) V[i] = gperp[(size_t)b * n + i];
         } else {
-            for (int i = tid; i < nstart * n; i += nt) V[i] = Pvt[(size_t)b * vstride + i];
+            for (int i = tid; i < nstart * n; i += nt) V[i] = Pvt[(size_t)b * vstride + (size_t)sel[i / n] * n + (i % n)];
         }
     }
     __syncthreads();

@@ -83,48 +83,261 @@ class _CalculatorSurface:
         g_out.copy_(torch.from_numpy(g).view(1, -1))
 
 
+class _HessianView:
+    """Duck type of the reference's ApproximateHessian (sella/linalg.py:143-353) over a host copy of a
+    dense matrix (B is None: uninitialised = identity, linalg.py:319-334).  `evals` / `evecs` come from
+    the CUDA eigensolver through the sella._gpu seam (sella_b200/_gpu.py), lazily."""
+
+    def __init__(self, dim, B=None, initialized=None):
+        self.dim = dim
+        self.shape = (dim, dim)
+        self.B = None if B is None else np.array(B, dtype=np.float64)
+        self.initialized = (B is not None) if initialized is None else initialized
+        self._evals = self._evecs = None
+
+    def _spectrum(self):
+        if self._evals is None and self.B is not None:
+            from .._gpu import gpu_eigh
+            self._evals, self._evecs = gpu_eigh(self.B)
+
+    @property
+    def evals(self):
+        self._spectrum()
+        return self._evals
+
+    @property
+    def evecs(self):
+        self._spectrum()
+        return self._evecs
+
+    def asarray(self):
+        return self.B if self.B is not None else np.eye(self.dim)
+
+    def project(self, U):
+        """linalg.py:306-317: U^T B U (None stays None)."""
+        if self.B is None:
+            return _HessianView(U.shape[1], None)
+        from .._gpu import gpu_project
+        return _HessianView(U.shape[1], gpu_project(self.B, np.ascontiguousarray(U)))
+
+    def dot(self, v):
+        return v if self.B is None else self.B @ v
+
+    __matmul__ = dot
+
+    def __add__(self, other):
+        ob = other.B if isinstance(other, _HessianView) else other
+        if self.B is None or ob is None:
+            return _HessianView(self.dim, None, initialized=False)
+        return _HessianView(self.dim, self.B + ob)
+
+    def __sub__(self, other):
+        ob = other.B if isinstance(other, _HessianView) else other
+        if self.B is None or ob is None:
+            return _HessianView(self.dim, None, initialized=False)
+        return _HessianView(self.dim, self.B - ob)
+
+
 class _PESView:
-    """The public bits of the reference's ``dyn.pes`` that user scripts and tests touch."""
+    """The reference's `dyn.pes` duck type (sella/peswrapper.py:214-606) as views over the
+    device-resident engine state of this one search: names, argument meaning and return conventions of the
+    reference; every array is a fresh host copy."""
+    n_cell_dof = 0
+    int = None
+    dummies = None
 
     def __init__(self, opt):
         self._o = opt
+        self._saved = None
+
+    # -- state
+    @property
+    def _e(self):
+        return self._o._eng
+
+    @property
+    def atoms(self):
+        return self._o.atoms
+
+    @property
+    def cons(self):
+        return self._o.constraints
+
+    @property
+    def dim(self):
+        return self._e.n
+
+    ncart = dim
 
     @property
     def neval(self):
         return self._o._surface.neval
 
+    @property
+    def eta(self):
+        return self._e.eta
+
+    @property
+    def hessian_function(self):
+        return self._o._hessian_function
+
+    @property
+    def traj(self):
+        return self._o._surface.traj
+
     def get_x(self):
-        return self._o._eng.x[0].cpu().numpy()
+        return self._e.x[0].cpu().numpy()
 
     def get_f(self):
-        return float(self._o._eng.f[0])
+        self._e.ensure_evaluated()
+        return float(self._e.f[0])
 
     def get_g(self):
-        return self._o._eng.g[0].cpu().numpy()
+        self._e.ensure_evaluated()
+        return self._e.g[0].cpu().numpy()
 
+    @property
+    def curr(self):
+        e = self._e
+        ev = e._evaluated
+        return dict(x=self.get_x(), f=float(e.f[0]) if ev else None, g=e.g[0].cpu().numpy() if ev else None,
+                    L=self._multipliers() if ev else None)
+
+    def save(self):
+        """peswrapper.py:305-312 keeps the atomic positions of a point to come back to."""
+        self._saved = self._e.x.clone()
+
+    def restore(self):
+        if self._saved is None:
+            raise RuntimeError("PES.restore() without a save()")
+        self._e.x.copy_(self._saved)
+        self._e._evaluated = False
+        self.atoms.positions = self.get_x().reshape((-1, 3))
+
+    # -- constraints (peswrapper.py:388-438, 467-481)
+    def _bases(self):
+        """(drdx, Ucons, Unred, Ufree) at the current geometry, as _calc_basis (peswrapper.py:395-407)."""
+        from scipy.linalg import qr
+        e = self._e
+        n = e.n
+        drdx = self.get_drdx()
+        if drdx.shape[0] == 0:
+            return drdx, np.zeros((n, 0)), np.eye(n), np.eye(n)
+        Q, R, _ = qr(drdx.T, mode="full", pivoting=True, check_finite=False)
+        d = np.abs(np.diag(R))
+        nc = int(np.sum(d > 1e-6 * d[0])) if (d.size and d[0] > 0) else 0
+        return drdx, Q[:, :nc], np.eye(n), Q[:, nc:]
+
+    def get_drdx(self):
+        e = self._e
+        if getattr(e, "fmask", None) is not None:
+            fixed = np.nonzero(e.fmask.cpu().numpy() == 0.0)[0]
+            return np.eye(e.n)[fixed]
+        if e.cons is None:
+            return np.zeros((0, e.n))
+        if "nl" in e.cons:
+            e.ensure_evaluated()
+            e.converged(0.0)                      # refreshes the bases if the geometry moved
+            return e.cons["C"][0].cpu().numpy()
+        C = e.cons["C"]
+        return (C[0] if C.dim() == 3 else C).cpu().numpy()
+
+    def get_res(self):
+        e = self._e
+        if e.cons is None:
+            return np.zeros(self.get_drdx().shape[0])
+        e.ensure_evaluated()
+        e.converged(0.0)
+        return e.cons["res"][0].cpu().numpy()
+
+    def get_Ucons(self):
+        return self._bases()[1]
+
+    def get_Unred(self):
+        return self._bases()[2]
+
+    def get_Ufree(self):
+        return self._bases()[3]
+
+    def get_scons(self):
+        """peswrapper.py:429-438: minimum-norm step that restores the constraints."""
+        drdx, Ucons = self._bases()[:2]
+        if drdx.shape[0] == 0:
+            return np.zeros(self._e.n)
+        return -Ucons @ np.linalg.lstsq(drdx @ Ucons, self.get_res(), rcond=None)[0]
+
+    def _multipliers(self):
+        drdx = self.get_drdx()
+        if drdx.shape[0] == 0:
+            return np.zeros(0)
+        return np.linalg.lstsq(drdx.T, self.get_g(), rcond=None)[0]
+
+    # -- Hessians (peswrapper.py:335-386)
+    @property
+    def H(self):
+        e = self._e
+        return _HessianView(e.n, e.B[0].cpu().numpy() if e.H_initialized else None)
+
+    def get_H(self):
+        return self.H
+
+    def get_Hc(self):
+        e = self._e
+        if e.cons is not None and "nl" in e.cons:
+            e.ensure_evaluated()
+            e._refresh_bases()
+            nl = e.cons["nl"]
+            Hc = nl["ints"].ldot(e.x, nl["Lmul"][:, nl["nlin"]:].contiguous())
+            return Hc[0].cpu().numpy()
+        return np.zeros((e.n, e.n))
+
+    def get_HL(self):
+        return self.get_H() - self.get_Hc()
+
+    def get_HL_projected(self, U):
+        return self.get_HL().project(U)
+
+    # -- actions
     def converged(self, fmax, cmax=1e-5):
-        e = self._o._eng
+        e = self._e
         e.ensure_evaluated()
         e.converged(fmax, cmax)
         f1 = float(e.fmax[0])
         c1 = float(e.cons["cmax"][0]) if e.cons is not None else 0.0
         return bool(e.conv[0]), f1, c1
 
-    class _H:
-        def __init__(self, eng):
-            self._e = eng
+    def diag(self, gamma=0.1, threepoint=False, maxiter=None):
+        """PES.diag (peswrapper.py:508-556): Davidson diagonalisation at the current geometry followed by
+        the block update of the approximate Hessian with every operator product collected."""
+        e = self._e
+        e.ensure_evaluated()
+        old = (e.gamma, e.threepoint, e.diag_maxiter)
+        if threepoint and not e.threepoint:
+            raise NotImplementedError("threepoint must be chosen when the optimiser is created")
+        e.gamma, e.diag_maxiter = float(gamma), maxiter
+        try:
+            if e.hessian_function is not None:
+                e._calculate_hessian()
+            else:
+                e._diag(None)
+        finally:
+            e.gamma, e.threepoint, e.diag_maxiter = old
+        self._o._check()
 
-        @property
-        def B(self):
-            return self._e.B[0].cpu().numpy() if self._e.H_initialized else None
+    def kick(self, dx, diag=False, **diag_kwargs):
+        raise NotImplementedError("PES.kick with a caller-supplied displacement is not on the CUDA path; "
+                                  "Sella.step() performs the kick of its own restricted step")
 
-        @property
-        def evals(self):
-            return self._e.evals[0].cpu().numpy() if self._e.H_initialized else None
-
-    @property
-    def H(self):
-        return _PESView._H(self._o._eng)
+    def set_x(self, target):
+        """peswrapper.py:313-322 (Cartesian): move to `target`; returns (dx_initial, dx_final, g_par)."""
+        e = self._e
+        target = np.asarray(target, dtype=np.float64).ravel()
+        diff = target - self.get_x()
+        g0 = e.g[0].cpu().numpy() if e._evaluated else np.zeros_like(diff)
+        e.x.copy_(torch.from_numpy(target[None].copy()).to(e.x.device))
+        e._evaluated = False
+        self.atoms.positions = target.reshape((-1, 3))
+        return diff, diff, g0
 
 
 class Sella(_Base):
@@ -196,6 +409,7 @@ class Sella(_Base):
                                  v0=None if v0 is None else torch.from_numpy(
                                      np.asarray(v0, dtype=np.float64).reshape(1, -1).copy()).to(dev()),
                                  constraints=self._engine_constraints(lin, nonlin, x0))
+        self._hessian_function = hessian_function
         self.pes = _PESView(self)
         self.ord = order
         self.eta = eta
@@ -231,6 +445,9 @@ class Sella(_Base):
 
     def step(self):
         self._eng.step()
+        self._check()
+
+    def _check(self):
         st = int(self._eng.status[0])
         if st & 8:
             # the Davidson subspace filled its 32 slots before the reference's criterion was met: the

@@ -327,3 +327,59 @@ def test_sella_long_first_davidson():
         if t == 0:
             assert p.last_rr[1].shape[1] > 16
         np.testing.assert_allclose(atoms.positions.ravel(), p.get_x(), rtol=0, atol=1e-6, err_msg="step %d" % t)
+
+
+class _MorseAtoms:
+    """ASE-Atoms duck with a pairwise Morse potential E = sum_{i<j} eps (e^{-2 rho0 (r/r0 - 1)} - 2 e^{-rho0 (r/r0 - 1)})
+    (the functional form of ase.calculators.morse.MorsePotential without its cutoff switch)."""
+
+    def __init__(self, pos, eps=1.0, r0=4.73, rho0=4.73 * 1.099):
+        self.positions = np.array(pos, dtype=float)
+        self.pbc = np.array([False, False, False])
+        self.constraints = []
+        self.par = (eps, r0, rho0)
+
+    def __len__(self):
+        return len(self.positions)
+
+    def _ef(self):
+        eps, r0, rho0 = self.par
+        x = self.positions
+        d = x[:, None, :] - x[None, :, :]
+        r = np.sqrt((d ** 2).sum(-1)) + np.eye(len(x))
+        e1 = np.exp(-rho0 * (r / r0 - 1.0))
+        pair = eps * (e1 * e1 - 2.0 * e1)
+        dEdr = eps * (-2.0 * rho0 / r0) * (e1 * e1 - e1)
+        np.fill_diagonal(pair, 0.0); np.fill_diagonal(dEdr, 0.0)
+        forces = -((dEdr / r)[:, :, None] * d).sum(axis=1)
+        return 0.5 * pair.sum(), forces
+
+    def get_potential_energy(self):
+        return self._ef()[0]
+
+    def get_forces(self):
+        return self._ef()[1]
+
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_morse_cluster_like_the_reference(order):
+    """The logic of the reference's own integration test (tests/integration/test_morse_cluster.py:11-46,
+    Cartesian cases): a 4-atom Morse cluster with translation + rotation held, run to fmax = 1e-3, then
+    through the PES duck type: the projected gradient vanishes and, after a tight re-diagonalisation, the
+    projected Lagrangian Hessian has exactly `order` negative eigenvalues."""
+    from sella_b200 import Sella, Constraints
+    rng = np.random.RandomState(4)
+    atoms = _MorseAtoms(rng.normal(size=(4, 3), scale=3.0))
+    cons = Constraints(atoms)
+    cons.fix_translation()
+    cons.fix_rotation()
+    opt = Sella(atoms, order=order, internal=False, gamma=1e-3, constraints=cons, logfile=None)
+    assert opt.run(fmax=1e-3, steps=500)
+    Ufree = opt.pes.get_Ufree()
+    assert Ufree.shape == (12, 6)
+    np.testing.assert_allclose(opt.pes.get_g() @ Ufree, 0, atol=5e-3)
+    np.testing.assert_allclose(opt.pes.get_Ucons().T @ Ufree, 0, atol=1e-10)          # test_peswrapper.py:35-36
+    opt.pes.diag(gamma=1e-16)
+    H = opt.pes.get_HL().project(Ufree)
+    assert np.sum(H.evals < 0) == order, H.evals
+    assert opt.pes.neval > 0 and opt.pes.get_drdx().shape == (6, 12)
