@@ -445,7 +445,11 @@ def run_ours(args):
 
     b, n = args.batch, args.n
     cons = None
-    first = rank * b                     # global index of this rank's first system (= its seed index)
+    from sella_b200.sharding import shard_range, max_over_ranks
+    # weak scaling: the global batch is world * b systems, rank r owns the contiguous block shard_range gives it
+    # (system index = seed index: both arms and the parity check draw system i from RandomState(1000 + i))
+    first, last = shard_range(world * b, rank, world)
+    assert last - first == b
     if args.workload == "quadratic":
         A, xs, x0 = host_generated_batch(first, b, n, dev, world)
         surf = QuadraticSurface(A, xs)
@@ -512,10 +516,7 @@ def run_ours(args):
                 ("singular", 16), ("davidson_stall", 32)) if ((st & bit) != 0).any()}
     steps_done = int(eng.nsteps.sum().item()) - b * args.warmup
     assert steps_done == b * args.steps
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max = max_over_ranks(ms, device=dev)
     value = world * b * args.steps / (ms_max / 1e3)
 
     # ---------------- in-run parity: systems 0..P-1 of THIS run's timed batch vs the reference algorithm on
@@ -612,10 +613,7 @@ def run_ours(args):
         host_step()
     e1.record()
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * b * args.steps / (float(t.item()) / 1e3)
+    e2e_value = world * b * args.steps / (max_over_ranks(e0.elapsed_time(e1), device=dev) / 1e3)
     e2e = dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=world * b * n * 8,
                d2h_bytes_per_step=world * (b * n * 8 + 2 * b * 8))
 

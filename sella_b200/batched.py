@@ -704,6 +704,18 @@ class BatchedSella:
         self._spectral_apply(self.spB, self.s.view(b, 1, n), self.up1, 1, active)
         return True
 
+    def _sync_rows(self):
+        """ONE small device->host read: the exact bounds on the explicit-row counts (and whether any system
+        wants a re-diagonalisation)."""
+        stats = [self.ev.max(), self.spB.mrows.max(), self.spB.mrows.min()]
+        if self.sp is not self.spB:
+            stats += [self.sp.mrows.max(), self.sp.mrows.min()]
+        vals = torch.stack(stats).tolist()
+        nev, self.spB.rb, self.spB.mmin = vals[:3]
+        if self.sp is not self.spB:
+            self.sp.rb, self.sp.mmin = vals[3:]
+        return nev
+
     def _step_compact(self, active):
         b, n = self.batch, self.n
         ready = self._predict_compact(active)
@@ -722,13 +734,7 @@ class BatchedSella:
         # ONE small read per step: does any system re-diagonalise, and how many explicit rows do the
         # passes have to visit (the bound kept on the host grows by the number of TERMS per update, the
         # true count by the number of NEW directions, usually half of that)
-        stats = [self.ev.max(), self.spB.mrows.max(), self.spB.mrows.min()]
-        if self.sp is not self.spB:
-            stats += [self.sp.mrows.max(), self.sp.mrows.min()]
-        vals = torch.stack(stats).tolist()
-        nev, self.spB.rb, self.spB.mmin = vals[:3]
-        if self.sp is not self.spB:
-            self.sp.rb, self.sp.mmin = vals[3:]
+        nev = self._sync_rows()
         if nev > 0:
             if self.hessian_function is not None:
                 self._calculate_hessian(self.ev)
@@ -937,14 +943,27 @@ class BatchedSella:
         # (eigensolvers.py:31-66: A is the projected operator of peswrapper.py:531-537)
         nfree = self.cons["nfree"] if self.cons is not None else (self.nfree if getattr(self, "fmask", None) is not None else n)
         maxiter_eff = nfree if self.diag_maxiter is None else min(nfree, int(self.diag_maxiter))
-        rounds = nstart
+        rounds = nstart                 # operator products so far (the reference's subspace size)
+        kbound = nstart                 # host-side bound on the current subspace sizes ksz[b]
+        hbound = nstart                 # ... and on the history lengths nhist[b]
         while True:
             call("sb_davidson_rr", _p(self.V), _p(self.AV), I(kc), _p(self.ksz), I(n), D(self.gamma),
                  I(maxiter_eff), _p(self.lams), _p(self.rv), _p(self.theta), _p(self.dav_state),
                  _p(self.status), I(b), _stream())
             m = (self.dav_state == DAV_EXPAND).to(torch.int32)
-            if int(m.sum().item()) == 0:
+            if int(m.sum().item()) == 0 or rounds >= maxiter_eff:
                 break
+            if kbound >= kc:
+                # The device subspace is full where the reference would go on (up to min(n, maxiter) vectors,
+                # eigensolvers.py:65-66).  Thick restart: sb_davidson_rr has just rotated (V, AV) to Ritz
+                # vectors in ascending order, so keeping the lowest `keep` of them loses nothing about the pairs
+                # being sought; the operator products collected so far go into the Hessian as one block
+                # update (they would all enter the single update at the end of PES.diag, peswrapper.py:541-551)
+                keep = max(2, kc // 2)
+                self._flush_history(part, min(hbound, kc), nl)
+                self.nhist.zero_()
+                self.ksz.copy_(torch.where(m > 0, torch.clamp(self.ksz, max=keep), self.ksz))
+                kbound, hbound, first = keep, 0, False
             lanczos = int(self.eigensolver == 2)
             if first or lanczos:
                 tin = None
@@ -979,16 +998,25 @@ class BatchedSella:
             m = (self.dav_state == DAV_EXPAND).to(torch.int32)
             self._hvp(self.vnew, n, self.dav_state, DAV_EXPAND, m)
             rounds += 1
+            kbound += 1
+            hbound += 1
+        if hbound > 0:
+            self._flush_history(part, min(hbound, kc), nl)
+        self.ndiag += 1
+
+    def _flush_history(self, part, nv, nl):
+        """PES.diag tail (peswrapper.py:541-551): Ritz-rotate the operator history and feed it to the
+        Hessian as one block update."""
+        b, n, kc = self.batch, self.n, self.kcap
         hcvs = None
         if nl is not None:
             if nl["HcVs"] is None:
                 nl["HcVs"] = torch.zeros_like(self.Vs)
             hcvs = nl["HcVs"]
-            K.hv_ld(nl["Hc"], self.Vs, hcvs, min(rounds, kc), active=part)
+            K.hv_ld(nl["Hc"], self.Vs, hcvs, nv, active=part)
         call("sb_history_ritz", _p(self.Vs), _p(self.AVs), I(kc), _p(self.nhist), I(n), _p(self.nvec),
              _p(self.dav_state), _p(self.status), _p(hcvs), I(b), _stream())
-        self._update(self.Vs, self.AVs, self.upk, self.nvec, min(rounds, kc), part)
-        self.ndiag += 1
+        self._update(self.Vs, self.AVs, self.upk, self.nvec, nv, part)
 
     # ------------------------------------------------------------------ public
     def step(self, active=None):
@@ -1091,6 +1119,41 @@ class BatchedSella:
                 self._calculate_hessian(self.ev)
             else:
                 self._diag(self.ev)
+
+    def kick(self, dx, diag=False):
+        """PES.kick (peswrapper.py:578-602) with a caller-supplied displacement dx [b, n]: move, evaluate,
+        rho = (f1 - f0) / (g0.dx + 1/2 dx.B dx), secant update with (dx, g1 - g0) and, if `diag`, a
+        re-diagonalisation.  The trust radius is NOT touched (that is Sella.step's business, optimize.py:
+        412-434).  Returns rho [b]."""
+        b, n = self.batch, self.n
+        check_f64(dx)
+        self.ensure_evaluated()
+        if not self.H_initialized:
+            self._identity_model()
+        self.s.copy_(dx)
+        S1 = self.s.view(b, 1, n)
+        call("sb_axpy", _p(self.x), _p(self.s), _p(self.xnew), I(n), _p(None), I(b), _stream())
+        if self.compact:
+            self.skip.zero_()
+            self._spectral_apply(self.spB, S1, self.up1, 1, None)
+        else:
+            K.hv_ld(self._B, S1, self.up1["BS"], 1)
+        self.surface.evaluate(self.xnew, self.fnew, self.gnew)
+        keep = self.delta.clone()
+        self.smag.copy_(self.s.norm(dim=1))
+        call("sb_kick_finish", _p(self.x), _p(self.f), _p(self.g), _p(self.xnew), _p(self.fnew), _p(self.gnew),
+             _p(self.s), _p(self.up1["BS"]), _p(self.smag), _p(self.dg), _p(self.delta), _p(self.rho),
+             _p(self.nsteps), self._dpar, self._ipar, I(n), _p(None), I(b), _stream())
+        self.delta.copy_(keep)
+        self._update(S1, self.dg.view(b, 1, n), self.up1, None, 1, None, bs_ready=True, abs_ready=self.compact)
+        if self.compact:
+            self._sync_rows()
+        if diag:
+            if self.hessian_function is not None:
+                self._calculate_hessian()
+            else:
+                self._diag(None)
+        return self.rho.clone()
 
     def ensure_evaluated(self):
         """Energy and gradient at the current geometry, evaluated at most once per geometry

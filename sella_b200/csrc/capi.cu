@@ -84,7 +84,7 @@ extern "C" int sb_davidson_init_c_impl(const double*, const double*, const doubl
                                        int*, int*, int*, int*, const int*, const int*, const double*, const double*,
                                        long long, long long, int, cudaStream_t);
 
-long long sb_launch_counter = 0;
+std::atomic<long long> sb_launch_counter{0};
 
 namespace {
 
@@ -147,7 +147,7 @@ int sb_add_scaled_identity(double* M, double scale, double diag, int n, int batc
     return SB_LAUNCH_CHECK();
 }
 
-long long sb_launch_count(void) { return sb_launch_counter; }
+long long sb_launch_count(void) { return sb_launch_counter.load(std::memory_order_relaxed); }
 
 int sb_device_sms(void) {
     int dev = 0, sms = 0;

@@ -113,8 +113,9 @@ __device__ __forceinline__ void sb_block_sum2(double& a, double& b, double* scra
 #define SB_SCRATCH_DOUBLES 68
 
 // number of kernels this library has launched (reported by bench.py as gpu_launches)
-extern "C" long long sb_launch_counter;
-#define SB_COUNT(k) (sb_launch_counter += (k))
+#include <atomic>
+extern std::atomic<long long> sb_launch_counter;      // host threads may launch concurrently
+#define SB_COUNT(k) (sb_launch_counter.fetch_add((k), std::memory_order_relaxed))
 
 static inline int sb_check(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }
 #define SB_LAUNCH_CHECK() sb_check(cudaGetLastError())

@@ -304,13 +304,16 @@ __global__ void hvt_ldg_kernel(const double* __restrict__ A, const double* __res
 
 int g_sms = 0;
 int g_smem_optin = 0;
+int g_dev = -1;
 
+// SM count and opt-in shared memory of the CURRENT device (one process may drive several devices)
 void query_device() {
-    if (g_sms) return;
     int dev = 0;
     cudaGetDevice(&dev);
+    if (dev == g_dev) return;
     cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    g_dev = dev;
 }
 
 HvPlan plan_hv(int n, int nvec, bool transposed, int m) {

@@ -698,7 +698,7 @@ __device__ void apply_rotations(double* __restrict__ Vt, int n, const int* __res
 // Zs: [b, zcap, n] (row t = V^T p_t in the CURRENT row order of Vt), work: [b, n, n],
 // qwork: [b, n, n].  On exit evals ascending, Vt rows permuted accordingly.
 template <int CPT, bool SPLIT>
-__global__ void __launch_bounds__(SECK_THREADS, SPLIT ? 6 : 4)
+__global__ void __launch_bounds__(SECK_THREADS, SPLIT ? 7 : 4)
 secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, double* __restrict__ Z_, int zcap,
                       const double* __restrict__ sig_, const int* __restrict__ nterm, int n,
                       double* __restrict__ work_, double* __restrict__ qwork_, int* __restrict__ status,
@@ -925,6 +925,9 @@ secular_update_kernel(double* __restrict__ evals_, double* __restrict__ Vt_, dou
             }
         }
         SEC_MARK(2);
+        // every thread must have read S.nrot (the cluster count of stage 1) before thread 0 reuses it below:
+        // with no cluster there is no barrier inside the loop above (compute-sanitizer racecheck)
+        __syncthreads();
         // ---------------- deflation, stage 2 (LAPACK dlaed2): neighbouring survivors whose
         // eigenvalues are close enough are combined by a plane rotation
         if (tid == 0) {

@@ -103,6 +103,7 @@ __device__ inline void sbs_jacobi_warp(double* C, int k, double* Z, double* w, i
                 const double app = C[p * SB_KLD + p], aqq = C[q * SB_KLD + q];
                 // skip rotations that cannot change anything at double precision
                 if (fabs(apq) <= 1e-300 || fabs(apq) <= 1e-19 * (fabs(app) + fabs(aqq))) {
+                    __syncwarp();           // all lanes have read C[p][q] before lane 0 clears it
                     if (lane == 0 && apq != 0.0 && fabs(apq) <= 1e-19 * (fabs(app) + fabs(aqq))) {
                         C[p * SB_KLD + q] = 0.0; C[q * SB_KLD + p] = 0.0;
                     }

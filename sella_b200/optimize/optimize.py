@@ -325,8 +325,21 @@ class _PESView:
         self._o._check()
 
     def kick(self, dx, diag=False, **diag_kwargs):
-        raise NotImplementedError("PES.kick with a caller-supplied displacement is not on the CUDA path; "
-                                  "Sella.step() performs the kick of its own restricted step")
+        """PES.kick (peswrapper.py:578-602): displace by dx, update the Hessian with the secant pair, optionally
+        re-diagonalise; returns rho = actual / predicted energy change."""
+        e = self._e
+        if getattr(e, "cons", None) is not None:
+            raise NotImplementedError("PES.kick with a caller-supplied displacement: unconstrained searches only")
+        old = (e.gamma, e.diag_maxiter)
+        e.gamma = float(diag_kwargs.get("gamma", e.gamma))
+        e.diag_maxiter = diag_kwargs.get("maxiter", e.diag_maxiter)
+        try:
+            d = torch.from_numpy(np.asarray(dx, dtype=np.float64).reshape(1, -1).copy()).to(e.x.device)
+            rho = float(e.kick(d, diag=diag)[0])
+        finally:
+            e.gamma, e.diag_maxiter = old
+        self._o._check()
+        return rho
 
     def set_x(self, target):
         """peswrapper.py:313-322 (Cartesian): move to `target`; returns (dx_initial, dx_final, g_par)."""

@@ -524,3 +524,20 @@ def test_carried_spectrum_after_300_updates(spectrum):
         np.testing.assert_allclose(full, np.linalg.eigvalsh(B[i]), atol=1e-10 * max(1.0, np.abs(th).max()))
     if spectrum == "compact":
         assert int(eng.mrows.min()) == n        # long past the point where the explicit rank reaches 3N
+
+
+@pytest.mark.parametrize("spectrum", ["compact", "dense"])
+def test_davidson_beyond_device_capacity(spectrum):
+    """gamma = 1e-4 needs more vectors than the device subspace holds (kcap = 8): the reference keeps expanding
+    (eigensolvers.py:65-66); the engine restarts with the lowest Ritz vectors and must converge to the same
+    lowest eigenpair of the true Hessian, without the capacity flag."""
+    n, systems = 48, [0, 1, 2]
+    eng, data = make_engine(n, systems, method="prfo", rs="tr", gamma=1e-4, kcap=8, spectrum=spectrum)
+    eng.step()                                   # first diagonalisation + one step
+    assert int((eng.status & 8).max()) == 0      # SB_ST_DAVIDSON_CAP never raised
+    eng.check_status()
+    lam = eng.lams[:, 0].cpu().numpy()
+    for i, (A, xs, x0) in enumerate(data):
+        w = np.linalg.eigvalsh(A)
+        np.testing.assert_allclose(lam[i], w[0], rtol=5e-3)        # converged Ritz value (residual < gamma |theta|)
+    assert eng.surface.neval > 10                # it really went past the 8 slots

@@ -383,3 +383,40 @@ def test_morse_cluster_like_the_reference(order):
     H = opt.pes.get_HL().project(Ufree)
     assert np.sum(H.evals < 0) == order, H.evals
     assert opt.pes.neval > 0 and opt.pes.get_drdx().shape == (6, 12)
+
+
+def test_pes_duck_type_kick_and_views():
+    """dyn.pes with the reference's names (peswrapper.py:214-606): kick with a caller-supplied displacement
+    against the oracle's PES.kick (rho, updated Hessian), the Hessian view and save/restore."""
+    from sella_b200 import Sella
+    from sella_b200.synthetic import quadratic_system, quadratic_func
+    from oracle.pes import CartesianPES
+    from oracle.driver import SaddleSearch
+    n = 30
+    A, xs, x0 = quadratic_system(2, n)
+    func = quadratic_func(A, xs)
+    atoms = _Atoms(func, x0)
+    dyn = Sella(atoms, logfile=None, proj_trans=False, proj_rot=False, method="qn", rs="tr")
+    p = CartesianPES(func, x0)
+    o = SaddleSearch(p, method="qn", rs="tr")
+    dyn.step(); o.step()
+    rng = np.random.RandomState(0)
+    for diag in (False, True):
+        dx = 0.05 * rng.normal(size=n)
+        rho = dyn.pes.kick(dx, diag=diag, gamma=0.1)
+        rho_ref = p.kick(dx, diag, gamma=0.1)
+        np.testing.assert_allclose(rho, rho_ref, rtol=1e-9)
+        np.testing.assert_allclose(dyn.pes.get_x(), p.get_x(), atol=1e-12)
+        np.testing.assert_allclose(dyn.pes.H.B, p.H.B, rtol=1e-7, atol=1e-9)
+    H = dyn.pes.get_H()
+    np.testing.assert_allclose(H.evals, np.linalg.eigvalsh(H.asarray()), atol=1e-10)
+    U = np.linalg.qr(rng.normal(size=(n, 5)))[0]
+    np.testing.assert_allclose(H.project(U).asarray(), U.T @ H.B @ U, atol=1e-11)
+    assert dyn.pes.get_Ufree().shape == (n, n) and dyn.pes.get_Ucons().shape == (n, 0)
+    assert dyn.pes.get_drdx().shape == (0, n) and np.abs(dyn.pes.get_scons()).max() == 0.0
+    x_keep = dyn.pes.get_x()
+    dyn.pes.save()
+    dyn.pes.kick(0.01 * rng.normal(size=n))
+    dyn.pes.restore()
+    np.testing.assert_array_equal(dyn.pes.get_x(), x_keep)
+    assert dyn.pes.curr["f"] is None and dyn.pes.get_f() == pytest.approx(func(x_keep)[0], rel=1e-12)
