@@ -70,6 +70,8 @@ def ncu_traffic(files, kernel_regex, per="launch"):
             by_kernel.setdefault(r[kn], []).append(tot)
         if not by_kernel:
             continue
+        if per == "max":                    # the largest launch (the full n x n pass among rectangular ones)
+            return max(max(v) for v in by_kernel.values()), name
         means = [sum(v) / len(v) for v in by_kernel.values()]
         return (sum(means) if per == "group" else sum(means) / len(means)), name
     return None, None
@@ -660,8 +662,8 @@ def run_ours(args):
     sec_cnt, sec_ms = prof.get("eigen_update_k1" if compact else "secular_update_k1", (0, 0.0))
     part_ms = [sum(p[i] for p in parts) / len(parts) for i in range(3)] if parts else [0.0, 0.0, 0.0]
     caps = NCU_CAPTURES.get((b, n), {})
-    traffic, traffic_src = ncu_traffic(caps.get("eigen", ()), r"cluster_reflect|secular_update|cluster_qr|append_", per="group")
-    hv_traffic, hv_traffic_src = ncu_traffic(caps.get("hv", ()), r"hv_tma_kernel<1>")
+    traffic, traffic_src = ncu_traffic(caps.get("eigen", ()), r"cluster_reflect|secular_update|secular_apply|cluster_qr|append_", per="group")
+    hv_traffic, hv_traffic_src = ncu_traffic(caps.get("hv", ()), r"hv_tma_kernel<1>", per="max")
     if compact:
         # one rank-2 eigen-update on r explicit rows: Z = VR P, W1 = VR^T Z, VR Qc, VR^T D2 (4 reads of the
         # r x n block) + the secular rotation (read + write of the rows it changes, <= r)

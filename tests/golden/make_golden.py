@@ -325,6 +325,40 @@ def golden_rotation():
     save("rotation", **out)
 
 
+def golden_sparse_hessians(ref):
+    """Assembly of per-coordinate second derivatives by the reference's own SparseInternalHessians.ldot / rdot
+    (sella/linalg.py:540-646; importable without JAX).  The per-coordinate (m,3,m,3) blocks fed to it are
+    the oracle's (oracle/internals.py: the reference obtains them from JAX, which is not installed), so this
+    pins the scatter / contraction logic of `ldot` and `rdot` -- everything but the derivative values."""
+    from oracle import internals as oi
+    rng = np.random.RandomState(31)
+    natoms = 9
+    pos = rng.normal(size=(natoms, 3)) * 1.2 + np.arange(natoms)[:, None] * np.array([0.9, 0.2, -0.1])
+    bonds = [(i, i + 1) for i in range(natoms - 1)] + [(0, 5)]
+    angles = [(i, i + 1, i + 2) for i in range(natoms - 2)]
+    diheds = [(i, i + 1, i + 2, i + 3) for i in range(natoms - 3)]
+    q, B, H = oi.evaluate(pos, (), bonds, angles, diheds)
+    coords = bonds + angles + diheds
+    hess = []
+    blocks = []
+    for atoms, Hd in zip(coords, H):
+        m = len(atoms)
+        vals = np.zeros((m, 3, m, 3))
+        for ia, a in enumerate(atoms):
+            for ja, a2 in enumerate(atoms):
+                vals[ia, :, ja, :] = Hd[3 * a:3 * a + 3, 3 * a2:3 * a2 + 3]
+        hess.append(ref.linalg.SparseInternalHessian(natoms, list(atoms), vals))
+        blocks.append(vals)
+    D = ref.linalg.SparseInternalHessians(hess, 3 * natoms)
+    v = rng.normal(size=len(coords))
+    w = rng.normal(size=3 * natoms)
+    out = dict(pos=pos, bonds=np.array(bonds), angles=np.array(angles), dihedrals=np.array(diheds), v=v, w=w,
+               ldot=D.ldot(v), rdot=D.rdot(w), ddot=D.ddot(w, w))
+    for i, b in enumerate(blocks):
+        out["vals%d" % i] = b
+    save("sparse_hessians", **out)
+
+
 def main():
     golden_rotation()
     if "--rotation-only" in sys.argv:
@@ -338,6 +372,7 @@ def main():
     golden_steppers(ref)
     golden_restricted(ref)
     golden_loop(ref)
+    golden_sparse_hessians(ref)
 
 
 if __name__ == "__main__":
