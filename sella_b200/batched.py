@@ -943,7 +943,8 @@ class BatchedSella:
         # (eigensolvers.py:31-66: A is the projected operator of peswrapper.py:531-537)
         nfree = self.cons["nfree"] if self.cons is not None else (self.nfree if getattr(self, "fmask", None) is not None else n)
         maxiter_eff = nfree if self.diag_maxiter is None else min(nfree, int(self.diag_maxiter))
-        rounds = nstart                 # operator products so far (the reference's subspace size)
+        rounds = nstart                 # host-side bound on the operator products so far
+        restarted = False               # after a thick restart ksz no longer counts the products (see below)
         kbound = nstart                 # host-side bound on the current subspace sizes ksz[b]
         hbound = nstart                 # ... and on the history lengths nhist[b]
         while True:
@@ -951,7 +952,10 @@ class BatchedSella:
                  I(maxiter_eff), _p(self.lams), _p(self.rv), _p(self.theta), _p(self.dav_state),
                  _p(self.status), I(b), _stream())
             m = (self.dav_state == DAV_EXPAND).to(torch.int32)
-            if int(m.sum().item()) == 0 or rounds >= maxiter_eff:
+            # sb_davidson_rr stops each system at ksz[b] >= maxiter on its own (systems start with different
+            # numbers of vectors, so the host count `rounds` is only an upper bound); once a thick restart has
+            # clamped ksz the host count is what ends the run at the reference's total
+            if int(m.sum().item()) == 0 or (restarted and rounds >= maxiter_eff):
                 break
             if kbound >= kc:
                 # The device subspace is full where the reference would go on (up to min(n, maxiter) vectors,
@@ -963,7 +967,7 @@ class BatchedSella:
                 self._flush_history(part, min(hbound, kc), nl)
                 self.nhist.zero_()
                 self.ksz.copy_(torch.where(m > 0, torch.clamp(self.ksz, max=keep), self.ksz))
-                kbound, hbound, first = keep, 0, False
+                kbound, hbound, first, restarted = keep, 0, False, True
             lanczos = int(self.eigensolver == 2)
             if first or lanczos:
                 tin = None

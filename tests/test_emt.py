@@ -134,6 +134,40 @@ def test_engine_on_emt_surface_matches_oracle(case):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kdiag", [2, 5])
+def test_engine_on_emt_clusters_bench_setting(kdiag):
+    """The setting bench.py runs for the C2/C3 workloads: Davidson capped at `kdiag` vectors, re-run every
+    3rd step.  Systems enter a re-diagonalisation with DIFFERENT numbers of start vectors (one per negative
+    eigenvalue of the preconditioner), so the per-system cap must be honoured per system."""
+    torch = pytest.importorskip("torch")
+    from sella_b200.batched import BatchedSella
+    from sella_b200.emt import EMTSurface
+    from oracle.pes import CartesianPES
+    from oracle.driver import SaddleSearch
+    dev = torch.device("cuda:0")
+    nat, nsys = 20, 8
+    geoms = [fcc_cluster(nat, seed=40 + b, rattle=0.08) for b in range(nsys)]
+    C = _com_constraints(nat)
+    kw = dict(method="prfo", rs="tr", diag_maxiter=kdiag, diag_every_n=3)
+    x0 = np.stack([g.ravel() for g in geoms])
+    surf = EMTSurface(nsys, nat, dev, cell=None, pbc=(False,) * 3)
+    eng = BatchedSella(surf, torch.from_numpy(x0).to(dev), constraints=(C, None), **kw)
+    oracles = []
+    for b in range(nsys):
+        p = CartesianPES(oemt.emt_func(None, (False,) * 3), x0[b], C, C @ x0[b])
+        oracles.append((p, SaddleSearch(p, **kw)))
+    nstart = set()
+    for t in range(10):
+        eng.step()
+        nstart.update(eng.ninit.cpu().numpy().tolist())
+        x = eng.x.cpu().numpy()
+        for b, (p, o) in enumerate(oracles):
+            o.step()
+            np.testing.assert_allclose(x[b], p.get_x(), rtol=0, atol=1e-7, err_msg="system %d step %d" % (b, t))
+    eng.check_status()
+
+
+@pytest.mark.gpu
 def test_readme_example_cu111_adatom():
     """BASELINE.json config C1 = the reference's README example (README.md:17-38): Cu(111) 5x5x6 slab
     + adatom on a bridge site, atoms below the middle of the cell fixed with fix_translation,
