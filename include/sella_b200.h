@@ -371,6 +371,18 @@ int sb_rfo_ras_c(const double* Vg, const double* evals, const double* Vt, const 
                  int mode, double* s, double* smag, double* alpha, int32_t* status, const int32_t* active,
                  const double* sadd, int npole, const int32_t* rowmap, const double* gperp, const double* gam,
                  long long vstride, int batch, void* stream);
+/* MaxInternalStep (sella/optimize/restricted_step.py:186-243, the default restricted step of
+ * Sella(internal=True), optimize.py:166-168): cons(s) = max_j |s_j w_j| over the n internal coordinates.
+ * The model is a list of npole poles (evals[b,npole], Vg[b,npole]); pole i's eigenvector, lifted to the
+ * n internal coordinates, is row i of Wt[b] (vstride doubles per system, row length n); the step is
+ * s = sum_i c_i(alpha) Wt[i,:] + sadd with alpha solving cons(s) = delta (interior step when cons < delta
+ * at the model's alpha0).  w [n] is shared by the batch (wx/wb/wa/wd per coordinate kind, :222-243).   */
+int sb_qn_mis(const double* Vg, const double* evals, const double* Wt, const double* delta, int order, int n,
+              double* s, double* smag, double* alpha, int32_t* status, const int32_t* active, const double* sadd,
+              int npole, long long vstride, const double* w, int batch, void* stream);
+int sb_rfo_mis(const double* Vg, const double* evals, const double* Wt, const double* delta, int order, int n,
+               int mode, double* s, double* smag, double* alpha, int32_t* status, const int32_t* active,
+               const double* sadd, int npole, long long vstride, const double* w, int batch, void* stream);
 int sb_davidson_init_c(const double* v0, const double* pl, const double* Pvt, int mode, double* V, int kcap, int n,
                        int32_t* ksz, int32_t* ninit, int32_t* nhist, int32_t* dav_state, int32_t* status,
                        const int32_t* part, const int32_t* mrows, const double* lam0, const double* gperp,

@@ -35,6 +35,7 @@ _QN_NAMES = ("qn", "quasi-newton", "quasi newton", "newton", "mmf",
              "minimum mode following", "minimum-mode following", "dimer")
 _TR_NAMES = ("tr", "trust region", "trust-region", "trust radius", "trust-radius")
 _RAS_NAMES = ("ras", "restricted atomic step")
+_MIS_NAMES = ("mis", "max internal step")
 
 DAV_EXPAND, DAV_DONE, DAV_IDLE = 0, 1, 2
 
@@ -107,6 +108,10 @@ class BatchedSella:
             self.rs = "ras"
             if n % 3:
                 raise ValueError("restricted atomic step needs 3N coordinates")
+        elif rs in _MIS_NAMES:
+            if not getattr(self, "_internal", False):          # restricted_step.py:192-196
+                raise ValueError("Internal coordinates are required for the MaxInternalStep trust region method")
+            self.rs = "mis"
         else:
             raise ValueError("Unknown restricted step name: {}".format(rs))
         self.eig = d["eig"] if eig is None else bool(eig)
@@ -138,7 +143,7 @@ class BatchedSella:
         self._updates_since_refresh = 0
 
         delta0 = d["delta0"] if delta0 is None else delta0
-        delta_init = delta0 if self.rs == "ras" else delta0 * n
+        delta_init = delta0 if self.rs in ("ras", "mis") else delta0 * n      # optimize.py:183-187
         self._dpar = (ctypes.c_double * 5)(
             d["rho_inc"] if rho_inc is None else rho_inc,
             d["rho_dec"] if rho_dec is None else rho_dec,
@@ -922,6 +927,10 @@ class BatchedSella:
             v0 = self.cons["pg"]
             v0.copy_(self.g)
             self._project_free(v0.view(b, 1, n), 1, 1, part)            # Ufree^T g, lifted (peswrapper.py:524)
+        use_v0 = first
+        v0s = self._diag_start_vector(part)
+        if v0s is not None:
+            v0, use_v0 = v0s, True
         if self.compact:
             if not first:
                 self._refresh_poles(part)          # g_perp of the CURRENT complement (fallback start vector)
@@ -932,16 +941,16 @@ class BatchedSella:
                  I(kc), I(n), _p(self.ksz), _p(self.ninit), _p(self.nhist), _p(self.dav_state), _p(self.status),
                  _p(part), _p(self.sp.mrows), _p(self.lam0), _p(self.gperp), LL(n), LL(n * n), I(b), _stream())
         else:
-            call("sb_davidson_init", _p(v0), _p(self.evals), _p(self.Vt), I(0 if first else 1), _p(self.V),
+            call("sb_davidson_init", _p(v0), _p(self.evals), _p(self.Vt), I(0 if use_v0 else 1), _p(self.V),
                  I(kc), I(n), _p(self.ksz), _p(self.ninit), _p(self.nhist), _p(self.dav_state), _p(self.status),
                  _p(part), I(b), _stream())
-        nstart = 1 if first else int(self.ninit.max().item())
+        nstart = 1 if use_v0 else int(self.ninit.max().item())
         for j in range(nstart):
             m = ((self.dav_state == DAV_EXPAND) & (self.ninit > j)).to(torch.int32)
             self._hvp(self.V[:, j], kc * n, m, 1, m)
         # rayleigh_ritz stops at min(n, maxiter) vectors with n the dimension of the FREE space
         # (eigensolvers.py:31-66: A is the projected operator of peswrapper.py:531-537)
-        nfree = self.cons["nfree"] if self.cons is not None else (self.nfree if getattr(self, "fmask", None) is not None else n)
+        nfree = self._free_dim()
         maxiter_eff = nfree if self.diag_maxiter is None else min(nfree, int(self.diag_maxiter))
         rounds = nstart                 # host-side bound on the operator products so far
         restarted = False               # after a thick restart ksz no longer counts the products (see below)
@@ -1007,6 +1016,17 @@ class BatchedSella:
         if hbound > 0:
             self._flush_history(part, min(hbound, kc), nl)
         self.ndiag += 1
+
+    def _free_dim(self):
+        """Dimension of the space the Davidson operator acts in (Ufree.shape[1], peswrapper.py:513-514)."""
+        if self.cons is not None:
+            return self.cons["nfree"]
+        return self.nfree if getattr(self, "fmask", None) is not None else self.n
+
+    def _diag_start_vector(self, part):
+        """Hook: a start vector that overrides the choice made from the model (internal coordinates: the first
+        diagonalisation starts from Ufree^T g although a model Hessian exists, peswrapper.py:521-528)."""
+        return None
 
     def _flush_history(self, part, nv, nl):
         """PES.diag tail (peswrapper.py:541-551): Ritz-rotate the operator history and feed it to the

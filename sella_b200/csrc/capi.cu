@@ -375,6 +375,26 @@ int sb_rfo_ras_c(const double* Vg, const double* evals, const double* Vt, const 
     return sb_rfo_ras_c_impl(Vg, evals, Vt, delta, order, n, mode, s, smag, alpha, status, active, sadd, npole, rowmap,
                              gperp, gam, vstride, batch, ST);
 }
+extern "C" int sb_qn_mis_impl(const double*, const double*, const double*, const double*, int, int, double*, double*,
+                              double*, int*, const int*, const double*, int, long long, const double*, int,
+                              cudaStream_t);
+extern "C" int sb_rfo_mis_impl(const double*, const double*, const double*, const double*, int, int, int, double*,
+                               double*, double*, int*, const int*, const double*, int, long long, const double*, int,
+                               cudaStream_t);
+int sb_qn_mis(const double* Vg, const double* evals, const double* Wt, const double* delta, int order, int n,
+              double* s, double* smag, double* alpha, int32_t* status, const int32_t* active, const double* sadd,
+              int npole, long long vstride, const double* w, int batch, void* stream) {
+    if (npole < 1 || n < 1 || !w) return -1;
+    return sb_qn_mis_impl(Vg, evals, Wt, delta, order, n, s, smag, alpha, status, active, sadd, npole, vstride, w, batch,
+                          ST);
+}
+int sb_rfo_mis(const double* Vg, const double* evals, const double* Wt, const double* delta, int order, int n,
+               int mode, double* s, double* smag, double* alpha, int32_t* status, const int32_t* active,
+               const double* sadd, int npole, long long vstride, const double* w, int batch, void* stream) {
+    if (npole < 1 || n < 1 || mode < 0 || mode > 1 || !w) return -1;
+    return sb_rfo_mis_impl(Vg, evals, Wt, delta, order, n, mode, s, smag, alpha, status, active, sadd, npole, vstride, w,
+                           batch, ST);
+}
 int sb_davidson_init_c(const double* v0, const double* pl, const double* Pvt, int mode, double* V, int kcap, int n,
                        int32_t* ksz, int32_t* ninit, int32_t* nhist, int32_t* dav_state, int32_t* status,
                        const int32_t* part, const int32_t* mrows, const double* lam0, const double* gperp,

@@ -292,7 +292,8 @@ rfo_ras_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_
                double* __restrict__ smag, double* __restrict__ alpha_out, int* __restrict__ status,
                const int* __restrict__ active, const double* __restrict__ sadd_, int np,
                const int* __restrict__ rowmap_, const double* __restrict__ gperp_, const double* __restrict__ gam_,
-               long long vstride) {
+               long long vstride, const double* __restrict__ wmis) {
+    // wmis != NULL: MaxInternalStep measure max_j |s_j w_j| over the n internal coordinates (restricted_step.py:206-216)
     // np poles (np = n for the dense representation); pole i -> eigenvector row rowmap[i] of Vt
     // (NULL: row i; -1: the unit vector gperp/gam; -2: padding), as in qn_ras_kernel
     const int b = blockIdx.x;
@@ -397,6 +398,12 @@ rfo_ras_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_
         }
         __syncthreads();
         double bv = -1.0; int bi = 0;
+        if (wmis) {
+            for (int j = tid; j < n; j += nt) {
+                const double nr = fabs(s[j] * wmis[j]);
+                if (nr > bv) { bv = nr; bi = j; }
+            }
+        } else
         for (int a = tid; a < natoms; a += nt) {
             const double x = s[3 * a], y = s[3 * a + 1], z = s[3 * a + 2];
             const double nr = sqrt(x * x + y * y + z * z);
@@ -414,6 +421,8 @@ rfo_ras_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_
             for (int w = 1; w < nt / 32; ++w)
                 if (best_val[w] > bv || (best_val[w] == bv && best_idx[w] < bi)) { bv = best_val[w]; bi = best_idx[w]; }
             val = bv;
+            if (wmis) dval = (s[bi] < 0.0 ? -1.0 : (s[bi] > 0.0 ? 1.0 : 0.0)) * ds[bi] * wmis[bi];
+            else
             dval = (ds[3 * bi] * s[3 * bi] + ds[3 * bi + 1] * s[3 * bi + 1] + ds[3 * bi + 2] * s[3 * bi + 2]) /
                    fmax(bv, 1e-12);
             int go = 1;
@@ -478,17 +487,18 @@ extern "C" int sb_rfo_tr_impl(const double* Vg, const double* evals, const doubl
     return SB_LAUNCH_CHECK();
 }
 
-extern "C" int sb_rfo_ras_c_impl(const double* Vg, const double* evals, const double* Vt, const double* delta,
-                                 int order, int n, int mode, double* s, double* smag, double* alpha, int* status,
-                                 const int* active, const double* sadd, int np, const int* rowmap, const double* gperp,
-                                 const double* gam, long long vstride, int batch, cudaStream_t st) {
+static int launch_rfo_ras(const double* Vg, const double* evals, const double* Vt, const double* delta,
+                          int order, int n, int mode, double* s, double* smag, double* alpha, int* status,
+                          const int* active, const double* sadd, int np, const int* rowmap, const double* gperp,
+                          const double* gam, long long vstride, const double* wmis, int batch, cudaStream_t st) {
     const int npl = (np + 31) / 32;
     const size_t smem = (size_t)(2 * np + 2 * n) * sizeof(double) + (size_t)(np + 2) * sizeof(int);
+    if (smem > 200 * 1024) return -2;
     SB_COUNT(1);
 #define SB_RFOR(N)                                                                                             \
     cudaFuncSetAttribute(rfo_ras_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
     rfo_ras_kernel<N><<<batch, 256, smem, st>>>(Vg, evals, Vt, delta, order, n, mode, s, smag, alpha, status, \
-                                                active, sadd, np, rowmap, gperp, gam, vstride)
+                                                active, sadd, np, rowmap, gperp, gam, vstride, wmis)
     if (npl <= 4) { SB_RFOR(4); }
     else if (npl <= 8) { SB_RFOR(8); }
     else if (npl <= 12) { SB_RFOR(12); }
@@ -499,6 +509,24 @@ extern "C" int sb_rfo_ras_c_impl(const double* Vg, const double* evals, const do
     else return -2;
 #undef SB_RFOR
     return SB_LAUNCH_CHECK();
+}
+
+extern "C" int sb_rfo_ras_c_impl(const double* Vg, const double* evals, const double* Vt, const double* delta,
+                                 int order, int n, int mode, double* s, double* smag, double* alpha, int* status,
+                                 const int* active, const double* sadd, int np, const int* rowmap, const double* gperp,
+                                 const double* gam, long long vstride, int batch, cudaStream_t st) {
+    return launch_rfo_ras(Vg, evals, Vt, delta, order, n, mode, s, smag, alpha, status, active, sadd, np, rowmap, gperp,
+                          gam, vstride, nullptr, batch, st);
+}
+
+// MaxInternalStep with the rfo / prfo models: see sb_qn_mis_impl
+extern "C" int sb_rfo_mis_impl(const double* Vg, const double* evals, const double* Wt, const double* delta, int order,
+                               int n, int mode, double* s, double* smag, double* alpha, int* status,
+                               const int* active, const double* sadd, int np, long long vstride, const double* w,
+                               int batch, cudaStream_t st) {
+    if (!w) return -1;
+    return launch_rfo_ras(Vg, evals, Wt, delta, order, n, mode, s, smag, alpha, status, active, sadd, np, nullptr,
+                          nullptr, nullptr, vstride, w, batch, st);
 }
 
 extern "C" int sb_rfo_ras_impl(const double* Vg, const double* evals, const double* Vt, const double* delta, int order,

@@ -117,7 +117,10 @@ qn_ras_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_,
               const double* __restrict__ delta_, int order, int n, double* __restrict__ s_out,
               double* __restrict__ smag, double* __restrict__ alpha_out, int* __restrict__ status,
               const int* __restrict__ active, const double* __restrict__ sadd_, int np, const int* __restrict__ rowmap_,
-              const double* __restrict__ gperp_, const double* __restrict__ gam_, long long vstride) {
+              const double* __restrict__ gperp_, const double* __restrict__ gam_, long long vstride,
+              const double* __restrict__ wmis) {
+    // wmis != NULL: MaxInternalStep (restricted_step.py:206-216) -- the measure is max_j |s_j w_j| over the
+    // n internal coordinates (weights wmis[n], shared by the batch) instead of the largest atomic displacement
     const int b = blockIdx.x;
     if (active && !active[b]) return;
     extern __shared__ double sm[];
@@ -172,6 +175,12 @@ qn_ras_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_,
         __syncthreads();
         // cons: largest atomic displacement (first maximum, as numpy argmax)
         double bv = -1.0; int bi = 0;
+        if (wmis) {
+            for (int j = tid; j < n; j += nt) {
+                const double nr = fabs(s[j] * wmis[j]);
+                if (nr > bv) { bv = nr; bi = j; }
+            }
+        } else
         for (int a = tid; a < natoms; a += nt) {
             const double x = s[3 * a], y = s[3 * a + 1], z = s[3 * a + 2];
             const double nr = sqrt(x * x + y * y + z * z);
@@ -188,6 +197,8 @@ qn_ras_kernel(const double* __restrict__ Vg_, const double* __restrict__ evals_,
         for (int w = 1; w < nt / 32; ++w)
             if (best_val[w] > bv || (best_val[w] == bv && best_idx[w] < bi)) { bv = best_val[w]; bi = best_idx[w]; }
         S.val = bv;
+        if (wmis) S.dval = (s[bi] < 0.0 ? -1.0 : (s[bi] > 0.0 ? 1.0 : 0.0)) * ds[bi] * wmis[bi];
+        else
         S.dval = (ds[3 * bi] * s[3 * bi] + ds[3 * bi + 1] * s[3 * bi + 1] + ds[3 * bi + 2] * s[3 * bi + 2]) /
                  fmax(bv, 1e-12);
         __syncthreads();
@@ -343,16 +354,36 @@ extern "C" int sb_qn_tr_impl(const double* Vg, const double* evals, const double
     return SB_LAUNCH_CHECK();
 }
 
+static int launch_qn_ras(const double* Vg, const double* evals, const double* Vt, const double* delta,
+                         int order, int n, double* s, double* smag, double* alpha, int* status,
+                         const int* active, const double* sadd, int np, const int* rowmap, const double* gperp,
+                         const double* gam, long long vstride, const double* wmis, int batch, cudaStream_t st) {
+    const size_t smem = (size_t)(4 * np + 2 * n + SB_SCRATCH_DOUBLES) * sizeof(double) + (size_t)(np + 2) * sizeof(int);
+    if (smem > 200 * 1024) return -2;
+    cudaFuncSetAttribute(qn_ras_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SB_COUNT(1);
+    qn_ras_kernel<<<batch, TR_THREADS, smem, st>>>(Vg, evals, Vt, delta, order, n, s, smag, alpha, status, active,
+                                                   sadd, np, rowmap, gperp, gam, vstride, wmis);
+    return SB_LAUNCH_CHECK();
+}
+
 extern "C" int sb_qn_ras_c_impl(const double* Vg, const double* evals, const double* Vt, const double* delta,
                                 int order, int n, double* s, double* smag, double* alpha, int* status,
                                 const int* active, const double* sadd, int np, const int* rowmap, const double* gperp,
                                 const double* gam, long long vstride, int batch, cudaStream_t st) {
-    const size_t smem = (size_t)(4 * np + 2 * n + SB_SCRATCH_DOUBLES) * sizeof(double) + (size_t)(np + 2) * sizeof(int);
-    cudaFuncSetAttribute(qn_ras_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    SB_COUNT(1);
-    qn_ras_kernel<<<batch, TR_THREADS, smem, st>>>(Vg, evals, Vt, delta, order, n, s, smag, alpha, status, active,
-                                                   sadd, np, rowmap, gperp, gam, vstride);
-    return SB_LAUNCH_CHECK();
+    return launch_qn_ras(Vg, evals, Vt, delta, order, n, s, smag, alpha, status, active, sadd, np, rowmap, gperp, gam,
+                         vstride, nullptr, batch, st);
+}
+
+// MaxInternalStep: npole poles whose eigenvector rows (length n = number of internal coordinates) are the
+// first npole rows of Wt[b] (vstride doubles per system); weights w[n]
+extern "C" int sb_qn_mis_impl(const double* Vg, const double* evals, const double* Wt, const double* delta,
+                              int order, int n, double* s, double* smag, double* alpha, int* status,
+                              const int* active, const double* sadd, int np, long long vstride, const double* w,
+                              int batch, cudaStream_t st) {
+    if (!w) return -1;
+    return launch_qn_ras(Vg, evals, Wt, delta, order, n, s, smag, alpha, status, active, sadd, np, nullptr, nullptr,
+                         nullptr, vstride, w, batch, st);
 }
 
 extern "C" int sb_qn_ras_impl(const double* Vg, const double* evals, const double* Vt, const double* delta,

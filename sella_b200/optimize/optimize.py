@@ -353,16 +353,142 @@ class _PESView:
         return diff, diff, g0
 
 
+class _InternalPESView:
+    """`dyn.pes` of an internal-coordinate search: the reference's InternalPES duck type
+    (sella/peswrapper.py:609-1288) as views over the engine state of this one search."""
+    n_cell_dof = 0
+    dummies = None
+
+    def __init__(self, opt):
+        self._o = opt
+        self._saved = None
+
+    _e = property(lambda self: self._o._eng)
+    atoms = property(lambda self: self._o.atoms)
+    int = property(lambda self: self._o.internal)
+    cons = property(lambda self: self._o.internal.cons)
+    dim = property(lambda self: self._e.n)
+    ncart = property(lambda self: self._e.ncart)
+    neval = property(lambda self: self._o._surface.neval)
+    eta = property(lambda self: self._e.eta)
+    traj = property(lambda self: self._o._surface.traj)
+    hessian_function = None
+    apos = property(lambda self: self._e.pos[0].cpu().numpy().reshape((-1, 3)))
+
+    def get_x(self):
+        return self._e.x[0].cpu().numpy()
+
+    def get_f(self):
+        self._e.ensure_evaluated()
+        return float(self._e.f[0])
+
+    def get_g(self):
+        self._e.ensure_evaluated()
+        return self._e.g[0].cpu().numpy()
+
+    @property
+    def H(self):
+        return _HessianView(self._e.n, self._e.B[0].cpu().numpy())
+
+    def get_H(self):
+        return self.H
+
+    def _np(self, key):
+        return self._e.geo[key][0].cpu().numpy()
+
+    def get_Unred(self):
+        return self._np("Q")
+
+    def get_Ucons(self):
+        if not self._e.nc:
+            return np.zeros((self._e.n, 0))
+        return self._np("Q") @ self._np("Vc")
+
+    def get_Ufree(self):
+        """An orthonormal basis of the free space (peswrapper.py:1050-1082); any basis of that space serves the
+        callers (column order and rotation within the space are not defined by the reference either)."""
+        Q = self._np("Q")
+        if not self._e.nc:
+            return Q
+        from scipy.linalg import qr
+        Vc = self._np("Vc")
+        full = qr(Vc, mode="full")[0]
+        return Q @ full[:, Vc.shape[1]:]
+
+    def get_drdx(self):
+        if not self._e.nc:
+            return np.zeros((0, self._e.n))
+        return self._np("red") @ self._np("Q").T
+
+    def get_res(self):
+        return self._np("res") if self._e.nc else np.zeros(0)
+
+    def get_Hc(self):
+        e = self._e
+        if not e.nc:
+            return np.zeros((e.n, e.n))
+        e.ensure_evaluated()
+        if not e.geo.get("model"):
+            e._model()
+        Q = self._np("Q")
+        return Q @ self._np("HcR") @ Q.T
+
+    def get_HL(self):
+        return self.get_H() - self.get_Hc()
+
+    def get_HL_projected(self, U):
+        return self.get_HL().project(U)
+
+    def get_projected_forces(self):
+        self.converged(0.0)
+        g, Uf = self.get_g(), self.get_Ufree()
+        return -((Uf @ (Uf.T @ g)) @ self._np("Bw")).reshape((-1, 3))
+
+    @property
+    def curr(self):
+        e = self._e
+        ev = e._evaluated
+        return dict(x=self.get_x(), f=float(e.f[0]) if ev else None, g=e.g[0].cpu().numpy() if ev else None)
+
+    def converged(self, fmax, cmax=1e-5):
+        e = self._e
+        e.converged(fmax, cmax)
+        c1 = float(np.linalg.norm(self.get_res())) if e.nc else 0.0
+        return bool(e.conv[0]), float(e.fmax[0]), c1
+
+    def diag(self, gamma=0.1, threepoint=False, maxiter=None):
+        e = self._e
+        e.ensure_evaluated()
+        old = (e.gamma, e.diag_maxiter)
+        e.gamma, e.diag_maxiter = float(gamma), maxiter
+        try:
+            e._run_diag(None)
+        finally:
+            e.gamma, e.diag_maxiter = old
+        self._o._check()
+
+    def kick(self, dx, diag=False, **diag_kwargs):
+        e = self._e
+        d = torch.from_numpy(np.asarray(dx, dtype=np.float64).reshape(1, -1).copy()).to(e.x.device)
+        rho = float(e.kick(d, diag=diag)[0])
+        self._o._check()
+        return rho
+
+
 class Sella(_Base):
     def __init__(self, atoms, restart=None, logfile='-', trajectory=None, master=None, delta0=None,
                  sigma_inc=None, sigma_dec=None, rho_dec=None, rho_inc=None, order=1, eig=None, eta=1e-4,
                  method=None, gamma=0.1, threepoint=False, constraints=None, constraints_tol=1e-5, v0=None,
                  internal=False, append_trajectory=False, rs=None, nsteps_per_diag=3, diag_every_n=None,
                  hessian_function=None, optimize_cell=False, **kwargs):
-        if internal:
-            raise NotImplementedError("internal coordinates are not on the CUDA path yet")
         if optimize_cell:
             raise NotImplementedError("optimize_cell is not on the CUDA path")
+        if internal:
+            return self._init_internal(atoms, restart, logfile, trajectory, master, order, eig, eta, method, gamma,
+                                       threepoint, constraints, constraints_tol, v0, internal, append_trajectory, rs,
+                                       nsteps_per_diag, diag_every_n, hessian_function,
+                                       dict(delta0=delta0, sigma_inc=sigma_inc, sigma_dec=sigma_dec, rho_dec=rho_dec,
+                                            rho_inc=rho_inc), kwargs)
         pbc = np.asarray(getattr(atoms, "pbc", [False] * 3))
         proj_trans = kwargs.pop("proj_trans", None)
         proj_rot = kwargs.pop("proj_rot", None)
@@ -429,6 +555,75 @@ class Sella(_Base):
         self.constraints_tol = constraints_tol
         self.fmax = None
 
+    # ------------------------------------------------------------------ internal coordinates
+    def _init_internal(self, atoms, restart, logfile, trajectory, master, order, eig, eta, method, gamma, threepoint,
+                       constraints, constraints_tol, v0, internal, append_trajectory, rs, nsteps_per_diag,
+                       diag_every_n, hessian_function, trust, kwargs):
+        """optimize.py:237-280: `internal=True` builds the coordinate list with the three finders on a copy,
+        `internal=<Internals>` takes the list as given (constraints then belong to the Internals object)."""
+        from ..topology import Internals
+        if hessian_function is not None or v0 is not None:
+            raise NotImplementedError("hessian_function / v0 together with internal coordinates are not on the CUDA path")
+        if isinstance(internal, Internals):
+            auto = False
+            if constraints is not None:
+                raise ValueError("Internals object and Constraint object cannot both be provided to Sella. "
+                                 "Instead, you must pass the Constraints object to the constructor of the "
+                                 "Internals object.")
+        else:
+            auto = True
+            internal = Internals(atoms, cons=constraints)
+        self.user_internal = internal
+        self._auto_internals = auto
+        self.constraints = None
+        eigensolver = kwargs.pop("eigensolver", "jd0")
+        diag_maxiter = kwargs.pop("diag_maxiter", None)
+        exact_geodesic = kwargs.pop("exact_geodesic", None)
+        if kwargs.pop("iterative_stepper", 0):
+            raise NotImplementedError("iterative_stepper is not on the CUDA path (the geodesic integrator is)")
+        if kwargs:
+            raise TypeError("unsupported keyword arguments: %s" % sorted(kwargs))
+        if trajectory is not None and not hasattr(trajectory, "write"):
+            if not _HAVE_ASE:
+                raise NotImplementedError("trajectory=<file name> needs ASE (ase.io.trajectory.Trajectory); "
+                                          "pass an object with a write() method or install ASE")
+            from ase.io.trajectory import Trajectory
+            trajectory = Trajectory(trajectory, mode="a" if append_trajectory else "w", atoms=atoms, master=master)
+        if restart is not None and not _HAVE_ASE:
+            raise NotImplementedError("restart files are handled by ASE's Optimizer, which is not installed")
+        _Base.__init__(self, atoms, restart=restart, logfile=logfile, trajectory=None, master=master)
+        self._surface = _CalculatorSurface(atoms, traj=trajectory)
+        if order != 0 and eig is False:
+            warnings.warn("Saddle point optimizations with eig=False will most likely fail!\n Proceeding anyway, "
+                          "but you shouldn't be optimistic.")
+        self._ikw = dict(order=order, eig=eig, eta=eta, method=method, gamma=gamma, rs='mis' if rs is None else rs,
+                         nsteps_per_diag=nsteps_per_diag, diag_every_n=diag_every_n, eigensolver=eigensolver,
+                         threepoint=threepoint, diag_maxiter=diag_maxiter,
+                         exact_geodesic=True if exact_geodesic is None else exact_geodesic, **trust)
+        self._hessian_function = None
+        self._build_internal_engine()
+        self.ord = order
+        self.eta = eta
+        self.constraints_tol = constraints_tol
+        self.fmax = None
+
+    def _build_internal_engine(self):
+        """InternalPES.__init__ (peswrapper.py:609-661): coordinate list (copy + finders), model Hessian."""
+        from ..batched_internal import BatchedInternalSella
+        ints = self.user_internal.copy()
+        if self._auto_internals:
+            ints.find_all_bonds()
+            ints.find_all_angles()
+            ints.find_all_dihedrals()
+        rows, targets = ints.constraint_rows()
+        self.internal = ints
+        x0 = torch.from_numpy(np.asarray(self.atoms.positions, dtype=np.float64).reshape(1, -1).copy()).to(dev())
+        self._eng = BatchedInternalSella(self._surface, x0, ints.device_coordinates(), cons_rows=rows,
+                                         cons_targets=targets if len(rows) else None,
+                                         h0=np.diag(ints.guess_hessian()), atol=ints.atol * 180.0 / np.pi,
+                                         kcap=16, **self._ikw)
+        self.pes = _InternalPESView(self)
+
     def _wrap_hessian(self, fn):
         """hessian_function(atoms) -> (3N, 3N) ndarray, as in the reference (optimize.py:76)."""
         if fn is None:
@@ -459,6 +654,15 @@ class Sella(_Base):
     def step(self):
         self._eng.step()
         self._check()
+        if getattr(self, "internal", None) is not None and bool(self._eng.bad_internals()[0]):
+            # optimize.py:382-410: an angle has come close to 0 or pi -- new coordinate list, new PES object,
+            # the trust radius is kept
+            if not self._auto_internals:
+                raise RuntimeError("an angle of the user-supplied Internals has become linear; re-detection of the "
+                                   "coordinate list needs internal=True")
+            delta = self._eng.delta.clone()
+            self._build_internal_engine()
+            self._eng.delta.copy_(delta)
 
     def _check(self):
         st = int(self._eng.status[0])
@@ -469,7 +673,8 @@ class Sella(_Base):
             warnings.warn("sella_b200: Davidson stopped at the subspace capacity (32 vectors)")
             self._eng.status &= ~8
         self._eng.check_status()
-        self.atoms.positions = self._eng.x[0].cpu().numpy().reshape((-1, 3))
+        cart = self._eng.pos if getattr(self, "internal", None) is not None else self._eng.x
+        self.atoms.positions = cart[0].cpu().numpy().reshape((-1, 3))
 
     def converged(self, forces=None):
         fmax = self.fmax if self.fmax is not None else 0.05
