@@ -23,7 +23,7 @@ Dormand-Prince 5(4) steps with PER-SYSTEM step control (the reference calls scip
 atol 1e-6; this scheme runs at rtol 1e-6 / atol 1e-8 and is restated in oracle/internal_pes.py for
 step-by-step parity), followed by the Newton projection onto the constraint manifold (:928-994).
 
-Not on the device (status bit 64 / NotImplementedError): a rank-deficient Wilson matrix (the
+Not on the device (status bit 256 / NotImplementedError): a rank-deficient Wilson matrix (the
 reference's SVD branch, :691-704 -- free molecules without translation/rotation coordinates),
 dummy atoms, the iterative stepper, the "violation alone exceeds the radius" branch of the
 restricted step, re-detection of the coordinate list when an angle becomes linear (the engine
@@ -36,8 +36,8 @@ from . import kernels as K
 from ._lib import I, D, LL, _p, _stream, call, check_f64
 from .batched import BatchedSella, DAV_EXPAND
 
-SB_ST_WILSON_RANK = 64
-SB_ST_GEODESIC = 128
+SB_ST_WILSON_RANK = 256        # (1..64 are the library's SB_ST_* bits, include/sella_b200.h)
+SB_ST_GEODESIC = 512
 
 # Dormand-Prince 5(4)
 _C = (0.0, 1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0)
@@ -82,7 +82,7 @@ class BatchedInternalSella(BatchedSella):
                  weights=(1.0, 1.0, 1.0, 1.0), exact_geodesic=True, rs=None, atol=15.0, **kw):
         """surface: Cartesian evaluator (`evaluate(x[b, ncart], f, g, active)`); pos0 [b, ncart];
         ints: BatchedInternals; cons_rows: positions of the constrained coordinates within it, held at
-        cons_targets [nc] / [b, nc] (None / NaN: their values at pos0); h0 [nint]: diagonal model Hessian
+        cons_targets [nc] / [b, nc] (None / NaN: their values at pos0); h0 [nint] or [b, nint]: diagonal model Hessian
         (Internals.guess_hessian), projected onto range(Bw) as the reference does, or H0 [b, nint, nint];
         weights: (wx, wb, wa, wd) of MaxInternalStep."""
         check_f64(pos0)
@@ -128,7 +128,7 @@ class BatchedInternalSella(BatchedSella):
             if cons_targets is None:
                 tg = cur.clone()
             else:
-                t = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(
+                t = torch.from_numpy(np.array(np.broadcast_to(
                     np.asarray(cons_targets, dtype=np.float64), (b, self.nc)))).to(dev)
                 tg = torch.where(torch.isnan(t), cur, t)
         self.targets = tg
@@ -146,9 +146,9 @@ class BatchedInternalSella(BatchedSella):
             if h0 is None:
                 raise ValueError("internal coordinates need the diagonal model Hessian h0 (Internals.guess_hessian) "
                                  "or a full H0")
-            h = torch.as_tensor(np.asarray(h0, dtype=np.float64)).to(dev)
+            h = torch.from_numpy(np.array(h0, dtype=np.float64)).to(dev)
             Qm = self.geo["Q"]
-            core = K.gemm(Qm, (h.view(1, n, 1) * Qm).contiguous(), transA=True)        # Q^T diag(h0) Q
+            core = K.gemm(Qm, (h.reshape(-1, n, 1) * Qm).contiguous(), transA=True)    # Q^T diag(h0) Q
             H0 = K.gemm(Qm, K.gemm(core, Qm, transB=True))                             # P diag(h0) P, P = Q Q^T
             H0 = 0.5 * (H0 + H0.transpose(1, 2))
         self._B.copy_(H0)

@@ -302,6 +302,18 @@ ql_kernel(double* __restrict__ dio, double* __restrict__ eio, double* __restrict
     }
     __syncthreads();
     const double eps = 2.220446049250313e-16;
+    // An off-diagonal element is negligible relative to its diagonal neighbours OR relative to the whole
+    // matrix (EISPACK tql2 / LAPACK dsteqr): without the second test a rank-deficient matrix -- the model
+    // Hessian P diag(h0) P of an internal-coordinate search has an exact (nint - ncart)-fold zero eigenvalue --
+    // leaves d ~ e ~ 1e-16 |A| in the zero cluster and the purely relative test never fires.
+    __shared__ double sh_anorm;
+    if (tid == 0) {
+        double a = 0.0;
+        for (int i = 0; i < n; ++i) a = fmax(a, fabs(d[i]) + (i < n - 1 ? fabs(e[i]) : 0.0));
+        sh_anorm = a;
+    }
+    __syncthreads();
+    const double tiny = eps * sh_anorm;
     bool failed = false;
     for (int l = 0; l < n; ++l) {
         int iter = 0;
@@ -310,7 +322,7 @@ ql_kernel(double* __restrict__ dio, double* __restrict__ eio, double* __restrict
                 int m = l;
                 for (; m < n - 1; ++m) {
                     const double dd = fabs(d[m]) + fabs(d[m + 1]);
-                    if (fabs(e[m]) <= eps * dd) break;
+                    if (fabs(e[m]) <= eps * dd || fabs(e[m]) <= tiny) break;
                 }
                 sh_m = m;
                 sh_flag = 0;

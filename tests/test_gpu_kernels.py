@@ -78,6 +78,12 @@ def test_eigh_against_lapack(n):
     u = rng.normal(size=(n, min(2, n)))
     A[1] = 0.7 * np.eye(n) + u @ u.T - 2.0 * np.outer(u[:, 0], u[:, 0])
     A[2] = np.diag(rng.normal(size=n))            # already diagonal
+    # exactly rank deficient: P diag(h) P with a projector of rank n/3 (the model Hessian of an
+    # internal-coordinate search, peswrapper.py:641-652) -- a (2n/3)-fold eigenvalue 0 +- 1e-16 |A|
+    if n >= 6:
+        qq = np.linalg.qr(rng.normal(size=(n, n // 3)))[0]
+        A[3] = qq @ (qq.T * (1.0 + 50.0 * rng.rand(n))[None, :]) @ qq @ qq.T
+        A[3] = 0.5 * (A[3] + A[3].T)
     w, Vt, status = K.eigh(to_dev(A))
     w, Vt = w.cpu().numpy(), Vt.cpu().numpy()
     assert int(status.abs().sum()) == 0

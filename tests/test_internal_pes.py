@@ -317,8 +317,9 @@ def test_cuda_internal_engine_matches_oracle_loop(method, angles):
     x0 = np.stack([p[0].positions.ravel() for p in problems])
     surf = EMTSurface(len(problems), ints.natoms, dev, cell=at.cell, pbc=tuple(at.pbc))
     kw = dict(method=method, diag_maxiter=6)
+    h0 = np.stack([cs.guess_hessian(a.positions) for a, _, _ in problems])      # per system: it depends on the geometry
     eng = BatchedInternalSella(surf, torch.from_numpy(x0).to(dev), ints.device_coordinates(), cons_rows=rows,
-                               h0=np.diag(ints.guess_hessian()), **kw)
+                               h0=h0, **kw)
     oracles = []
     for a, _, _ in problems:
         p = InternalPES(a.func, a.positions.ravel(), cs, csc, integrator="rk")
