@@ -118,7 +118,8 @@ class InternalPES(CartesianPES):
         c = self._geom()
         if "Binv" not in c:
             Q, R = self._jacobian_qr()
-            c["Binv"] = solve_triangular(R, Q.T, check_finite=False)
+            if "Binv" not in c:                       # the SVD branch has stored it already
+                c["Binv"] = solve_triangular(R, Q.T, check_finite=False)
         return c["Binv"]
 
     # -- constraints ---------------------------------------------------------------------------

@@ -23,9 +23,9 @@ Dormand-Prince 5(4) steps with PER-SYSTEM step control (the reference calls scip
 atol 1e-6; this scheme runs at rtol 1e-6 / atol 1e-8 and is restated in oracle/internal_pes.py for
 step-by-step parity), followed by the Newton projection onto the constraint manifold (:928-994).
 
-Not on the device (status bit 256 / NotImplementedError): a rank-deficient Wilson matrix (the
-reference's SVD branch, :691-704 -- free molecules without translation/rotation coordinates),
-dummy atoms, the iterative stepper, the "violation alone exceeds the radius" branch of the
+A rank-deficient Wilson matrix (a free molecule: the reference's SVD branch, :691-704) is served by the
+eigendecomposition of Bw^T Bw instead of the QR (`_factor`); status bit 256 flags a system whose rank
+differs from the batch's.  Not on the device (NotImplementedError): dummy atoms, the iterative stepper, the "violation alone exceeds the radius" branch of the
 restricted step, re-detection of the coordinate list when an angle becomes linear (the engine
 reports `bad_internals()`; the Sella shell rebuilds the object, optimize.py:382-410).
 """
@@ -105,6 +105,7 @@ class BatchedInternalSella(BatchedSella):
         self.atol = float(atol) * np.pi / 180.0
         rows = np.zeros(0, dtype=np.int64) if cons_rows is None else np.asarray(cons_rows, dtype=np.int64)
         self.nc = len(rows)
+        self.nnull, self.svd_path = 0, False
         self.nfree_int = ncart - self.nc
         self.rows = torch.from_numpy(rows).to(dev)
         self._gc = torch.zeros(b, ncart, dtype=torch.float64, device=dev)
@@ -141,6 +142,12 @@ class BatchedInternalSella(BatchedSella):
         self.first_diag = True
         self.ode_steps = 0
         # ---- geometry at the start and the model Hessian (peswrapper.py:641-652)
+        # rank of the Wilson matrix at the start decides the factorisation (one choice per batch: a free
+        # molecule is rank deficient at every geometry, a slab with held atoms at none)
+        sv = torch.linalg.svdvals(self.ints.jacobian(self.pos)[:1].cpu())[0]
+        self.nnull = int((sv <= 1e-6).sum())
+        self.svd_path = self.nnull > 0
+        self.nfree_int = ncart - self.nc - self.nnull
         self.geo = self._geometry(self.pos)
         if H0 is None:
             if h0 is None:
@@ -164,16 +171,35 @@ class BatchedInternalSella(BatchedSella):
             v[:, lo:hi] = torch.remainder(v[:, lo:hi] + np.pi, 2.0 * np.pi) - np.pi
         return v
 
+    def _factor(self, Bw):
+        """(Q, Rinv) with Bw = Q Rinv^-1 on range(Bw) and B+ = Rinv Q^T (peswrapper.py:674-736).
+
+        Full column rank (slabs / crystals with held atoms): economy QR, Rinv = R^-1.  Rank deficient (a free
+        molecule: the six rigid-body directions, the reference's SVD branch :691-704): the same two factors
+        from the eigendecomposition of Bw^T Bw = V S^2 V^T -- Rinv = V S^-1, Q = Bw Rinv with ZERO columns for
+        the null directions (singular values <= 1e-6 as in the reference); eigenvalues come out ascending, so
+        the null directions are the first `nnull` columns of every system."""
+        if not self.svd_path:
+            Q, R = K.qr(Bw)
+            Rinv, st = K.trtri(R)
+            rd = torch.diagonal(R, dim1=1, dim2=2).abs()
+            bad = (rd.min(dim=1).values < 1e-6 * rd.max(dim=1).values).to(torch.int32)
+            self.status |= bad * SB_ST_WILSON_RANK
+            self.status |= st
+            return Q, Rinv
+        G = K.gemm(Bw, Bw, transA=True)
+        w, Vt, _ = K.eigh((0.5 * (G + G.transpose(1, 2))).contiguous(), status=self.status)
+        keep = w > 1e-12
+        self.status |= (keep.sum(dim=1) != self.ncart - self.nnull).to(torch.int32) * SB_ST_WILSON_RANK
+        sinv = torch.where(keep, w.clamp(min=1e-300).rsqrt(), torch.zeros_like(w))
+        Rinv = (Vt * sinv[:, :, None]).transpose(1, 2).contiguous()
+        return K.gemm(Bw, Rinv), Rinv
+
     def _geometry(self, pos):
-        """q, Bw = Q R, R^-1 and the constraint basis at `pos` [b, ncart]."""
+        """q, the factors of the Wilson matrix and the constraint basis at `pos` [b, ncart]."""
         q, Bw = self.ints.calc(pos, jacobian=True)
-        Q, R = K.qr(Bw)
-        Rinv, st = K.trtri(R)
-        rd = torch.diagonal(R, dim1=1, dim2=2).abs()
-        bad = (rd.min(dim=1).values < 1e-6 * rd.max(dim=1).values).to(torch.int32)
-        self.status |= bad * SB_ST_WILSON_RANK            # the reference switches to an SVD here (:691-704)
-        self.status |= st
-        geo = dict(pos=pos, q=q, Bw=Bw, Q=Q, R=R, Rinv=Rinv)
+        Q, Rinv = self._factor(Bw)
+        geo = dict(pos=pos, q=q, Bw=Bw, Q=Q, Rinv=Rinv)
         if self.nc:
             J = Bw[:, self.rows].contiguous()                               # cons.jacobian(): rows of Bw
             red = K.gemm(J, Rinv)                                            # drdx in the basis Q [b, nc, ncart]
@@ -235,7 +261,15 @@ class BatchedInternalSella(BatchedSella):
             HLr = Hr
             Bp = 0.5 * (Hr + Hr.transpose(1, 2))
             sigma = 1.0 + 8.0 * hnorm
-        geo["HLr"] = 0.5 * (HLr + HLr.transpose(1, 2))
+        HLr = 0.5 * (HLr + HLr.transpose(1, 2))
+        if self.nnull:
+            # the null directions of the Wilson matrix (zero columns of Q: exact zero rows / columns of HL_r) are not
+            # part of Unred: lift them to sigma like the constraint directions
+            k = self.nnull
+            dz = sigma[:, None] * torch.ones(k, dtype=torch.float64, device=self.dev)[None, :]
+            Bp.diagonal(dim1=1, dim2=2)[:, :k] += dz
+            HLr.diagonal(dim1=1, dim2=2)[:, :k] += dz
+        geo["HLr"] = HLr
         evr, Vtr, _ = K.eigh(Bp.contiguous(), status=self.status)
         geo["evr"], geo["Vtr"] = evr, Vtr
         # lifted eigenvectors: rows of W = Vt_r Q^T; the model spectrum the Davidson code and the step use
@@ -249,10 +283,7 @@ class BatchedInternalSella(BatchedSella):
         """peswrapper.py:1200-1221 for y = (x, dx/dt, g) [b, 3, ncart]."""
         pos = y[:, 0].contiguous()
         if self.exact_geodesic:
-            q, Bw = self.ints.calc(pos, jacobian=True)
-            Q, R = K.qr(Bw)
-            Rinv, st = K.trtri(R)
-            self.status |= st
+            Q, Rinv = self._factor(self.ints.jacobian(pos))
         else:
             Q, Rinv = geo0["Q"], geo0["Rinv"]
         Rd = self.ints.rdot(pos, y[:, 1].contiguous())                      # [b, nint, ncart]
@@ -427,8 +458,9 @@ class BatchedInternalSella(BatchedSella):
             self.gfull.copy_(self.g)
         gr = K.gemm(_row(self.gfull), geo["Q"])
         self.Vg_r.copy_(K.gemm(gr, geo["Vtr"], transB=True).view(b, ncart))
-        if nc:
-            self.Vg_r[:, ncart - nc:] = 0.0       # the poles at sigma are the constraint directions: Ufree^T removes them
+        if nc + self.nnull:
+            # the poles at sigma are the constraint (and null) directions: Ufree^T removes them
+            self.Vg_r[:, ncart - nc - self.nnull:] = 0.0
         if self.method == "qn":
             call("sb_qn_mis", _p(self.Vg_r), _p(geo["evr"]), _p(self.Vt), _p(self.delta), I(self.order), I(n),
                  _p(self.s), _p(self.smag), _p(self.alpha), _p(self.status), _p(None), _p(sadd), I(ncart),

@@ -75,11 +75,25 @@ def cluster_problem(seed, natoms=10, rattle=0.08, variant=0):
     return at, cons, ints
 
 
+def molecule_problem(variant=0, natoms=8):
+    """A free Cu cluster (no constraints): the Wilson matrix has rank 3N - 6, the reference's SVD branch."""
+    pos = fcc_cluster(natoms, seed=77, rattle=0.08)
+    at = _Atoms(pos, None, (False,) * 3, oemt.emt_func(None, (False,) * 3))
+    cons = Constraints(at)
+    ints = Internals(at, cons=cons)
+    ints.find_all_bonds()
+    ints.find_all_angles()
+    ints.find_all_dihedrals()
+    if variant:
+        at.positions += 0.02 * np.random.RandomState(2000 + variant).normal(size=at.positions.shape)
+    return at, cons, ints
+
+
 def oracle_sets(ints):
     tr, b, a, d, tv = ints.lists()
     cs = CoordinateSet(ints.natoms, tr, b, a, d, tvecs=tv, numbers=ints.atoms.numbers)
     rows, tg = ints.constraint_rows()
-    csc = CoordinateSet(ints.natoms, [tr[r] for r in rows])
+    csc = CoordinateSet(ints.natoms, [tr[r] for r in rows]) if len(rows) else None
     return cs, csc, rows
 
 
@@ -201,6 +215,9 @@ class _FakeInts:
             return q
         return q, torch.from_numpy(np.stack([self.cs.jacobian(p) for p in x.numpy()]))
 
+    def jacobian(self, x):
+        return self.calc(x, jacobian=True)[1]
+
     def ldot(self, x, v):
         import torch
         return torch.from_numpy(np.stack([self.cs.ldot(p, w) for p, w in zip(x.numpy(), v.numpy())]))
@@ -228,16 +245,21 @@ def _cpu_engine(monkeypatch, problems):
     eng.dih = (cs.ntrans + cs.nbonds + cs.nangles, cs.nint)
     eng.exact_geodesic = True
     eng.ode_steps = 0
-    eng.targets = eng.ints.calc(pos)[:, eng.rows].clone()
+    eng.targets = eng.ints.calc(pos)[:, eng.rows].clone() if eng.nc else None
+    sv = np.linalg.svd(cs.jacobian(problems[0][0].positions), compute_uv=False)
+    eng.nnull = int((sv <= 1e-6).sum())
+    eng.svd_path = eng.nnull > 0
+    eng.nfree_int = cs.ndof - len(rows) - eng.nnull
     eng.geo = eng._geometry(pos)
     eng.x = eng.geo["q"].clone()
     return eng, cs, csc
 
 
-@pytest.mark.parametrize("angles", [False, True])
+@pytest.mark.parametrize("angles", [False, True, "free"])
 def test_engine_algebra_matches_oracle_on_cpu_stand_ins(monkeypatch, angles):
     torch = pytest.importorskip("torch")
-    problems = [slab_problem(30 + s, angles=angles) for s in range(2)]
+    problems = [molecule_problem(s) for s in range(2)] if angles == "free" else \
+        [slab_problem(30 + s, angles=angles) for s in range(2)]
     eng, cs, csc = _cpu_engine(monkeypatch, problems)
     b, n, ncart, nc = eng.batch, eng.n, eng.ncart, eng.nc
     rng = np.random.RandomState(5)
@@ -262,10 +284,12 @@ def test_engine_algebra_matches_oracle_on_cpu_stand_ins(monkeypatch, angles):
         Uf, Uc = p.get_Ufree(), p.get_Ucons()
         nfree = Uf.shape[1]
         assert nfree == eng.nfree_int
-        np.testing.assert_allclose(geo["L"][i].numpy(), p.curr["L"], atol=1e-10)
         Hc = p.get_Hc()
         V = rng.normal(size=(3, n))
-        np.testing.assert_allclose(eng._hc_apply(geo, torch.from_numpy(V[None].repeat(b, 0)))[i].numpy(), V @ Hc, atol=1e-9)
+        if nc:
+            np.testing.assert_allclose(geo["L"][i].numpy(), p.curr["L"], atol=1e-10)
+            np.testing.assert_allclose(eng._hc_apply(geo, torch.from_numpy(V[None].repeat(b, 0)))[i].numpy(), V @ Hc,
+                                       atol=1e-9)
         np.testing.assert_allclose(eng._free_project(geo, torch.from_numpy(V[None].repeat(b, 0)))[i].numpy(),
                                    V @ Uf @ Uf.T, atol=1e-11)
         ref = np.linalg.eigvalsh(Uf.T @ (p.H.B - Hc) @ Uf)
@@ -274,9 +298,11 @@ def test_engine_algebra_matches_oracle_on_cpu_stand_ins(monkeypatch, angles):
         W = eng.Vt[i, :ncart].numpy()
         np.testing.assert_allclose(W[:nfree] @ W[:nfree].T, np.eye(nfree), atol=1e-11)
         np.testing.assert_allclose(Uf @ Uf.T @ W[:nfree].T, W[:nfree].T, atol=1e-11)       # span = free space
-        np.testing.assert_allclose(Uc @ Uc.T @ W[nfree:].T, W[nfree:].T, atol=1e-10)       # sigma rows = Ucons
+        if nc:
+            np.testing.assert_allclose(Uc @ Uc.T @ W[nfree:nfree + nc].T, W[nfree:nfree + nc].T, atol=1e-10)   # = Ucons
         ev2 = np.linalg.eigvalsh(geo["HLr"][i].numpy())
-        np.testing.assert_allclose(ev2, p.get_HL_projected(p.get_Unred()).evals, atol=1e-9)
+        ref2 = p.get_HL_projected(p.get_Unred()).evals
+        np.testing.assert_allclose(ev2[:len(ref2)], ref2, atol=1e-9)      # null directions sit at sigma, above
     # geodesic + projection: the engine's integrator against the oracle's restatement of it
     s = 0.05 * rng.normal(size=(b, n))
     for i, p in enumerate(oracles):
@@ -292,6 +318,8 @@ def test_engine_algebra_matches_oracle_on_cpu_stand_ins(monkeypatch, angles):
         # the fixed atoms have stayed where they were
         np.testing.assert_allclose(cs.calc(p.pos)[:nc], eng.x[i, :nc].numpy(), atol=1e-7)
     assert int(eng.status.max()) == 0
+    if not nc:
+        return
     # Newton projection onto the constraint manifold after a displaced start
     posd = eng.pos.clone()
     posd[:, :3] += 1e-4
@@ -303,15 +331,18 @@ def test_engine_algebra_matches_oracle_on_cpu_stand_ins(monkeypatch, angles):
 
 # ----------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.parametrize("method,angles", [("qn", False), ("prfo", False), ("prfo", True)])
+@pytest.mark.parametrize("method,angles", [("qn", False), ("prfo", False), ("prfo", True), ("prfo", "free")])
 def test_cuda_internal_engine_matches_oracle_loop(method, angles):
-    """Every step of three C3-style searches in internal coordinates (bonds [+ angles], bottom half fixed) on
-    the CUDA engine equals the oracle InternalPES loop run with the same integrator."""
+    """Every step of three searches in internal coordinates on the CUDA engine equals the oracle InternalPES loop
+    run with the same integrator: C3-style slabs (bonds, bottom half fixed), clusters with three held atoms and the
+    full automatic list (bonds, angles, dihedrals), and FREE clusters (rank-deficient Wilson matrix: the
+    reference's SVD branch)."""
     torch = pytest.importorskip("torch")
     from sella_b200.batched_internal import BatchedInternalSella
     from sella_b200.emt import EMTSurface
     dev = torch.device("cuda:0")
-    problems = [slab_problem(40 + s, angles=angles) for s in range(3)]
+    problems = [molecule_problem(s) for s in range(3)] if angles == "free" else \
+        [slab_problem(40 + s, angles=angles) for s in range(3)]
     at, cons, ints = problems[0]
     cs, csc, rows = oracle_sets(ints)
     x0 = np.stack([p[0].positions.ravel() for p in problems])
@@ -361,3 +392,19 @@ def test_sella_internal_true_on_a_slab():
     assert abs(dyn.nsteps - o.nsteps) <= max(3, o.nsteps // 4)
     fixed = np.nonzero(ref.pos.reshape(-1, 3)[:, 2] < ref.pos.reshape(-1, 3)[:, 2].mean())[0]
     assert dyn.pes.int is not None and dyn.pes.dim == ints.nint
+
+
+@pytest.mark.gpu
+def test_sella_internal_true_on_a_free_cluster():
+    """`Sella(cluster, internal=True, order=0)`: automatic coordinate list, rank-deficient Wilson matrix, a
+    minimisation without Davidson (eig=False); ends at a minimum of the surface with the rigid-body motions
+    untouched (no net force or torque enters the internal gradient)."""
+    pytest.importorskip("torch")
+    from sella_b200 import Sella
+    at, cons, ints = molecule_problem(0)
+    e0 = at.get_potential_energy()
+    dyn = Sella(at, internal=True, order=0, logfile=None)
+    assert dyn.pes.int.nbonds > 0 and dyn.pes.int.nangles > 0
+    assert dyn.run(1e-3, 300)
+    assert at.get_potential_energy() < e0
+    assert np.linalg.norm(at.get_forces(), axis=1).max() < 1e-3
