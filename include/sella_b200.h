@@ -283,7 +283,8 @@ int sb_rotation(const double* x, int natoms, const double* refpos, long long ref
  *             Q [b, m, n] with orthonormal columns, R [b, n, n] upper triangular (LAPACK signs):
  *             gpu_qr (_gpu.py:100-111), _get_jacobian_qr (peswrapper.py:674-709).  Blocked (panels of
  *             16 columns, compact WY, trailing updates as sb_gemm); work: batch * (m*n + 32*n +
- *             256*ceil(n/16)) doubles.
+ *             256*ceil(n/16)) doubles.  Q == NULL: R only (half the work; B+ w = R^-1 R^-T A^T w then
+ *             needs no Q -- the stages of the geodesic integrator, peswrapper.py:1200-1221).
  *   sb_trtri: Rinv [b, n, n] = R^-1 (upper triangular; diagonal blocks of <= 48 by back substitution,
  *             assembled with sb_gemm); work: batch*n*n doubles; SB_ST_SINGULAR on a zero diagonal. */
 int sb_gemm(int transA, int transB, int M, int N, int K, double alpha, const double* A, int lda,

@@ -50,7 +50,7 @@ DP_A = [
 ]
 DP_B5 = np.array([35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84, 0.0])
 DP_B4 = np.array([5179 / 57600, 0.0, 7571 / 16695, 393 / 640, -92097 / 339200, 187 / 2100, 1 / 40])
-RK_ATOL, RK_RTOL, RK_MAXSTEPS = 1e-8, 1e-6, 64
+RK_ATOL, RK_RTOL, RK_MAXSTEPS = 1e-7, 1e-4, 64
 
 
 def range_space_projector(B):

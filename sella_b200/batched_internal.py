@@ -20,7 +20,7 @@ the max-internal-step search (sb_qn_mis / sb_rfo_mis) and the Davidson code of t
 
 Moving to a target q is the geodesic of peswrapper.py:841-880, 1200-1221, integrated on the device by
 Dormand-Prince 5(4) steps with PER-SYSTEM step control (the reference calls scipy's LSODA with
-atol 1e-6; this scheme runs at rtol 1e-6 / atol 1e-8 and is restated in oracle/internal_pes.py for
+atol 1e-6 and scipy's default rtol 1e-3; this scheme runs ten times tighter, atol 1e-7 / rtol 1e-4, and is restated in oracle/internal_pes.py for
 step-by-step parity), followed by the Newton projection onto the constraint manifold (:928-994).
 
 A rank-deficient Wilson matrix (a free molecule: the reference's SVD branch, :691-704) is served by the
@@ -50,7 +50,7 @@ _A = ((),
       (35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84))
 _B5 = (35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84, 0.0)
 _B4 = (5179 / 57600, 0.0, 7571 / 16695, 393 / 640, -92097 / 339200, 187 / 2100, 1 / 40)
-RK_ATOL, RK_RTOL, RK_MAXSTEPS = 1e-8, 1e-6, 64
+RK_ATOL, RK_RTOL, RK_MAXSTEPS = 1e-7, 1e-4, 64
 
 
 def _row(v):
@@ -171,7 +171,7 @@ class BatchedInternalSella(BatchedSella):
             v[:, lo:hi] = torch.remainder(v[:, lo:hi] + np.pi, 2.0 * np.pi) - np.pi
         return v
 
-    def _factor(self, Bw):
+    def _factor(self, Bw, want_q=True):
         """(Q, Rinv) with Bw = Q Rinv^-1 on range(Bw) and B+ = Rinv Q^T (peswrapper.py:674-736).
 
         Full column rank (slabs / crystals with held atoms): economy QR, Rinv = R^-1.  Rank deficient (a free
@@ -180,7 +180,7 @@ class BatchedInternalSella(BatchedSella):
         the null directions (singular values <= 1e-6 as in the reference); eigenvalues come out ascending, so
         the null directions are the first `nnull` columns of every system."""
         if not self.svd_path:
-            Q, R = K.qr(Bw)
+            Q, R = K.qr(Bw, want_q=want_q)
             Rinv, st = K.trtri(R)
             rd = torch.diagonal(R, dim1=1, dim2=2).abs()
             bad = (rd.min(dim=1).values < 1e-6 * rd.max(dim=1).values).to(torch.int32)
@@ -193,7 +193,7 @@ class BatchedInternalSella(BatchedSella):
         self.status |= (keep.sum(dim=1) != self.ncart - self.nnull).to(torch.int32) * SB_ST_WILSON_RANK
         sinv = torch.where(keep, w.clamp(min=1e-300).rsqrt(), torch.zeros_like(w))
         Rinv = (Vt * sinv[:, :, None]).transpose(1, 2).contiguous()
-        return K.gemm(Bw, Rinv), Rinv
+        return (K.gemm(Bw, Rinv) if want_q else None), Rinv
 
     def _geometry(self, pos):
         """q, the factors of the Wilson matrix and the constraint basis at `pos` [b, ncart]."""
@@ -282,13 +282,16 @@ class BatchedInternalSella(BatchedSella):
     def _rhs(self, y, geo0):
         """peswrapper.py:1200-1221 for y = (x, dx/dt, g) [b, 3, ncart]."""
         pos = y[:, 0].contiguous()
+        # B+ w = Rinv Rinv^T Bw^T w (semi-normal equations): no Q, which is half of a QR
         if self.exact_geodesic:
-            Q, Rinv = self._factor(self.ints.jacobian(pos))
+            Bw = self.ints.jacobian(pos)
+            Rinv = self._factor(Bw, want_q=False)[1]
         else:
-            Q, Rinv = geo0["Q"], geo0["Rinv"]
+            Bw, Rinv = geo0["Bw"], geo0["Rinv"]
         Rd = self.ints.rdot(pos, y[:, 1].contiguous())                      # [b, nint, ncart]
         X = y[:, 1:3].contiguous()
-        out = K.gemm(K.gemm(K.gemm(X, Rd, transB=True), Q), Rinv, transB=True)
+        u = K.gemm(K.gemm(K.gemm(X, Rd, transB=True), Bw), Rinv)            # (Rinv^T Bw^T (Rd X))^T
+        out = K.gemm(u, Rinv, transB=True)
         return torch.cat([y[:, 1:2], -out], dim=1)
 
     def _integrate(self, y0, geo0):

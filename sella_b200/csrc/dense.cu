@@ -335,8 +335,12 @@ extern "C" int sb_qr_impl(double* A, int m, int n, double* Q, double* R, double*
     }
     {
         dim3 g1((n * n + 255) / 256, batch), g2((m * n + 255) / 256, batch);
-        SB_COUNT(2);
+        SB_COUNT(1);
         qr_copy_r_kernel<<<g1, 256, 0, st>>>(A, m, n, R, active);
+        // Q == NULL: R only (the caller works with the semi-normal equations B+ w = R^-1 R^-T B^T w, e.g.
+        // every stage of the geodesic integrator) -- the accumulation of Q is half of the work
+        if (!Q) return SB_LAUNCH_CHECK();
+        SB_COUNT(1);
         qr_init_q_kernel<<<g2, 256, 0, st>>>(Q, m, n, active);
     }
     for (int p = npan - 1; p >= 0; --p) {

@@ -175,13 +175,14 @@ def gemm(A, B, transA=False, transB=False, alpha=1.0, beta=0.0, out=None, active
     return out
 
 
-def qr(A, active=None):
-    """Economy QR of A [b, m, n], m >= n: Q [b, m, n], R [b, n, n] (LAPACK sign convention)."""
+def qr(A, active=None, want_q=True):
+    """Economy QR of A [b, m, n], m >= n: Q [b, m, n], R [b, n, n] (LAPACK sign convention);
+    want_q=False: (None, R), half the work."""
     require_cuda()
     check_f64(A)
     b, m, n = A.shape
     fac = A.clone()
-    Q = torch.empty((b, m, n), dtype=torch.float64, device=A.device)
+    Q = torch.empty((b, m, n), dtype=torch.float64, device=A.device) if want_q else None
     R = torch.empty((b, n, n), dtype=torch.float64, device=A.device)
     work = torch.empty(b * (m * n + 32 * n + 256 * ((n + 15) // 16)), dtype=torch.float64, device=A.device)
     call("sb_qr", _p(fac), I(m), I(n), _p(Q), _p(R), _p(work), _p(_mask(active)), I(b), _stream())

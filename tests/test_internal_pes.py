@@ -176,10 +176,10 @@ class _FakeK:
         return torch.matmul(A, B).contiguous()
 
     @staticmethod
-    def qr(A, **kw):
+    def qr(A, want_q=True, **kw):
         import torch
         Q, R = torch.linalg.qr(A, mode="reduced")
-        return Q.contiguous(), R.contiguous()
+        return (Q.contiguous() if want_q else None), R.contiguous()
 
     @staticmethod
     def trtri(R, **kw):
