@@ -71,7 +71,9 @@ int sb_emt_pes(const double* x, int natoms, const double* cell, long long cellst
  * sella/linalg.py:174-195, sella/optimize/stepper.py:79-83,
  * sella/eigensolvers.py:11, sella/_gpu.py:70-97 (gpu_eigh / gpu_eigh_t).
  * evals[b,:] ascending; Vt[b,i,:] = eigenvector i (row = eigenvector).
- * work: batch*n*n doubles, small: 3*batch*n doubles.                              */
+ * work: batch*n*n doubles, small: 3*batch*n doubles.
+ * Vt == NULL: eigenvalues only (scipy eigvalsh; the re-diagonalisation test optimize.py:369-371
+ * looks at eigenvalues alone) -- tridiagonalisation + QL on (d, e), no eigenvector work. */
 int sb_eigh(const double* A, double* evals, double* Vt, double* work, double* small_work,
             int32_t* status, const int32_t* active, int batch, int n, void* stream);
 /* same, with Q^T accumulated by blocked compact-WY GEMMs (faster for batches of large matrices);

@@ -1123,7 +1123,7 @@ class BatchedSella:
         ev_evals = self.evalsB
         if nl is not None and self.eig and int((self.since_diag >= int(self._ipar[2])).any().item()):
             # optimize.py:369-371 looks at the Hessian of the Lagrangian (B - Hc), not at B
-            K.eigh(nl["HL"], evals=nl["evalsHL"], Vt=self.eig_ws.work, status=self.status)
+            K.eigvalsh(nl["HL"], evals=nl["evalsHL"], status=self.status)
             ev_evals = nl["evalsHL"]
         call("sb_ev_decide", _p(ev_evals), I(n), I(1), _p(self.since_diag), _p(self.ev), self._dpar,
              self._ipar, _p(active), I(b), _stream())

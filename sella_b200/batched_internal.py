@@ -34,7 +34,7 @@ import torch
 
 from . import kernels as K
 from ._lib import I, D, LL, _p, _stream, call, check_f64
-from .batched import BatchedSella, DAV_EXPAND
+from .batched import BatchedSella, DAV_EXPAND, _Spec
 
 SB_ST_WILSON_RANK = 256        # (1..64 are the library's SB_ST_* bits, include/sella_b200.h)
 SB_ST_GEODESIC = 512
@@ -141,6 +141,23 @@ class BatchedInternalSella(BatchedSella):
         self.Vg_r = torch.zeros(b, ncart, **f64)
         self.first_diag = True
         self.ode_steps = 0
+        # ---- H is held twice, as the compact engine with track_B does (batched.py): densely (`_B`, for
+        # the projections Q^T H Q and H.v) and as explicit eigenpairs (evalsB, VtB rows) + the eigenvalue
+        # lam0 = 0 on their complement -- the model Hessian P diag(h0) P has rank <= ncart and every secant
+        # update adds rank 2, so the eigen-update works on a few hundred rows instead of nint
+        if self.kcap > 16:
+            raise NotImplementedError("kcap <= 16 with internal coordinates")
+        zi = lambda *sh: torch.zeros(*sh, dtype=torch.int32, device=dev)      # noqa: E731
+        self.sp = self.spB = _Spec(b, n, dev, self.evalsB, self.VtB)
+        self.tracked_B = self._B
+        self.lam0.zero_()
+        import os
+        self.split_rotation = os.environ.get("SB_SPLIT_ROTATION", "1") != "0"
+        self.split_min_rows = int(os.environ.get("SB_SPLIT_MIN_ROWS", "24"))
+        self.sec_aux, self.ncand = zi(b, n + 4), zi(b)
+        for sec, zc in ((self.sec1, 2), (self.seck, 2 * self.kcap)):
+            for k in ("W1", "Qc", "D2", "W2"):
+                sec[k] = torch.zeros(b, zc, n, **f64)
         # ---- geometry at the start and the model Hessian (peswrapper.py:641-652)
         # rank of the Wilson matrix at the start decides the factorisation (one choice per batch: a free
         # molecule is rank deficient at every geometry, a slab with held atoms at none)
@@ -153,14 +170,24 @@ class BatchedInternalSella(BatchedSella):
             if h0 is None:
                 raise ValueError("internal coordinates need the diagonal model Hessian h0 (Internals.guess_hessian) "
                                  "or a full H0")
-            h = torch.from_numpy(np.array(h0, dtype=np.float64)).to(dev)
+            h = torch.from_numpy(np.array(h0, dtype=np.float64)).to(dev).abs()
             Qm = self.geo["Q"]
             core = K.gemm(Qm, (h.reshape(-1, n, 1) * Qm).contiguous(), transA=True)    # Q^T diag(h0) Q
-            H0 = K.gemm(Qm, K.gemm(core, Qm, transB=True))                             # P diag(h0) P, P = Q Q^T
-            H0 = 0.5 * (H0 + H0.transpose(1, 2))
-        self._B.copy_(H0)
+            th, Wc, _ = K.eigh((0.5 * (core + core.transpose(1, 2))).contiguous(), status=self.status)
+            rows = K.gemm(Wc, Qm, transB=True)           # eigenvectors of P diag(h0) P = Q core Q^T, lifted
+            m = ncart - self.nnull                       # (rank-deficient Wilson matrix: the null columns of Q
+            self.VtB[:, :m] = rows[:, self.nnull:]       # give exact zero eigenvalues, the lowest ones -- skipped)
+            self.evalsB[:, :m] = th[:, self.nnull:]
+            self._B.copy_(K.gemm(rows, (th[:, :, None] * rows).contiguous(), transA=True))
+        else:
+            check_f64(H0)
+            m = n
+            self._B.copy_(0.5 * (H0 + H0.transpose(1, 2)))
+            K.eigh(self._B, evals=self.evalsB, Vt=self.VtB, ws=self.eig_ws, status=self.status)
+        self._B.copy_(0.5 * (self._B + self._B.transpose(1, 2)))
+        self.sp.mrows.fill_(m)
+        self.sp.rb = self.sp.mmin = m
         self.H_initialized = True
-        K.eigh(self._B, evals=self.evalsB, Vt=self.VtB, ws=self.eig_ws, status=self.status)
         self.eig_valid = True
         self.Vt.zero_()
 
@@ -240,7 +267,7 @@ class BatchedInternalSella(BatchedSella):
         b, n, nc, ncart = self.batch, self.n, self.nc, self.ncart
         Q, Rinv = geo["Q"], geo["Rinv"]
         Hr = K.gemm(Q, K.gemm(self._B, Q), transA=True)                     # Q^T H Q
-        hnorm = torch.maximum(self.evalsB[:, 0].abs(), self.evalsB[:, -1].abs())
+        hnorm = self._hnorm()
         if nc:
             gr = K.gemm(_row(self.g), Q)                                    # (Q^T g)^T
             L = K.gemm(K.gemm(gr, geo["Vc"]), geo["Rcinv"], transB=True)    # Rc^-1 Vcons^T Q^T g  [b, 1, nc]
@@ -421,6 +448,18 @@ class BatchedInternalSella(BatchedSella):
                  _p(self.dav_state), _p(self.status), _p(None), I(self.batch), _stream())
         self._update(self.Vs, self.AVs, self.upk, self.nvec, nv, part)
 
+    def _hnorm(self):
+        """[b] largest |eigenvalue| of H (explicit pairs; the complement's eigenvalue is 0)."""
+        R = max(1, self.sp.rb)
+        live = torch.arange(R, device=self.dev)[None, :] < self.sp.mrows[:, None]
+        return (self.evalsB[:, :R].abs() * live).max(dim=1).values
+
+    def _update(self, S, Y, bufs, kvec, nv, active, bs_ready=False, abs_ready=False):
+        """ApproximateHessian.update (linalg.py:274-304): the compact eigen-update of the Cartesian engine on H's
+        explicit eigenpairs (complement eigenvalue 0), the dense copy carried along by sb_update_apply."""
+        self._update_compact(S, Y, bufs, kvec, nv, active)
+        self._sync_rows()                 # exact bounds on the explicit-row counts (one small read)
+
     def _run_diag(self, part):
         if not self.geo.get("model"):
             self._model()
@@ -475,7 +514,7 @@ class BatchedInternalSella(BatchedSella):
         # ---- re-diagonalise?  eigenvalues of Unred^T (H - Hc) Unred (optimize.py:362-371)
         ev_evals = geo["evr"]
         if self.eig and int((self.since_diag >= int(self._ipar[2])).any().item()):
-            K.eigh(geo["HLr"].contiguous(), evals=self.evalsHL, status=self.status)
+            K.eigvalsh(geo["HLr"].contiguous(), evals=self.evalsHL, status=self.status)
             ev_evals = self.evalsHL
         call("sb_ev_decide", _p(ev_evals), I(ncart), I(1), _p(self.since_diag), _p(self.ev), self._dpar,
              self._ipar, _p(None), I(b), _stream())
@@ -540,4 +579,8 @@ class BatchedInternalSella(BatchedSella):
         return self._B
 
     def lowest_evals(self):
-        return self.evalsB[:, 0].clone()
+        """[b] lowest eigenvalue of H (0 from the complement while not every direction is explicit)."""
+        R = max(1, self.sp.rb)
+        live = torch.arange(R, device=self.dev)[None, :] < self.sp.mrows[:, None]
+        lo = torch.where(live, self.evalsB[:, :R], torch.full_like(self.evalsB[:, :R], float("inf"))).min(dim=1).values
+        return torch.where(self.sp.mrows < self.n, torch.clamp(lo, max=0.0), lo)

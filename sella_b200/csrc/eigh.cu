@@ -373,7 +373,7 @@ ql_kernel(double* __restrict__ dio, double* __restrict__ eio, double* __restrict
             const int flag = sh_flag, m = sh_m, lo = sh_l_lo;
             if (flag == 2) { failed = true; break; }
             if (flag == 0) break;               // e[l] negligible: eigenvalue l done
-            if (lo <= m - 1) apply_sweep<CPT>(Mt, cs, n, lo, m, tid, nt);
+            if (Mt_ && lo <= m - 1) apply_sweep<CPT>(Mt, cs, n, lo, m, tid, nt);
             ++iter;
             __syncthreads();
         }
@@ -407,6 +407,7 @@ sort_kernel(const double* __restrict__ din, double* __restrict__ evals, double* 
         evals[(size_t)b * n + rank] = di;
     }
     __syncthreads();
+    if (!Mt_) return;                              // eigenvalues only
     // rows: new[r] = old[src[r]]; cycle-following, independently per column.
     // A cycle is walked from its smallest member ("leader"), found once per start.
     int* leader = src + n;
@@ -476,7 +477,10 @@ extern "C" int sb_eigh_impl(const double* A, double* evals, double* Vt, double* 
         else return -2;
 #undef SB_TRIDIAG
     }
-    if (work2 && n >= 4 * FQ_NB) {
+    if (!Vt) {
+        // eigenvalues only (the "did the lowest modes turn positive" test, optimize.py:362-371): no Q^T, and
+        // the QL iteration runs on (d, e) alone -- the rotation sweeps over Vt are most of a full eigensolve
+    } else if (work2 && n >= 4 * FQ_NB) {
         double* Vp = work2;
         double* W1 = Vp + (size_t)batch * n * n;
         double* W2 = W1 + (size_t)batch * FQ_NB * n;

@@ -64,18 +64,26 @@ class EighWorkspace:
         return self.work2
 
 
-def eigh(A, active=None, evals=None, Vt=None, ws=None, status=None):
-    """Ascending eigenvalues [b,n] and eigenvectors as ROWS of Vt [b,n,n]."""
+def eigvalsh(A, active=None, evals=None, ws=None, status=None):
+    """Ascending eigenvalues [b,n] only (no eigenvector work)."""
+    return eigh(A, active=active, evals=evals, ws=ws, status=status, vectors=False)[0]
+
+
+def eigh(A, active=None, evals=None, Vt=None, ws=None, status=None, vectors=True):
+    """Ascending eigenvalues [b,n] and eigenvectors as ROWS of Vt [b,n,n] (vectors=False: Vt is None)."""
     require_cuda()
     check_f64(A)
     b, n, _ = A.shape
     dev = A.device
     evals = torch.empty((b, n), dtype=torch.float64, device=dev) if evals is None else evals
-    Vt = torch.empty((b, n, n), dtype=torch.float64, device=dev) if Vt is None else Vt
+    if vectors:
+        Vt = torch.empty((b, n, n), dtype=torch.float64, device=dev) if Vt is None else Vt
+    else:
+        Vt = None
     ws = EighWorkspace(b, n, dev) if ws is None else ws
     status = torch.zeros(b, dtype=torch.int32, device=dev) if status is None else status
     active = _mask(active)
-    if n >= 64 and b * n * n >= (1 << 22):
+    if vectors and n >= 64 and b * n * n >= (1 << 22):
         call("sb_eigh_blocked", _p(A), _p(evals), _p(Vt), _p(ws.work), _p(ws.small), _p(ws.blocked()), _p(status),
              _p(active), I(b), I(n), _stream())
     else:

@@ -96,6 +96,19 @@ def test_eigh_against_lapack(n):
         np.testing.assert_allclose(A[i] @ V, V * w[i][None, :], atol=5e-12 * scale * max(1, n / 32))
 
 
+@pytest.mark.parametrize("n", [24, 96, 384])
+def test_eigvalsh_values_only(n):
+    from sella_b200 import kernels as K
+    rng = np.random.RandomState(500 + n)
+    A = rand_sym(rng, 5, n)
+    st = torch.zeros(5, dtype=torch.int32, device=dev())
+    w = K.eigvalsh(to_dev(A), status=st).cpu().numpy()
+    assert int(st.abs().sum()) == 0
+    for i in range(5):
+        wref = np.linalg.eigvalsh(A[i])
+        np.testing.assert_allclose(w[i], wref, rtol=0, atol=5e-13 * max(1.0, np.abs(wref).max()) * max(1, n / 32))
+
+
 def test_eigh_mask_leaves_inactive_untouched():
     from sella_b200 import kernels as K
     rng = np.random.RandomState(3)

@@ -195,6 +195,14 @@ class _FakeK:
         return w, V.transpose(1, 2).contiguous(), status
 
     @staticmethod
+    def eigvalsh(A, evals=None, status=None, **kw):
+        import torch
+        w = torch.linalg.eigvalsh(A)
+        if evals is not None:
+            evals.copy_(w)
+        return w
+
+    @staticmethod
     def hv_ld(A, X, Y, nvec, transposed=False, active=None):
         import torch
         Y[:, :nvec] = torch.matmul(X[:, :nvec], A if transposed else A.transpose(1, 2))
@@ -271,6 +279,8 @@ def test_engine_algebra_matches_oracle_on_cpu_stand_ins(monkeypatch, angles):
     # engine state: H, g, f as the oracle has them
     eng._B = torch.from_numpy(np.stack([p.H.B for p in oracles]))
     eng.evalsB = torch.from_numpy(np.stack([np.linalg.eigvalsh(p.H.B) for p in oracles]))
+    from types import SimpleNamespace
+    eng.sp = SimpleNamespace(rb=n, mrows=torch.full((b,), n, dtype=torch.int32))
     eng.g = torch.from_numpy(np.stack([p.curr["g"] for p in oracles]))
     eng._evaluated = True
     eng.evals, eng.Vt = torch.zeros(b, n), torch.zeros(b, n, n)
@@ -364,8 +374,15 @@ def test_cuda_internal_engine_matches_oracle_loop(method, angles):
             np.testing.assert_allclose(delta[i], o.delta, rtol=1e-6)
     eng.check_status()
     Hd = eng.B.cpu().numpy()
+    mrows = eng.sp.mrows.cpu().numpy()
     for i, (p, o) in enumerate(oracles):
         np.testing.assert_allclose(Hd[i], p.H.B, rtol=1e-5, atol=1e-5)
+        # the carried eigenpairs of H (explicit rows + the eigenvalue 0 on their complement) are those of the
+        # dense copy that sb_update_apply carries independently
+        m = int(mrows[i])
+        th, VR = eng.evalsB[i, :m].cpu().numpy(), eng.VtB[i, :m].cpu().numpy()
+        np.testing.assert_allclose(VR @ VR.T, np.eye(m), atol=1e-10)
+        np.testing.assert_allclose(VR.T @ (th[:, None] * VR), Hd[i], atol=1e-8 * max(1.0, np.abs(th).max()))
     conv = eng.converged(1e-3).cpu().numpy()
     fm = eng.fmax.cpu().numpy()
     for i, (p, o) in enumerate(oracles):
