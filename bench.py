@@ -319,6 +319,8 @@ def run_reference(args):
         return
     warm, steps = min(args.warmup, 2), min(args.steps, 4)     # bounded sample of the same workload
     t0 = time.perf_counter()
+    if args.internal:
+        return _run_reference_internal(args, t0)
     cb = cpu_reference(args, warm, steps)
     wall = time.perf_counter() - t0
     what = ("the reference's own Sella + PES classes (unmodified files, oracle/ref_loader.py)" if cb["kind"] == "reference"
@@ -331,6 +333,39 @@ def run_reference(args):
                note="%s on host cores; ms_per_step is the extrapolated time for one step of the whole "
                     "%d-system batch; wall %.1fs" % (what, args.batch, wall))
     print(json.dumps(out))
+
+
+def _internal_cpu_baseline(args, first, exact, warm=1, steps=2):
+    """C3 as named on the host cores: one system per core, the oracle InternalPES loop with the reference's
+    integrator (scipy LSODA); rate = median per-process rate x processes."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    jobs = [([first + i], args.n, args.kdiag, args.diag_every, warm, steps, args.method, "lsoda", exact)
+            for i in range(cores)]
+    with mp.get_context("spawn").Pool(cores) as pool:
+        res = pool.map(_internal_cpu_worker, jobs)
+    rates = sorted(r[0] / r[1] for r in res if r[1] > 0)
+    med = rates[len(rates) // 2]
+    return dict(value=med * cores, unit=UNIT, cores=cores, kind="port",
+                sample="systems 0..%d of the GPU arm's batch x (%d warm-up + %d timed) steps of the oracle InternalPES "
+                       "loop (reference algorithm, scipy LSODA geodesic), %d procs x 1 BLAS thread, median per-process "
+                       "rate x processes" % (cores - 1, warm, steps, cores))
+
+
+def _run_reference_internal(args, t0):
+    cb = _internal_cpu_baseline(args, 0, not args.inexact_geodesic)
+    wall = time.perf_counter() - t0
+    cfg = dict(workload="batch=%d/GPU x 3N=%d EMT-form surface, Cu(111) slabs in INTERNAL coordinates (nearest-neighbour "
+                        "bonds + the fixed atoms' Cartesian coordinates), %s + MaxInternalStep, TS-BFGS, jd0 Davidson "
+                        "maxiter=%d, diag_every_n=%d" % (args.batch, args.n, args.method, args.kdiag, args.diag_every),
+               batch_per_gpu=args.batch, dof=args.n, rs="mis", method=args.method, davidson_maxiter=args.kdiag,
+               diag_every_n=args.diag_every, coordinates="internal")
+    print(json.dumps(dict(metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=2, warmup=1,
+                          ms_per_step=1e3 * args.batch / cb["value"], higher_is_better=True, scaling="weak",
+                          vs_baseline=None, dtype="f64", data="synthetic", impl="reference", config=cfg, cpu_baseline=cb,
+                          e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                          note="CPU restatement (oracle/internal_pes.py) of the reference's InternalPES path on host "
+                               "cores; wall %.1fs" % wall)))
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -1027,19 +1062,8 @@ def run_internal(args):
                    diagonalisations=eng.ndiag)
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            warm, steps = 1, 2
-            jobs = [([first + i], n, args.kdiag, args.diag_every, warm, steps, args.method, "lsoda", exact)
-                    for i in range(cores)]
             try:
-                with mp.get_context("spawn").Pool(cores) as pool:
-                    res = pool.map(_internal_cpu_worker, jobs)
-                rates = sorted(r[0] / r[1] for r in res if r[1] > 0)
-                med = rates[len(rates) // 2]
-                out["cpu_baseline"] = dict(value=med * cores, unit=UNIT, cores=cores, kind="port",
-                                           sample="systems 0..%d of the GPU arm's batch x (%d warm-up + %d timed) steps of "
-                                                  "the oracle InternalPES loop (reference algorithm, scipy LSODA geodesic), "
-                                                  "%d procs x 1 BLAS thread, median per-process rate x processes"
-                                                  % (cores - 1, warm, steps, cores))
+                out["cpu_baseline"] = _internal_cpu_baseline(args, first, exact)
             except Exception as exc:
                 out["cpu_baseline"] = dict(value=None, unit=UNIT, cores=cores, kind="port", sample="failed: %r" % (exc,))
     if world > 1:

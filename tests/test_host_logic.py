@@ -158,3 +158,32 @@ def test_bench_reference_arm_contract():
     # baseline/_ref present); "port": the oracle restatement
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert "workload" in d["config"]
+
+
+def test_bench_internal_problem_and_reference_arm():
+    """BASELINE config C3 as named (internal coordinates): the host-side problem builder shared by both arms
+    (one coordinate list per batch, per-system model Hessian) and the `--impl reference --internal` line."""
+    import argparse
+    import json
+    import os
+    import subprocess
+    import sys
+    import bench
+    ns = argparse.Namespace(workload="emt-slab", n=384)
+    X0, cell, pbc, ints, rows, cs, h0 = bench.internal_problem(ns, 5, 2)
+    assert X0.shape == (2, 384) and ints.nbonds == 720 and ints.ntrans == 192 and ints.nint == 912
+    np.testing.assert_array_equal(rows, np.arange(192))
+    assert h0.shape == (2, 912) and (h0 > 0).all() and not np.array_equal(h0[0], h0[1])
+    B = cs.jacobian(X0[0])
+    assert np.linalg.matrix_rank(B) == 384
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "emt-slab", "--internal",
+           "--n", "96", "--batch", "4"]
+    out = subprocess.run(cmd, env=dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0"), capture_output=True,
+                         text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["config"]["coordinates"] == "internal" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port"
