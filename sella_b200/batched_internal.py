@@ -198,7 +198,7 @@ class BatchedInternalSella(BatchedSella):
             v[:, lo:hi] = torch.remainder(v[:, lo:hi] + np.pi, 2.0 * np.pi) - np.pi
         return v
 
-    def _factor(self, Bw, want_q=True):
+    def _factor(self, Bw, want_q=True, idx=None):
         """(Q, Rinv) with Bw = Q Rinv^-1 on range(Bw) and B+ = Rinv Q^T (peswrapper.py:674-736).
 
         Full column rank (slabs / crystals with held atoms): economy QR, Rinv = R^-1.  Rank deficient (a free
@@ -210,14 +210,21 @@ class BatchedInternalSella(BatchedSella):
             Q, R = K.qr(Bw, want_q=want_q)
             Rinv, st = K.trtri(R)
             rd = torch.diagonal(R, dim1=1, dim2=2).abs()
-            bad = (rd.min(dim=1).values < 1e-6 * rd.max(dim=1).values).to(torch.int32)
-            self.status |= bad * SB_ST_WILSON_RANK
-            self.status |= st
+            bad = (rd.min(dim=1).values < 1e-6 * rd.max(dim=1).values).to(torch.int32) * SB_ST_WILSON_RANK | st
+            if idx is None:
+                self.status |= bad
+            else:
+                self.status[idx] |= bad
             return Q, Rinv
         G = K.gemm(Bw, Bw, transA=True)
-        w, Vt, _ = K.eigh((0.5 * (G + G.transpose(1, 2))).contiguous(), status=self.status)
+        st = torch.zeros(Bw.shape[0], dtype=torch.int32, device=self.dev)
+        w, Vt, _ = K.eigh((0.5 * (G + G.transpose(1, 2))).contiguous(), status=st)
         keep = w > 1e-12
-        self.status |= (keep.sum(dim=1) != self.ncart - self.nnull).to(torch.int32) * SB_ST_WILSON_RANK
+        st |= (keep.sum(dim=1) != self.ncart - self.nnull).to(torch.int32) * SB_ST_WILSON_RANK
+        if idx is None:
+            self.status |= st
+        else:
+            self.status[idx] |= st
         sinv = torch.where(keep, w.clamp(min=1e-300).rsqrt(), torch.zeros_like(w))
         Rinv = (Vt * sinv[:, :, None]).transpose(1, 2).contiguous()
         return (K.gemm(Bw, Rinv) if want_q else None), Rinv
@@ -306,39 +313,45 @@ class BatchedInternalSella(BatchedSella):
         geo["model"] = True
 
     # ------------------------------------------------------------------ geodesic
-    def _rhs(self, y, geo0):
-        """peswrapper.py:1200-1221 for y = (x, dx/dt, g) [b, 3, ncart]."""
+    def _rhs(self, y, geo0, idx=None):
+        """peswrapper.py:1200-1221 for y = (x, dx/dt, g) [m, 3, ncart]; idx: the systems these m rows belong to
+        (None: the whole batch, in order)."""
         pos = y[:, 0].contiguous()
         # B+ w = Rinv Rinv^T Bw^T w (semi-normal equations): no Q, which is half of a QR
         if self.exact_geodesic:
             Bw = self.ints.jacobian(pos)
-            Rinv = self._factor(Bw, want_q=False)[1]
-        else:
+            Rinv = self._factor(Bw, want_q=False, idx=idx)[1]
+        elif idx is None:
             Bw, Rinv = geo0["Bw"], geo0["Rinv"]
-        Rd = self.ints.rdot(pos, y[:, 1].contiguous())                      # [b, nint, ncart]
+        else:
+            Bw, Rinv = geo0["Bw"][idx].contiguous(), geo0["Rinv"][idx].contiguous()
+        Rd = self.ints.rdot(pos, y[:, 1].contiguous())                      # [m, nint, ncart]
         X = y[:, 1:3].contiguous()
         u = K.gemm(K.gemm(K.gemm(X, Rd, transB=True), Bw), Rinv)            # (Rinv^T Bw^T (Rd X))^T
         out = K.gemm(u, Rinv, transB=True)
         return torch.cat([y[:, 1:2], -out], dim=1)
 
     def _integrate(self, y0, geo0):
-        """Dormand-Prince 5(4) from t = 0 to 1 with a step size per system (oracle/internal_pes.py:_rk)."""
+        """Dormand-Prince 5(4) from t = 0 to 1 with a step size per system (oracle/internal_pes.py:_rk).
+        Systems that have arrived leave the working set: every further iteration (rejected or shortened steps
+        of the few systems with a strongly curved path) runs on the unfinished ones only."""
         b = self.batch
         f64 = dict(dtype=torch.float64, device=self.dev)
-        t, h = torch.zeros(b, **f64), torch.ones(b, **f64)
-        done = torch.zeros(b, dtype=torch.bool, device=self.dev)
-        y = y0
+        yout = y0.clone()
+        idx = None                                   # None: all systems, in order
+        y, t, h = y0, torch.zeros(b, **f64), torch.ones(b, **f64)
         k1 = self._rhs(y, geo0)
         for _ in range(RK_MAXSTEPS):
+            m = y.shape[0]
             h = torch.minimum(h, 1.0 - t)
-            hh = h.view(b, 1, 1)
+            hh = h.view(m, 1, 1)
             ks = [k1]
             for s in range(1, 7):
                 acc = None
                 for a, k in zip(_A[s], ks):
                     if a != 0.0:
                         acc = a * k if acc is None else acc + a * k
-                ks.append(self._rhs(y + hh * acc, geo0))
+                ks.append(self._rhs(y + hh * acc, geo0, idx))
             inc = sum(w * k for w, k in zip(_B5, ks) if w != 0.0)
             e = hh * sum((w5 - w4) * k for w5, w4, k in zip(_B5, _B4, ks))
             ynew = y + hh * inc
@@ -346,19 +359,31 @@ class BatchedInternalSella(BatchedSella):
             err = (e.abs() / scale).flatten(1).max(dim=1).values
             fac = torch.where(err == 0.0, torch.full_like(err, 5.0),
                               torch.clamp(0.9 * err.clamp(min=1e-300) ** -0.2, 0.2, 5.0))
-            ok = (err <= 1.0) & ~done
-            okm = ok.view(b, 1, 1)
+            ok = err <= 1.0
+            okm = ok.view(m, 1, 1)
             y = torch.where(okm, ynew, y)
             k1 = torch.where(okm, ks[6], k1)
             t = torch.where(ok, t + h, t)
-            done = done | (ok & (t >= 1.0 - 1e-14))
-            h = torch.where(done, h, h * fac)
+            done = ok & (t >= 1.0 - 1e-14)
+            h = h * fac
             self.ode_steps += 1
-            if bool(done.all().item()):
+            ndone = int(done.sum().item())
+            if ndone:
+                if idx is None:
+                    yout = torch.where(done.view(m, 1, 1), y, yout)
+                else:
+                    yout[idx[done]] = y[done]
+            if ndone == m:
                 break
+            if ndone:
+                keep = ~done
+                idx = torch.nonzero(keep).flatten() if idx is None else idx[keep]
+                y, k1, t, h = y[keep].contiguous(), k1[keep].contiguous(), t[keep], h[keep]
         else:
-            self.status |= (~done).to(torch.int32) * SB_ST_GEODESIC
-        return y
+            left = torch.arange(b, device=self.dev) if idx is None else idx
+            self.status[left] |= SB_ST_GEODESIC
+            yout[left] = y
+        return yout
 
     def _set_x(self, target):
         """InternalPES.set_x (peswrapper.py:883-903) from the current geometry, WITHOUT committing:

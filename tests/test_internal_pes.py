@@ -315,19 +315,24 @@ def test_engine_algebra_matches_oracle_on_cpu_stand_ins(monkeypatch, angles):
         np.testing.assert_allclose(ev2[:len(ref2)], ref2, atol=1e-9)      # null directions sit at sigma, above
     # geodesic + projection: the engine's integrator against the oracle's restatement of it
     s = 0.05 * rng.normal(size=(b, n))
+    s[1] *= 14.0           # a long step: more integrator iterations than system 0 (which then leaves the working set)
     for i, p in enumerate(oracles):
         Uf = p.get_Ufree()
         s[i] = Uf @ (Uf.T @ s[i])
     pos, g2, dx_i, dx_f, g_par = eng._set_x(eng.x + torch.from_numpy(s))
+    nfev = [p.ode_nfev for p in oracles]
     for i, p in enumerate(oracles):
         a, c, d = p.set_x(p.get_x() + s[i])
         np.testing.assert_allclose(pos[i].numpy(), p.pos, atol=1e-10)
         np.testing.assert_allclose(dx_i[i].numpy(), a, atol=1e-12)
         np.testing.assert_allclose(dx_f[i].numpy(), c, atol=1e-9)
         np.testing.assert_allclose(g_par[i].numpy(), d, atol=1e-9)
+        nfev[i] = p.ode_nfev - nfev[i]
         # the fixed atoms have stayed where they were
         np.testing.assert_allclose(cs.calc(p.pos)[:nc], eng.x[i, :nc].numpy(), atol=1e-7)
     assert int(eng.status.max()) == 0
+    if angles is not True:                      # (the dihedral-rich cluster takes both steps in one iteration)
+        assert nfev[1] > nfev[0] and eng.ode_steps == (nfev[1] - 1) // 6
     if not nc:
         return
     # Newton projection onto the constraint manifold after a displaced start
