@@ -296,6 +296,12 @@ int sb_qr(double* A, int m, int n, double* Q, double* R, double* work, const int
           void* stream);
 int sb_trtri(const double* R, double* Rinv, double* work, int n, int32_t* status, const int32_t* active,
              int batch, void* stream);
+/* sb_potrf: in-place upper Cholesky factor of symmetric positive definite A [b, n, n] (A = R^T R; panels of 32
+ * in shared memory + one sb_gemm trailing update per panel; SB_ST_SINGULAR on a non-positive pivot).  With
+ * A = Bw^T Bw it gives the R factor of the Wilson matrix (np.linalg.qr at sella/peswrapper.py:691, _gpu.py:
+ * 100-111) where Q is not needed: the stages of the geodesic integrator (peswrapper.py:1200-1221) use
+ * B+ w = R^-1 R^-T Bw^T w.                                                                               */
+int sb_potrf(double* A, int n, int32_t* status, const int32_t* active, int batch, void* stream);
 
 /* ---- compact representation of the approximate Hessian and of its spectrum --------------------
  * B = lam0 I + VR^T diag(theta - lam0) VR: mrows[b] explicit eigenpairs (theta ascending in

@@ -327,6 +327,11 @@ int sb_qr(double* A, int m, int n, double* Q, double* R, double* work, const int
     if (m < n || n < 1 || batch < 1 || !work) return -1;
     return sb_qr_impl(A, m, n, Q, R, work, active, batch, (cudaStream_t)stream);
 }
+extern "C" int sb_potrf_impl(double*, int, int*, const int*, int, cudaStream_t);
+int sb_potrf(double* A, int n, int32_t* status, const int32_t* active, int batch, void* stream) {
+    if (n < 1 || batch < 1) return -1;
+    return sb_potrf_impl(A, n, status, active, batch, (cudaStream_t)stream);
+}
 int sb_trtri(const double* R, double* Rinv, double* work, int n, int32_t* status, const int32_t* active, int batch,
              void* stream) {
     if (n < 1 || batch < 1 || !work) return -1;

@@ -280,6 +280,74 @@ trtri_block_kernel(const double* __restrict__ R_, double* __restrict__ X_, int n
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Blocked Cholesky G = R^T R (R upper) of symmetric positive definite matrices, in place, one CTA per system
+// and panel: the diagonal block is factored in shared memory, the block row to its right is solved against it
+// (R12 = R11^-T G12, one thread per column, coalesced along the row), the trailing block is updated by
+// ONE GEMM per panel (G22 -= R12^T R12) launched by the host loop.  With G = Bw^T Bw this yields the R factor
+// of the Wilson matrix from one big GEMM + n/32 small panels instead of a Householder QR (the geodesic stages
+// only need R: B+ w = R^-1 R^-T Bw^T w).
+constexpr int CH_NB = 32, CH_THREADS = 256;
+
+__global__ void __launch_bounds__(CH_THREADS)
+chol_panel_kernel(double* __restrict__ A_, int n, int p0, int nb, int* __restrict__ status,
+                  const int* __restrict__ active) {
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    __shared__ double D[CH_NB][CH_NB + 1];
+    __shared__ int bad;
+    double* A = A_ + (size_t)b * n * n;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) bad = 0;
+    for (int idx = tid; idx < nb * nb; idx += nt) {
+        const int i = idx / nb, j = idx % nb;
+        D[i][j] = A[(size_t)(p0 + i) * n + p0 + j];
+    }
+    __syncthreads();
+    // unblocked upper Cholesky of the diagonal block: row k of R, then the rank-one downdate of the rest
+    for (int k = 0; k < nb; ++k) {
+        const double akk = D[k][k];
+        __syncthreads();
+        if (!(akk > 0.0)) {
+            if (tid == 0) { bad = 1; }
+            // keep going with a unit pivot so that every thread follows the same control flow
+        }
+        const double d = (akk > 0.0) ? sqrt(akk) : 1.0;
+        for (int j = k + tid; j < nb; j += nt) D[k][j] = (j == k) ? d : D[k][j] / d;
+        __syncthreads();
+        const int rem = nb - k - 1;
+        for (int idx = tid; idx < rem * rem; idx += nt) {
+            const int i = k + 1 + idx / rem, j = k + 1 + idx % rem;
+            if (j >= i) D[i][j] = fma(-D[k][i], D[k][j], D[i][j]);
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < nb * nb; idx += nt) {
+        const int i = idx / nb, j = idx % nb;
+        A[(size_t)(p0 + i) * n + p0 + j] = (j >= i) ? D[i][j] : 0.0;
+    }
+    // block row to the right: solve R11^T x = g for every column (forward substitution)
+    const int nr = n - p0 - nb;
+    for (int c = tid; c < nr; c += nt) {
+        double x[CH_NB];                       // fully unrolled below: stays in registers
+        double* col = A + (size_t)p0 * n + p0 + nb + c;
+#pragma unroll
+        for (int i = 0; i < CH_NB; ++i) x[i] = (i < nb) ? col[(size_t)i * n] : 0.0;
+#pragma unroll
+        for (int k = 0; k < CH_NB; ++k) {
+            // (rows beyond nb: D is not loaded there; their x stays 0 and is never stored)
+            const double xk = (k < nb) ? x[k] / D[k][k] : 0.0;
+            x[k] = xk;
+#pragma unroll
+            for (int i = k + 1; i < CH_NB; ++i) x[i] = (i < nb) ? fma(-D[k][i], xk, x[i]) : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < CH_NB; ++i)
+            if (i < nb) col[(size_t)i * n] = x[i];
+    }
+    if (tid == 0 && bad && status) atomicOr(&status[b], SB_ST_SINGULAR);
+}
+
 __global__ void zero_lower_kernel(double* __restrict__ X_, int n, const int* __restrict__ active) {
     const int b = blockIdx.y;
     if (active && !active[b]) return;
@@ -387,6 +455,27 @@ extern "C" int sb_trtri_impl(const double* R, double* X, double* work, int n, in
     zero_lower_kernel<<<grid, 256, 0, st>>>(X, n, active);
     const int rc = trtri_rec(R, X, work, n, 0, n, status, active, batch, st);
     if (rc) return rc;
+    return SB_LAUNCH_CHECK();
+}
+
+// In place: A [b, n, n] symmetric positive definite (full storage) -> upper Cholesky factor R (A = R^T R),
+// strictly lower part zeroed.  SB_ST_SINGULAR: a non-positive pivot (rank-deficient / indefinite input).
+extern "C" int sb_potrf_impl(double* A, int n, int* status, const int* active, int batch, cudaStream_t st) {
+    const long long sN = (long long)n * n;
+    for (int p0 = 0; p0 < n; p0 += CH_NB) {
+        const int nb = (n - p0 < CH_NB) ? n - p0 : CH_NB, nr = n - p0 - nb;
+        SB_COUNT(1);
+        chol_panel_kernel<<<batch, CH_THREADS, 0, st>>>(A, n, p0, nb, status, active);
+        if (nr > 0) {
+            const double* R12 = A + (size_t)p0 * n + p0 + nb;               // [nb, nr], ld n
+            double* A22 = A + (size_t)(p0 + nb) * n + p0 + nb;             // [nr, nr], ld n
+            const int rc = sb_gemm_impl(1, 0, nr, nr, nb, -1.0, R12, n, sN, R12, n, sN, 1.0, A22, n, sN, active, batch, st);
+            if (rc) return rc;
+        }
+    }
+    dim3 grid((n * n + 255) / 256, batch);
+    SB_COUNT(1);
+    zero_lower_kernel<<<grid, 256, 0, st>>>(A, n, active);
     return SB_LAUNCH_CHECK();
 }
 

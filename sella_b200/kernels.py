@@ -197,6 +197,17 @@ def qr(A, active=None, want_q=True):
     return Q, R
 
 
+def potrf(A, active=None, status=None):
+    """Upper Cholesky factor R (A = R^T R) of symmetric positive definite A [b, n, n]; A is not modified."""
+    require_cuda()
+    check_f64(A)
+    b, n, _ = A.shape
+    R = A.clone()
+    status = torch.zeros(b, dtype=torch.int32, device=A.device) if status is None else status
+    call("sb_potrf", _p(R), I(n), _p(status), _p(_mask(active)), I(b), _stream())
+    return R, status
+
+
 def trtri(R, active=None, status=None):
     """Inverse of the upper-triangular R [b, n, n]."""
     require_cuda()

@@ -125,3 +125,29 @@ def test_wilson_algebra():
         np.testing.assert_allclose(dfp[i], ref_df, rtol=1e-11, atol=1e-11)
         P = Qr @ Qr.T                                                                                # :72-82
         np.testing.assert_allclose(H0[i], P @ np.diag(h0) @ P, atol=1e-11)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [5, 32, 47, 96, 384])
+def test_potrf_against_lapack(n):
+    """sb_potrf: upper Cholesky factor of B^T B (the R factor of a tall matrix B up to row signs), and the
+    non-positive-pivot flag on an indefinite input."""
+    torch = pytest.importorskip("torch")
+    from sella_b200 import kernels as K
+    dev = torch.device("cuda:0")
+    rng = np.random.RandomState(n)
+    b = 5
+    Bm = rng.normal(size=(b, 2 * n + 3, n))
+    G = np.einsum("bki,bkj->bij", Bm, Bm)
+    R, st = K.potrf(torch.from_numpy(G).to(dev))
+    R = R.cpu().numpy()
+    assert int(st.abs().sum()) == 0
+    for i in range(b):
+        ref = np.linalg.cholesky(G[i]).T
+        np.testing.assert_allclose(R[i], ref, rtol=1e-11, atol=1e-11 * np.abs(ref).max())
+        assert np.array_equal(np.tril(R[i], -1), np.zeros((n, n)))
+        Rq = np.linalg.qr(Bm[i], mode="r")
+        np.testing.assert_allclose(np.abs(R[i]), np.abs(Rq), rtol=1e-9, atol=1e-9 * np.abs(Rq).max())
+    G[2] -= 2.0 * np.linalg.eigvalsh(G[2])[0] * np.eye(n) + np.eye(n)       # indefinite
+    _, st = K.potrf(torch.from_numpy(G).to(dev))
+    assert int(st[2]) & 16 and int(st[0]) == 0

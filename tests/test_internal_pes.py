@@ -182,6 +182,11 @@ class _FakeK:
         return (Q.contiguous() if want_q else None), R.contiguous()
 
     @staticmethod
+    def potrf(A, **kw):
+        import torch
+        return torch.linalg.cholesky(A, upper=True).contiguous(), torch.zeros(A.shape[0], dtype=torch.int32)
+
+    @staticmethod
     def trtri(R, **kw):
         import torch
         return torch.linalg.inv(R).contiguous(), torch.zeros(R.shape[0], dtype=torch.int32)
