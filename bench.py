@@ -1002,6 +1002,8 @@ def run_internal(args):
     geo = eng.geo
     Bw = geo["Bw"]
     Rw = K.qr(Bw)[1]
+    Gw = K.gemm(Bw, Bw, transA=True)
+    Gw = (0.5 * (Gw + Gw.transpose(1, 2))).contiguous()
     ncart = n
     phases = dict(
         wilson_qB=timed(lambda: eng.ints.calc(eng.pos, jacobian=True), 3),
@@ -1011,7 +1013,12 @@ def run_internal(args):
         geometry_total=timed(lambda: eng._geometry(eng.pos), 2),
         model_total=timed(lambda: eng._model(), 2),
         geodesic_total=timed(lambda: eng._set_x(eng.x + eng.s), 1),
-        eigh_ncart=timed(lambda: K.eigh(geo["HLr"].contiguous()), 2))
+        eigh_ncart=timed(lambda: K.eigh(geo["HLr"].contiguous()), 2),
+        eigvalsh_ncart=timed(lambda: K.eigvalsh(geo["HLr"].contiguous()), 2),
+        wilson_gram_gemm=timed(lambda: K.gemm(Bw, Bw, transA=True), 3),
+        wilson_potrf=timed(lambda: K.potrf(Gw), 3),
+        wilson_factor_R=timed(lambda: eng._factor(Bw, want_q=False), 3),
+        wilson_factor_QR=timed(lambda: eng._factor(Bw, want_q=True), 3))
     xv = eng.g.view(b, 1, nint)
     yv = torch.empty_like(xv)
     hv_ms = timed(lambda: K.hv_ld(eng.B, xv, yv, 1), 10)
@@ -1036,12 +1043,20 @@ def run_internal(args):
         fp64 = best
     except Exception:
         fp64 = None
+    gram_flops = 2.0 * b * nint * ncart * ncart
+    gach = gram_flops / (phases["wilson_gram_gemm"] * 1e-3) / 1e12
+    roofline_gemm = dict(kernel="gemm_kernel (sb_gemm): G = Bw^T Bw [%d x %d x %d], fp64 tensor-core tiles (DMMA m8n8k4, "
+                                "64 x 64 x 16); feeds sb_potrf, the R factor of every Wilson-matrix factorisation" % (ncart, ncart, nint),
+                         bound="tensor", achieved=gach, peak=fp64, unit="TFLOP/s", frac=(gach / fp64) if fp64 else None,
+                         traffic=None, ms_per_launch=phases["wilson_gram_gemm"], flops_per_launch=gram_flops,
+                         peak_source="measured here (sb_fp64_peak: max of DFMA and DMMA loops)")
     ach = qr_flops / (phases["wilson_qr"] * 1e-3) / 1e12
     roofline_qr = dict(kernel="sb_qr: blocked Householder QR of the Wilson matrix [%d x %d] (16-column panels in shared "
                               "memory, compact WY, DMMA trailing updates) incl. the explicit Q" % (nint, ncart),
                        bound="tensor", achieved=ach, peak=fp64, unit="TFLOP/s", frac=(ach / fp64) if fp64 else None,
                        traffic=None, ms_per_launch=phases["wilson_qr"], flops_per_launch=qr_flops,
-                       calls_per_step="7 per geodesic (one per Dormand-Prince stage with exact_geodesic) + 1",
+                       calls_per_step="not on the geodesic path any more (R comes from sb_potrf of Bw^T Bw: phase_ms "
+                                      "wilson_factor_R / _QR); still factors the constraint rows per geometry",
                        peak_source="measured here (sb_fp64_peak: max of DFMA and DMMA loops)")
     out = None
     if rank == 0:
@@ -1057,7 +1072,7 @@ def run_internal(args):
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                    ms_per_step=step_ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                    data="synthetic", config=cfg, clocks=clocks, e2e=e2e, gpu_launches=int(launches), parity=parity,
-                   roofline=roofline, roofline_qr=roofline_qr, phase_ms=phases,
+                   roofline=roofline, roofline_gemm=roofline_gemm, roofline_qr=roofline_qr, phase_ms=phases,
                    geodesic_steps_per_call=(eng.ode_steps - ode0) / max(1, args.steps), systems_flagged=flagged,
                    diagonalisations=eng.ndiag)
         if world == 1 and not args.no_cpu_baseline:

@@ -201,22 +201,21 @@ class BatchedInternalSella(BatchedSella):
     def _factor(self, Bw, want_q=True, idx=None):
         """(Q, Rinv) with Bw = Q Rinv^-1 on range(Bw) and B+ = Rinv Q^T (peswrapper.py:674-736).
 
-        Full column rank (slabs / crystals with held atoms): economy QR, Rinv = R^-1.  Rank deficient (a free
+        Full column rank (slabs / crystals with held atoms): R = chol(Bw^T Bw), Rinv = R^-1, Q = Bw Rinv (the
+        factors of the economy QR up to signs).  Rank deficient (a free
         molecule: the six rigid-body directions, the reference's SVD branch :691-704): the same two factors
         from the eigendecomposition of Bw^T Bw = V S^2 V^T -- Rinv = V S^-1, Q = Bw Rinv with ZERO columns for
         the null directions (singular values <= 1e-6 as in the reference); eigenvalues come out ascending, so
         the null directions are the first `nnull` columns of every system."""
         if not self.svd_path:
-            if want_q:
-                Q, R = K.qr(Bw)
-                Rinv, st = K.trtri(R)
-            else:
-                # R alone (the geodesic stages): Cholesky factor of Bw^T Bw -- one GEMM + n/32 small panels
-                # instead of a Householder QR; the semi-normal equations it feeds are of the same accuracy class
-                G = K.gemm(Bw, Bw, transA=True)
-                Q, (R, st0) = None, K.potrf((0.5 * (G + G.transpose(1, 2))).contiguous())
-                Rinv, st = K.trtri(R)
-                st = st | st0
+            # R from the Cholesky factor of Bw^T Bw (one GEMM + n/32 small panels instead of a Householder QR),
+            # Q = Bw R^-1 where it is needed: orthonormal to kappa(Bw)^2 eps ~ 1e-14 for the Wilson matrices of
+            # bonded networks (kappa ~ 10), the accuracy class of the reference's own B+ = R^-1 Q^T
+            G = K.gemm(Bw, Bw, transA=True)
+            R, st0 = K.potrf((0.5 * (G + G.transpose(1, 2))).contiguous())
+            Rinv, st = K.trtri(R)
+            st = st | st0
+            Q = K.gemm(Bw, Rinv) if want_q else None
             rd = torch.diagonal(R, dim1=1, dim2=2).abs()
             bad = (rd.min(dim=1).values < 1e-6 * rd.max(dim=1).values).to(torch.int32) * SB_ST_WILSON_RANK | st
             if idx is None:
