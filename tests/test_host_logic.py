@@ -187,3 +187,53 @@ def test_bench_internal_problem_and_reference_arm():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["config"]["coordinates"] == "internal" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port"
+
+
+def test_internals_bookkeeping_and_sella_internal_arguments():
+    """Host-side `Internals` (sella/internal.py:3033-3260) and the argument checks of `Sella(internal=...)`
+    (optimize.py:237-252) -- nothing here touches the device."""
+    from sella_b200 import Sella, Internals, Constraints
+    from sella_b200.topology import DuplicateInternalError, Coord
+    from sella_b200.synthetic import fcc111_slab
+
+    class Atoms:
+        def __init__(self, pos, cell, pbc):
+            self.positions, self.cell, self.pbc = np.array(pos, float), cell, np.array(pbc)
+            self.numbers = np.full(len(pos), 29)
+
+        def __len__(self):
+            return len(self.positions)
+    pos, cell, pbc = fcc111_slab(3, 2, 2, seed=1, rattle=0.02)
+    at = Atoms(pos, cell, pbc)
+    ints = Internals(at)
+    ints.add_bond((0, 1), mic=True)
+    with pytest.raises(DuplicateInternalError):
+        ints.add_bond((0, 1), mic=True)
+    # a coordinate equals its reverse (internal.py:359-369); the minimum-image bond is the short one
+    assert Coord((0, 1), ints.internals["bonds"][0].ncvecs).same(ints.internals["bonds"][0].reverse())
+    assert ints.internals["bonds"][0].value(pos, cell) < 3.0
+    ints.add_translation(4)
+    assert ints.ntrans == 3 and ints.nint == 4
+    with pytest.raises(NotImplementedError):
+        ints.add_translation((0, 1, 2), 0)
+    with pytest.raises(NotImplementedError):
+        Internals(at, allow_fragments=True)
+    cons = Constraints(at)
+    cons.fix_translation(2)
+    cons.fix_bond((0, 3))
+    ic = Internals(at, cons=cons)
+    assert ic.ntrans == 3 and ic.nbonds == 1                      # constraint coordinates join the list first
+    ic.find_all_bonds()
+    rows, targets = ic.constraint_rows()
+    np.testing.assert_array_equal(rows, [0, 1, 2, 3])
+    np.testing.assert_allclose(targets[:3], pos[2])
+    assert np.isnan(targets[3])                                    # "hold the current value"
+    cp = ic.copy()
+    cp.add_angle((0, 1, 2))
+    assert cp.nangles == 1 and ic.nangles == 0
+    with pytest.raises(ValueError):                                # Internals AND Constraints (optimize.py:241-247)
+        Sella(at, internal=ic, constraints=Constraints(at), logfile=None)
+    with pytest.raises(NotImplementedError):
+        Sella(at, internal=True, hessian_function=lambda a: None, logfile=None)
+    with pytest.raises(NotImplementedError):
+        Sella(at, internal=True, optimize_cell=True, logfile=None)
