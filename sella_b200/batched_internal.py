@@ -34,7 +34,7 @@ import torch
 
 from . import kernels as K
 from ._lib import I, D, LL, _p, _stream, call, check_f64
-from .batched import BatchedSella, DAV_EXPAND, _Spec
+from .batched import BatchedSella, _Spec
 
 SB_ST_WILSON_RANK = 256        # (1..64 are the library's SB_ST_* bits, include/sella_b200.h)
 SB_ST_GEODESIC = 512
@@ -470,14 +470,11 @@ class BatchedInternalSella(BatchedSella):
         self.AV.copy_(self._free_project(self.geo, self.AV))
 
     def _flush_history(self, part, nv, nl):
-        hc = dict(Hc=None, HcVs=None) if self.nc else None
-        if hc is not None:
-            hcvs = self._hc_apply(self.geo, self.Vs)
-            call("sb_history_ritz", _p(self.Vs), _p(self.AVs), I(self.kcap), _p(self.nhist), I(self.n), _p(self.nvec),
-                 _p(self.dav_state), _p(self.status), _p(hcvs), I(self.batch), _stream())
-        else:
-            call("sb_history_ritz", _p(self.Vs), _p(self.AVs), I(self.kcap), _p(self.nhist), I(self.n), _p(self.nvec),
-                 _p(self.dav_state), _p(self.status), _p(None), I(self.batch), _stream())
+        """PES.diag tail (peswrapper.py:541-551): Atilde = Vs^T sym(Vs, AVs) - Vs^T Hc Vs, Ritz rotation of the
+        operator history, one block update of H."""
+        hcvs = self._hc_apply(self.geo, self.Vs) if self.nc else None
+        call("sb_history_ritz", _p(self.Vs), _p(self.AVs), I(self.kcap), _p(self.nhist), I(self.n), _p(self.nvec),
+             _p(self.dav_state), _p(self.status), _p(hcvs), I(self.batch), _stream())
         self._update(self.Vs, self.AVs, self.upk, self.nvec, nv, part)
 
     def _hnorm(self):
