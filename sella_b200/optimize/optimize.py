@@ -62,6 +62,24 @@ except Exception:
             return self.converged()
 
 
+def _open_trajectory(trajectory, atoms, append, master):
+    """optimize.py:144-150: a file name opens a trajectory attached to the atoms -- ASE's `Trajectory` when ASE is
+    installed (the reference's format), else / for *.xyz names the extended-XYZ writer of
+    sella_b200.utilities.trajectory; an object with a write() method is used as it is."""
+    if trajectory is None:
+        return None
+    if isinstance(trajectory, str):
+        mode = "a" if append else "w"
+        if _HAVE_ASE and not trajectory.lower().endswith((".xyz", ".extxyz")):
+            from ase.io.trajectory import Trajectory
+            return Trajectory(trajectory, mode=mode, atoms=atoms, master=master)
+        from ..utilities.trajectory import XYZTrajectory
+        return XYZTrajectory(trajectory, mode=mode, atoms=atoms)
+    if not hasattr(trajectory, "write"):
+        raise TypeError("trajectory must be a file name or an object with a write() method")
+    return trajectory
+
+
 class _CalculatorSurface:
     """PES plug-in that evaluates the user's ASE calculator on the host (batch of one)."""
 
@@ -76,8 +94,12 @@ class _CalculatorSurface:
         self.atoms.positions = x[0].cpu().numpy().reshape((-1, 3))
         f = float(self.atoms.get_potential_energy())
         g = -np.asarray(self.atoms.get_forces(), dtype=np.float64).ravel()
-        if self.traj is not None:
-            self.traj.write()            # PES.eval writes every evaluated geometry (peswrapper.py:409-418)
+        if self.traj is not None:        # PES.eval writes every evaluated geometry (peswrapper.py:409-418)
+            from ..utilities.trajectory import XYZTrajectory
+            if isinstance(self.traj, XYZTrajectory):
+                self.traj.write(self.atoms, energy=f, forces=-g.reshape(-1, 3))
+            else:
+                self.traj.write()
         self.atoms.positions = old
         f_out.copy_(torch.tensor([f], dtype=torch.float64))
         g_out.copy_(torch.from_numpy(g).view(1, -1))
@@ -517,15 +539,7 @@ class Sella(_Base):
         diag_maxiter = kwargs.pop("diag_maxiter", None)
         if kwargs:
             raise TypeError("unsupported keyword arguments: %s" % sorted(kwargs))
-        if trajectory is not None and isinstance(trajectory, str):
-            # optimize.py:144-150: a file name opens an ASE Trajectory attached to the atoms
-            if not _HAVE_ASE:
-                raise NotImplementedError("trajectory=<file name> needs ASE (ase.io.trajectory.Trajectory); "
-                                          "pass an object with a write() method or install ASE")
-            from ase.io.trajectory import Trajectory
-            trajectory = Trajectory(trajectory, mode="a" if append_trajectory else "w", atoms=atoms, master=master)
-        elif trajectory is not None and not hasattr(trajectory, "write"):
-            raise TypeError("trajectory must be a file name or an object with a write() method")
+        trajectory = _open_trajectory(trajectory, atoms, append_trajectory, master)
         if restart is not None and not _HAVE_ASE:
             # the reference hands `restart` to ase.optimize.Optimizer (it has no read() of its own)
             raise NotImplementedError("restart files are handled by ASE's Optimizer, which is not installed")
@@ -583,12 +597,7 @@ class Sella(_Base):
             raise NotImplementedError("iterative_stepper is not on the CUDA path (the geodesic integrator is)")
         if kwargs:
             raise TypeError("unsupported keyword arguments: %s" % sorted(kwargs))
-        if trajectory is not None and not hasattr(trajectory, "write"):
-            if not _HAVE_ASE:
-                raise NotImplementedError("trajectory=<file name> needs ASE (ase.io.trajectory.Trajectory); "
-                                          "pass an object with a write() method or install ASE")
-            from ase.io.trajectory import Trajectory
-            trajectory = Trajectory(trajectory, mode="a" if append_trajectory else "w", atoms=atoms, master=master)
+        trajectory = _open_trajectory(trajectory, atoms, append_trajectory, master)
         if restart is not None and not _HAVE_ASE:
             raise NotImplementedError("restart files are handled by ASE's Optimizer, which is not installed")
         _Base.__init__(self, atoms, restart=restart, logfile=logfile, trajectory=None, master=master)

@@ -237,3 +237,52 @@ def test_internals_bookkeeping_and_sella_internal_arguments():
         Sella(at, internal=True, hessian_function=lambda a: None, logfile=None)
     with pytest.raises(NotImplementedError):
         Sella(at, internal=True, optimize_cell=True, logfile=None)
+
+
+def test_xyz_trajectory_writer(tmp_path):
+    """f4: a frame per evaluated geometry without ASE (peswrapper.py:409-418 writes an ASE Trajectory)."""
+    from sella_b200.utilities.trajectory import XYZTrajectory
+    from sella_b200.optimize.optimize import _open_trajectory, _CalculatorSurface
+
+    class Atoms:
+        def __init__(self):
+            self.positions = np.array([[0.0, 0.0, 0.0], [1.5, 0.2, -0.1]])
+            self.numbers = np.array([29, 8])
+            self.cell = np.diag([5.0, 6.0, 7.0])
+            self.pbc = np.array([True, True, False])
+
+        def __len__(self):
+            return 2
+
+        def get_potential_energy(self):
+            return float((self.positions ** 2).sum())
+
+        def get_forces(self):
+            return -2.0 * self.positions
+    at = Atoms()
+    name = str(tmp_path / "run.xyz")
+    traj = _open_trajectory(name, at, False, None)
+    assert isinstance(traj, XYZTrajectory)
+    torch = pytest.importorskip("torch")
+    surf = _CalculatorSurface(at, traj=traj)
+    f, g = torch.zeros(1, dtype=torch.float64), torch.zeros(1, 6, dtype=torch.float64)
+    for k in range(3):
+        surf.evaluate(torch.from_numpy(at.positions.reshape(1, -1) + 0.1 * k), f, g)
+    traj.close()
+    assert surf.neval == 3 and traj.nframes == 3
+    lines = open(name).read().splitlines()
+    assert len(lines) == 3 * 4 and lines[0] == "2" and lines[2].split()[0] == "Cu" and lines[3].split()[0] == "O"
+    assert 'Lattice="5.0000000000 0.0000000000' in lines[1] and 'pbc="T T F"' in lines[1] and "forces:R:3" in lines[1]
+    e2 = float([t for t in lines[9].split() if t.startswith("energy=")][0].split("=")[1])
+    np.testing.assert_allclose(e2, ((at.positions + 0.2) ** 2).sum(), rtol=1e-11)
+    row = np.array(lines[10].split()[1:], dtype=float)
+    np.testing.assert_allclose(row[:3], at.positions[0] + 0.2, atol=1e-9)
+    np.testing.assert_allclose(row[3:], -2.0 * (at.positions[0] + 0.2), atol=1e-9)
+    # append mode continues the file; an object with write() is used as it is; anything else is rejected
+    t2 = _open_trajectory(name, at, True, None)
+    t2.write(energy=1.0)
+    t2.close()
+    assert len(open(name).read().splitlines()) == 4 * 4
+    assert _open_trajectory(t2, at, False, None) is t2
+    with pytest.raises(TypeError):
+        _open_trajectory(3.5, at, False, None)
