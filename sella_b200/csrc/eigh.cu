@@ -371,8 +371,13 @@ ql_kernel(double* __restrict__ dio, double* __restrict__ eio, double* __restrict
             }
             __syncthreads();
             const int flag = sh_flag, m = sh_m, lo = sh_l_lo;
-            if (flag == 2) { failed = true; break; }
-            if (flag == 0) break;               // e[l] negligible: eigenvalue l done
+            if (flag != 1) {
+                // leaving the sweep loop: thread 0 goes straight on to the next eigenvalue and rewrites the flags --
+                // every thread must have read them first (compute-sanitizer racecheck, profiles/sanitizer_r2_*)
+                __syncthreads();
+                if (flag == 2) failed = true;
+                break;
+            }
             if (Mt_ && lo <= m - 1) apply_sweep<CPT>(Mt, cs, n, lo, m, tid, nt);
             ++iter;
             __syncthreads();
