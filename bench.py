@@ -1045,10 +1045,14 @@ def run_internal(args):
         fp64 = None
     gram_flops = 2.0 * b * nint * ncart * ncart
     gach = gram_flops / (phases["wilson_gram_gemm"] * 1e-3) / 1e12
+    gtraffic, gsrc = (ncu_traffic(("ncu_full_r2_wilson.csv",), r"gemm_kernel", per="max")
+                      if (b, n) == (1024, 384) else (None, None))
     roofline_gemm = dict(kernel="gemm_kernel (sb_gemm): G = Bw^T Bw [%d x %d x %d], fp64 tensor-core tiles (DMMA m8n8k4, "
                                 "64 x 64 x 16); feeds sb_potrf, the R factor of every Wilson-matrix factorisation" % (ncart, ncart, nint),
                          bound="tensor", achieved=gach, peak=fp64, unit="TFLOP/s", frac=(gach / fp64) if fp64 else None,
-                         traffic=None, ms_per_launch=phases["wilson_gram_gemm"], flops_per_launch=gram_flops,
+                         traffic=gtraffic, traffic_source=("profiles/" + gsrc) if gsrc else None,
+                         algorithmic_bytes=b * 8.0 * (nint * ncart + ncart * ncart),
+                         ms_per_launch=phases["wilson_gram_gemm"], flops_per_launch=gram_flops,
                          peak_source="measured here (sb_fp64_peak: max of DFMA and DMMA loops)")
     ach = qr_flops / (phases["wilson_qr"] * 1e-3) / 1e12
     roofline_qr = dict(kernel="sb_qr: blocked Householder QR of the Wilson matrix [%d x %d] (16-column panels in shared "
