@@ -435,3 +435,68 @@ def test_sella_internal_true_on_a_free_cluster():
     assert dyn.run(1e-3, 300)
     assert at.get_potential_energy() < e0
     assert np.linalg.norm(at.get_forces(), axis=1).max() < 1e-3
+
+
+# ----------------------------------------------------------------------------------------------
+# more of the oracle's InternalPES (CPU): the variants of set_x the reference offers lead to the same place
+def test_oracle_set_x_variants_agree():
+    """peswrapper.py:749-903: the Newton ("iterative") stepper, the geodesic with the exact B+ and the geodesic with
+    B+ frozen at the start reach the same geometry for a moderate step (to the integrators' tolerances), keep the
+    constrained coordinates, and report consistent (dx_initial, dx_final, g_par)."""
+    at, cons, ints = slab_problem(31)
+    cs, csc, rows = oracle_sets(ints)
+    rng = np.random.RandomState(2)
+    out = {}
+    for name, kw in (("ode", {}), ("frozen", dict(exact_geodesic=False)), ("newton", dict(iterative_stepper=1)),
+                     ("rk", dict(integrator="rk"))):
+        p = InternalPES(at.func, at.positions.ravel(), cs, csc, **kw)
+        p.get_g()
+        Uf = p.get_Ufree()
+        s = Uf @ (Uf.T @ (0.03 * np.random.RandomState(2).normal(size=cs.nint)))
+        x0 = p.get_x()
+        dx_i, dx_f, g_par = p.set_x(x0 + s)
+        out[name] = (p.pos.copy(), dx_i, dx_f, g_par, p.get_x() - x0)
+        np.testing.assert_allclose(cs.calc(p.pos)[:len(rows)], x0[:len(rows)], atol=1e-6)     # fixed atoms stay
+        np.testing.assert_allclose(dx_i, s, atol=1e-12)
+        # the realised change of the NON-redundant part of q equals the requested one to second order
+        Q = p._jacobian_qr()[0]
+        assert np.linalg.norm(Q.T @ ((p.get_x() - x0) - s)) < 0.05 * np.linalg.norm(s)
+    for name in ("frozen", "newton", "rk"):
+        np.testing.assert_allclose(out[name][0], out["ode"][0], atol=5e-4, err_msg=name)
+    np.testing.assert_allclose(out["rk"][0], out["ode"][0], atol=2e-5)
+    np.testing.assert_allclose(out["rk"][3], out["ode"][3], atol=1e-3)                         # transported gradient
+
+
+def test_oracle_constraint_projection_and_dihedral_unwrapping():
+    """_project_to_constraints (peswrapper.py:928-994) pulls a displaced constrained coordinate back without
+    touching the free internal coordinates to first order; get_x continues dihedrals across +-pi (:996-1008)."""
+    at, cons, ints = cluster_problem(31)
+    cs, csc, rows = oracle_sets(ints)
+    p = InternalPES(at.func, at.positions.ravel(), cs, csc)
+    p.get_g()
+    q0 = p.get_x()
+    p.pos = p.pos.copy()
+    p.pos[:3] += np.array([2e-3, -1e-3, 1.5e-3])             # atom 0 is held: residual 2e-3
+    assert np.abs(p.get_res()).max() > 1e-3
+    q1 = cs.calc(p.pos)
+    Uf = p._calc_basis()[3]
+    assert p._project_to_constraints()
+    assert np.abs(p.get_res()).max() < 1e-7
+    # the correction lives in the constraint subspace: the free internal coordinates of the displaced geometry
+    # are unchanged to first order in the residual (2e-3)
+    moved = cs.wrap(cs.calc(p.pos) - q1)
+    assert np.linalg.norm(Uf.T @ moved) < 0.05 * np.linalg.norm(moved)
+    # a step larger than the safety limit is refused (the optimiser's step must not be overridden)
+    p.pos[:3] += 0.2
+    before = p.pos.copy()
+    assert not p._project_to_constraints()
+    np.testing.assert_array_equal(p.pos, before)
+    # dihedral continuation
+    lo = cs.ntrans + cs.nbonds + cs.nangles
+    p2 = InternalPES(at.func, at.positions.ravel(), cs, csc)
+    p2.get_g()
+    x = p2.get_x()
+    k = lo + int(np.argmax(np.abs(x[lo:])))                   # the dihedral closest to +-pi
+    p2.curr["x"] = x.copy()
+    p2.curr["x"][k] = x[k] + 2 * np.pi * np.sign(x[k]) - 1e-3 * np.sign(x[k])     # "previous" value just across the cut
+    assert abs(p2.get_x()[k] - p2.curr["x"][k]) < 2e-3
