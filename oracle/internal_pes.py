@@ -27,9 +27,15 @@ Dormand-Prince 5(4) scheme with per-system step control that the CUDA engine run
 (sella_b200/batched_internal.py), restated here so that engine and oracle can be compared step by
 step; tests/test_internal_pes.py checks that both integrators lead to the same converged geometry.
 
-PARITY UNPINNED against the reference's own ``InternalPES`` object: it needs jax + ase, neither
-is installed.  Its ingredients are pinned separately (steppers / restricted step / Hessian update /
-Davidson against tests/golden, the coordinate derivatives by finite differences).
+PINNED against the reference's own ``InternalPES`` / ``MaxInternalStep`` / ``Sella.step`` code as far as this
+image allows: ``tests/golden/internal_loop.npz`` holds seven trajectories produced by the UNMODIFIED reference
+files driven through ``oracle/ref_internal_harness.py`` (slabs with held atoms: prfo, qn, frozen B+, Newton
+stepper; a cluster with bonds + angles + dihedrals; free clusters through the SVD branch, saddle search and
+minimisation), and ``tests/test_oracle_golden.py::test_internal_pes_oracle_matches_reference_internal_pes``
+reproduces every step (positions 2e-8 A, trust radius 1e-8, rho 1e-6, final Hessian 1e-6).  What stays
+unpinned is only what JAX computes in the reference: the coordinate derivatives themselves (both sides of that
+comparison take them from ``oracle/intcoords.py``; they are checked by finite differences and, for the assembly,
+against the reference's ``SparseInternalHessians``).
 """
 import numpy as np
 from scipy.integrate import LSODA

@@ -359,7 +359,54 @@ def golden_sparse_hessians(ref):
     save("sparse_hessians", **out)
 
 
+def golden_internal_loop(ref):
+    """The reference's own InternalPES + MaxInternalStep + Sella.step (peswrapper.py:609-1288,
+    restricted_step.py:186-243, optimize.py:317-440) on the EMT-form surface, driven through
+    oracle/ref_internal_harness.py: coordinate values and derivatives come from oracle.intcoords (JAX is absent),
+    every line of the internal-coordinate search itself is the reference's."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_internal_pes import slab_problem, cluster_problem, molecule_problem, oracle_sets
+    from oracle.ref_internal_harness import make_reference_internal_sella
+    cases = [("slab", slab_problem(40), dict(method="prfo"), 8),
+             ("slab", slab_problem(41), dict(method="qn"), 8),
+             ("slab", slab_problem(42), dict(method="prfo", exact_geodesic=False), 8),
+             ("slab", slab_problem(43), dict(method="prfo", iterative_stepper=1), 8),
+             ("cluster", cluster_problem(31), dict(method="prfo"), 6),
+             ("free", molecule_problem(0), dict(method="prfo"), 6),
+             ("free", molecule_problem(1), dict(order=0), 10)]
+    out = {}
+    for i, (kind, (at, cons, ints), kw, nsteps) in enumerate(cases):
+        cs, csc, rows = oracle_sets(ints)
+        tr, bd, an, dh, tv = ints.lists()
+        dyn = make_reference_internal_sella(ref, at.func, at.positions, cs, csc, cell=at.cell, pbc=at.pbc, **kw)
+        dyn.diagkwargs["maxiter"] = 6
+        n = at.positions.size
+        X = np.empty((nsteps, n)); D = np.empty(nsteps); R = np.empty(nsteps); F = np.empty(nsteps)
+        for t in range(nsteps):
+            dyn.step()
+            X[t] = dyn.pes.atoms.positions.ravel(); D[t] = dyn.delta; R[t] = dyn.rho; F[t] = dyn.pes.get_f()
+        out["meta%d" % i] = np.array([kind, repr(sorted(kw.items()))])
+        out["pos0_%d" % i] = np.array(at.positions)       # (the harness works on its own copy)
+        out["numbers%d" % i] = at.numbers
+        out["cell%d" % i] = np.zeros((0, 3)) if at.cell is None else np.asarray(at.cell)
+        out["pbc%d" % i] = np.asarray(at.pbc)
+        out["trans%d" % i] = np.asarray(tr, dtype=int).reshape(-1, 2)
+        out["bonds%d" % i] = np.asarray(bd, dtype=int).reshape(-1, 2)
+        out["angles%d" % i] = np.asarray(an, dtype=int).reshape(-1, 3)
+        out["diheds%d" % i] = np.asarray(dh, dtype=int).reshape(-1, 4)
+        for k in ("bonds", "angles", "dihedrals"):
+            out["tv_%s%d" % (k, i)] = tv[k]
+        out["rows%d" % i] = rows
+        out["x%d" % i], out["delta%d" % i], out["rho%d" % i], out["f%d" % i] = X, D, R, F
+        out["H%d" % i] = dyn.pes.H.B
+        out["neval%d" % i] = np.array(dyn.pes.neval)
+    out["ncases"] = np.array(len(cases))
+    save("internal_loop", **out)
+
+
 def main():
+    if "--internal-only" in sys.argv:
+        return golden_internal_loop(ref_loader.load())
     golden_rotation()
     if "--rotation-only" in sys.argv:
         return
@@ -373,6 +420,7 @@ def main():
     golden_restricted(ref)
     golden_loop(ref)
     golden_sparse_hessians(ref)
+    golden_internal_loop(ref)
 
 
 if __name__ == "__main__":

@@ -313,3 +313,50 @@ def test_projected_spectrum_identity_used_by_the_engine():
     np.testing.assert_allclose(delta, Bp - B, atol=1e-10)
     sv = np.linalg.svd(Bp - B, compute_uv=False)
     assert int((sv > 1e-10 * sv[0]).sum()) == 2 * nc
+
+
+def _internal_case(G, i):
+    """Rebuild the inputs of case i of internal_loop.npz: coordinate sets, surface, keyword arguments."""
+    import ast
+    from oracle.intcoords import CoordinateSet
+    from oracle import emt as oemt
+    pos0 = G["pos0_%d" % i]
+    cell = G["cell%d" % i]
+    cell = None if cell.shape[0] == 0 else cell
+    pbc = tuple(bool(p) for p in G["pbc%d" % i])
+    tv = {k: G["tv_%s%d" % (k, i)] for k in ("bonds", "angles", "dihedrals")}
+    tr = [tuple(t) for t in G["trans%d" % i]]
+    cs = CoordinateSet(len(pos0), tr, G["bonds%d" % i], G["angles%d" % i], G["diheds%d" % i], tvecs=tv,
+                       numbers=G["numbers%d" % i])
+    rows = G["rows%d" % i]
+    csc = CoordinateSet(len(pos0), [tr[r] for r in rows]) if len(rows) else None
+    kw = dict(ast.literal_eval(str(G["meta%d" % i][1])))
+    return pos0, cs, csc, oemt.emt_func(cell, pbc), kw
+
+
+@pytest.mark.parametrize("case", range(7))
+def test_internal_pes_oracle_matches_reference_internal_pes(golden, case):
+    """oracle/internal_pes.py + oracle/driver.py against the trajectory of the reference's OWN InternalPES,
+    MaxInternalStep and Sella.step (tests/golden/internal_loop.npz, produced by make_golden.py through
+    oracle/ref_internal_harness.py): slabs in bond coordinates with held atoms (prfo, qn, frozen B+, Newton
+    stepper), a cluster with the full automatic list, free clusters (SVD branch; saddle search and minimisation).
+    Both sides integrate the geodesic with scipy's LSODA, so every step agrees to round-off amplification."""
+    from oracle.internal_pes import InternalPES
+    from oracle.driver import SaddleSearch
+    G = golden("internal_loop")
+    assert int(G["ncases"]) == 7
+    pos0, cs, csc, func, kw = _internal_case(G, case)
+    pes_kw = {k: kw.pop(k) for k in ("exact_geodesic", "iterative_stepper") if k in kw}
+    p = InternalPES(func, pos0.ravel(), cs, csc, integrator="lsoda", **pes_kw)
+    o = SaddleSearch(p, rs="mis", diag_maxiter=6, **kw)
+    X, D, R, F = G["x%d" % case], G["delta%d" % case], G["rho%d" % case], G["f%d" % case]
+    for t in range(len(X)):
+        o.step()
+        msg = "case %d (%s) step %d" % (case, G["meta%d" % case], t)
+        np.testing.assert_allclose(p.pos, X[t], rtol=0, atol=2e-8, err_msg=msg)
+        np.testing.assert_allclose(o.delta, D[t], rtol=1e-8, err_msg=msg)
+        np.testing.assert_allclose(o.rho, R[t], rtol=1e-6, atol=1e-8, err_msg=msg)
+        np.testing.assert_allclose(p.curr["f"], F[t], rtol=0, atol=2e-8, err_msg=msg)
+    H = G["H%d" % case]
+    np.testing.assert_allclose(p.H.B, H, rtol=0, atol=1e-6 * max(1.0, np.abs(H).max()))
+    assert p.neval == int(G["neval%d" % case])
