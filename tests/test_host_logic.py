@@ -286,3 +286,50 @@ def test_xyz_trajectory_writer(tmp_path):
     assert _open_trajectory(t2, at, False, None) is t2
     with pytest.raises(TypeError):
         _open_trajectory(3.5, at, False, None)
+
+
+def test_topology_finders_on_small_molecules():
+    """find_all_angles / find_all_dihedrals (internal.py:3457-3671) on hand-made geometries."""
+    from sella_b200.topology import Internals
+
+    class Mol:
+        def __init__(self, pos, numbers):
+            self.positions = np.array(pos, float)
+            self.numbers = np.array(numbers)
+            self.cell, self.pbc = None, np.array([False] * 3)
+
+        def __len__(self):
+            return len(self.positions)
+
+    def full(mol):
+        im = Internals(mol)
+        im.find_all_bonds(); im.find_all_angles(); im.find_all_dihedrals()
+        return im
+    # planar star (NO3-like): 3 bonds, 3 angles, no proper dihedral through the centre -> ONE improper (n0, c, n1, n2)
+    r = 1.25
+    star = Mol([[0, 0, 0]] + [[r * np.cos(a), r * np.sin(a), 0] for a in (0, 2 * np.pi / 3, 4 * np.pi / 3)], [7, 8, 8, 8])
+    im = full(star)
+    assert (im.nbonds, im.nangles, im.ndihedrals) == (3, 3, 1)
+    assert im.internals["dihedrals"][0].indices[1] == 0
+    # butane-like zig-zag chain: 3 bonds, 2 angles, 1 proper dihedral; no improper (the centres carry a proper one)
+    chain = Mol([[0, 0, 0], [1.5, 0, 0], [2.1, 1.4, 0], [3.6, 1.5, 0.4]], [6, 6, 6, 6])
+    ic = full(chain)
+    assert (ic.nbonds, ic.nangles, ic.ndihedrals) == (3, 2, 1)
+    assert ic.internals["dihedrals"][0].indices in ((0, 1, 2, 3), (3, 2, 1, 0))
+    np.testing.assert_allclose(np.diag(ic.guess_hessian()) > 0, True)
+    # a near-linear angle at a centre with a third neighbour is replaced by an improper dihedral (:3546-3573) ...
+    tee = Mol([[0, 0, 0], [1.5, 0, 0], [-1.5, 0.02, 0], [0, 1.5, 0]], [6, 6, 6, 6])
+    it = Internals(tee)
+    it.find_all_bonds(); it.find_all_angles()
+    assert it.nangles == 2 and it.ndihedrals == 1 and len(it.forbidden["angles"]) == 1
+    # ... and at a centre with only two neighbours it needs a dummy atom, which the CUDA path does not have
+    co2 = Mol([[0, 0, 0], [1.16, 0, 0], [-1.16, 0, 0]], [6, 8, 8])
+    i2 = Internals(co2)
+    i2.find_all_bonds()
+    with pytest.raises(NotImplementedError):
+        i2.find_all_angles()
+    # disconnected fragments are joined by growing the covalent scale factor (:3392-3418)
+    dimer = Mol([[0, 0, 0], [0.96, 0, 0], [4.0, 0, 0], [4.96, 0, 0]], [8, 1, 8, 1])
+    idm = Internals(dimer)
+    idm.find_all_bonds()
+    assert idm.nbonds >= 3
