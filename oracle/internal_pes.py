@@ -28,7 +28,7 @@ Dormand-Prince 5(4) scheme with per-system step control that the CUDA engine run
 step; tests/test_internal_pes.py checks that both integrators lead to the same converged geometry.
 
 PINNED against the reference's own ``InternalPES`` / ``MaxInternalStep`` / ``Sella.step`` code as far as this
-image allows: ``tests/golden/internal_loop.npz`` holds seven trajectories produced by the UNMODIFIED reference
+image allows: ``tests/golden/internal_loop.npz`` holds eight trajectories produced by the UNMODIFIED reference
 files driven through ``oracle/ref_internal_harness.py`` (slabs with held atoms: prfo, qn, frozen B+, Newton
 stepper; a cluster with bonds + angles + dihedrals; free clusters through the SVD branch, saddle search and
 minimisation), and ``tests/test_oracle_golden.py::test_internal_pes_oracle_matches_reference_internal_pes``

@@ -365,7 +365,8 @@ def golden_internal_loop(ref):
     oracle/ref_internal_harness.py: coordinate values and derivatives come from oracle.intcoords (JAX is absent),
     every line of the internal-coordinate search itself is the reference's."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from test_internal_pes import slab_problem, cluster_problem, molecule_problem, oracle_sets
+    from test_internal_pes import (slab_problem, cluster_problem, molecule_problem, constrained_molecule_problem,
+                                   oracle_sets)
     from oracle.ref_internal_harness import make_reference_internal_sella
     cases = [("slab", slab_problem(40), dict(method="prfo"), 8),
              ("slab", slab_problem(41), dict(method="qn"), 8),
@@ -373,7 +374,8 @@ def golden_internal_loop(ref):
              ("slab", slab_problem(43), dict(method="prfo", iterative_stepper=1), 8),
              ("cluster", cluster_problem(31), dict(method="prfo"), 6),
              ("free", molecule_problem(0), dict(method="prfo"), 6),
-             ("free", molecule_problem(1), dict(order=0), 10)]
+             ("free", molecule_problem(1), dict(order=0), 10),
+             ("free+bond+angle", constrained_molecule_problem(), dict(method="prfo"), 6)]
     out = {}
     for i, (kind, (at, cons, ints), kw, nsteps) in enumerate(cases):
         cs, csc, rows = oracle_sets(ints)

@@ -89,12 +89,47 @@ def molecule_problem(variant=0, natoms=8):
     return at, cons, ints
 
 
+def constrained_molecule_problem(variant=0):
+    """A free Cu cluster with one bond and one angle held (fix_bond / fix_angle): the constraint rows are ordinary
+    internal coordinates with non-zero second derivatives (the D_cons term of peswrapper.py:1011-1031)."""
+    pos = fcc_cluster(8, seed=77, rattle=0.08)
+    at = _Atoms(pos, None, (False,) * 3, oemt.emt_func(None, (False,) * 3))
+    cons = Constraints(at)
+    cons.fix_bond((0, 1))
+    cons.fix_angle((1, 0, 2))
+    ints = Internals(at, cons=cons)
+    ints.find_all_bonds()
+    ints.find_all_angles()
+    ints.find_all_dihedrals()
+    if variant:
+        at.positions += 0.02 * np.random.RandomState(3000 + variant).normal(size=at.positions.shape)
+    return at, cons, ints
+
+
 def oracle_sets(ints):
     tr, b, a, d, tv = ints.lists()
     cs = CoordinateSet(ints.natoms, tr, b, a, d, tvecs=tv, numbers=ints.atoms.numbers)
     rows, tg = ints.constraint_rows()
-    csc = CoordinateSet(ints.natoms, [tr[r] for r in rows]) if len(rows) else None
+    csc = subset(ints.natoms, (tr, b, a, d, tv), rows) if len(rows) else None
     return cs, csc, rows
+
+
+def subset(natoms, lists, rows):
+    """The coordinates `rows` (positions in the full list, kind by kind in the reference's order) as their own set."""
+    tr, b, a, d, tv = lists
+    sel = dict(translations=[], bonds=[], angles=[], dihedrals=[])
+    tvs = dict(bonds=[], angles=[], dihedrals=[])
+    off = [0, len(tr), len(tr) + len(b), len(tr) + len(b) + len(a)]
+    for r in rows:
+        if r < off[1]:
+            sel["translations"].append(tr[r])
+        else:
+            kind, lst, o = (("bonds", b, off[1]) if r < off[2] else ("angles", a, off[2]) if r < off[3]
+                            else ("dihedrals", d, off[3]))
+            sel[kind].append(lst[r - o])
+            tvs[kind].append(tv[kind][r - o])
+    return CoordinateSet(natoms, sel["translations"], sel["bonds"], sel["angles"], sel["dihedrals"],
+                         tvecs={k: (np.array(v) if len(v) else None) for k, v in tvs.items()})
 
 
 def test_exact_coordinate_derivatives_match_the_finite_difference_oracle():

@@ -326,25 +326,27 @@ def _internal_case(G, i):
     pbc = tuple(bool(p) for p in G["pbc%d" % i])
     tv = {k: G["tv_%s%d" % (k, i)] for k in ("bonds", "angles", "dihedrals")}
     tr = [tuple(t) for t in G["trans%d" % i]]
-    cs = CoordinateSet(len(pos0), tr, G["bonds%d" % i], G["angles%d" % i], G["diheds%d" % i], tvecs=tv,
-                       numbers=G["numbers%d" % i])
+    lists = (tr, G["bonds%d" % i], G["angles%d" % i], G["diheds%d" % i], tv)
+    cs = CoordinateSet(len(pos0), *lists[:4], tvecs=tv, numbers=G["numbers%d" % i])
     rows = G["rows%d" % i]
-    csc = CoordinateSet(len(pos0), [tr[r] for r in rows]) if len(rows) else None
+    from test_internal_pes import subset
+    csc = subset(len(pos0), lists, rows) if len(rows) else None
     kw = dict(ast.literal_eval(str(G["meta%d" % i][1])))
     return pos0, cs, csc, oemt.emt_func(cell, pbc), kw
 
 
-@pytest.mark.parametrize("case", range(7))
+@pytest.mark.parametrize("case", range(8))
 def test_internal_pes_oracle_matches_reference_internal_pes(golden, case):
     """oracle/internal_pes.py + oracle/driver.py against the trajectory of the reference's OWN InternalPES,
     MaxInternalStep and Sella.step (tests/golden/internal_loop.npz, produced by make_golden.py through
     oracle/ref_internal_harness.py): slabs in bond coordinates with held atoms (prfo, qn, frozen B+, Newton
-    stepper), a cluster with the full automatic list, free clusters (SVD branch; saddle search and minimisation).
+    stepper), a cluster with the full automatic list, free clusters (SVD branch; saddle search, minimisation, and with a bond
+    and an angle held -- constraint rows with non-zero second derivatives).
     Both sides integrate the geodesic with scipy's LSODA, so every step agrees to round-off amplification."""
     from oracle.internal_pes import InternalPES
     from oracle.driver import SaddleSearch
     G = golden("internal_loop")
-    assert int(G["ncases"]) == 7
+    assert int(G["ncases"]) == 8
     pos0, cs, csc, func, kw = _internal_case(G, case)
     pes_kw = {k: kw.pop(k) for k in ("exact_geodesic", "iterative_stepper") if k in kw}
     p = InternalPES(func, pos0.ravel(), cs, csc, integrator="lsoda", **pes_kw)
